@@ -1,0 +1,118 @@
+/*
+ * lgu_corr.h -- C ABI of the B200-native LGU-SLAM correlation hot path.
+ *
+ * Every entry point takes raw DEVICE pointers, plain integer sizes and a CUDA
+ * stream (passed as void* so that this header needs no CUDA include); nothing
+ * in the signatures depends on torch.  All tensors are contiguous, fp32 unless
+ * stated otherwise.  Return value: 0 on success, one of LGU_ERR_* otherwise;
+ * lgu_last_error_string() describes the most recent failure on the calling
+ * thread.  Kernels are launched asynchronously on `stream`; nothing is
+ * allocated, retained or synchronised by the library (workspace, if any, is
+ * supplied by the caller).
+ *
+ * Each function replaces one operator of the reference's torch extension
+ * `defCorrSample` (binding: /root/reference/offersample_LGS/droid.cpp:138-147);
+ * the reference interface it replaces is cited per function.  Index / bounds
+ * logic is bit-exact with the reference kernels, including their quirks
+ * (x-major taps, top-left-corner gating, in-place zeroing of the centre
+ * offset tap).
+ *
+ * Layout vocabulary:  E = edges (frame pairs), (H1,W1) = source grid,
+ * (H2,W2) = target grid of this pyramid level, r = lookup radius, rd = 2r+1.
+ *   volume   [E,H1,W1,H2,W2]      one private H2xW2 slice per source pixel
+ *   coords   [E,2,H1,W1]          channel 0 = x, channel 1 = y (level units)
+ *   offset   [E,H1,W1,rd,rd,2]    [..,i,j,0] = x-offset of tap (i: x, j: y)
+ *   corr     [E,rd,rd,H1,W1]      tap-major output, i (x tap) outermost
+ */
+#ifndef LGU_CORR_H_
+#define LGU_CORR_H_
+
+#include <stdint.h>
+
+#if defined(LGU_BUILDING) && defined(__GNUC__)
+#define LGU_API __attribute__((visibility("default")))
+#else
+#define LGU_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGU_OK 0
+#define LGU_ERR_BAD_ARG 1      /* null pointer, non-positive size, unsupported radius/shape */
+#define LGU_ERR_LAUNCH 2       /* cudaGetLastError() after a launch was not cudaSuccess */
+#define LGU_ERR_UNSUPPORTED 3  /* valid arguments the sm_100a build does not implement */
+
+/* Library / build identification. */
+LGU_API int lgu_abi_version(void);                 /* bumped on any signature change */
+LGU_API const char* lgu_build_info(void);          /* "sm_100a, nvcc x.y, <date>" */
+LGU_API const char* lgu_last_error_string(void);   /* thread-local, never NULL */
+
+/* --------------------------------------------------------------------------
+ * corr_index_forward          (reference: offersample_LGS/droid.cpp:79-87,
+ *                              corrSample_kernel.cu:24-82,139-168)
+ * Plain bilinear lookup of a (2r+1)^2 window around coords.  corr is fully
+ * written (taps whose top-left corner is out of bounds are 0).
+ * ------------------------------------------------------------------------ */
+LGU_API int lgu_corr_index_forward(const float* volume, const float* coords, float* corr,
+                           int E, int H1, int W1, int H2, int W2, int radius, void* stream);
+
+/* corr_index_backward         (droid.cpp:89-99, corrSample_kernel.cu:84-136,170-199)
+ * volume_grad [E,H1,W1,H2,W2] is fully written (dense: zeros + scattered taps). */
+LGU_API int lgu_corr_index_backward(const float* coords, const float* corr_grad, float* volume_grad,
+                            int E, int H1, int W1, int H2, int W2, int radius, void* stream);
+
+/* --------------------------------------------------------------------------
+ * defCorr_index_forward       (droid.cpp:53-63, defCorrSample_kernel.cu:25-91,165-196)
+ * Deformable lookup: tap (i,j) samples at coords + offset[..,i,j,:] - r + (i,j).
+ * SIDE EFFECT (reference quirk Q5): offset[..,r,r,0:2] is set to 0 in place.
+ * ------------------------------------------------------------------------ */
+LGU_API int lgu_defcorr_index_forward(const float* volume, const float* coords, float* offset, float* corr,
+                              int E, int H1, int W1, int H2, int W2, int radius, void* stream);
+
+/* defCorr_index_backward      (droid.cpp:65-77, defCorrSample_kernel.cu:93-162,198-231)
+ * volume_grad dense, offset_grad [E,H1,W1,rd,rd,2] ([..,0] = d/dx, [..,1] = d/dy; 0 for
+ * gated taps).  Same in-place zeroing of the centre offset tap. */
+LGU_API int lgu_defcorr_index_backward(const float* volume, const float* coords, float* offset,
+                               const float* corr_grad, float* volume_grad, float* offset_grad,
+                               int E, int H1, int W1, int H2, int W2, int radius, void* stream);
+
+/* --------------------------------------------------------------------------
+ * gaussianMask                (droid.cpp:100-110, gaussianAttn.cu:19-68,134-163)
+ * means, covs [E,H1,W1,2] (channel 0 = x, 1 = y).  volume1 is dense: 3*V*exp(-0.5*d'S^-1 d)
+ * inside the (2r+1)^2 window centred on floor(mean), 0 elsewhere.
+ * ------------------------------------------------------------------------ */
+LGU_API int lgu_gaussian_mask_forward(const float* means, const float* covs, const float* volume, float* volume1,
+                              int E, int H1, int W1, int H2, int W2, int radius, void* stream);
+
+/* gaussianMask_backward       (droid.cpp:112-123, gaussianAttn.cu:72-131,165-200)
+ * means_grad, covs_grad [E,H1,W1,2]; the reference produces no gradient for volume. */
+LGU_API int lgu_gaussian_mask_backward(const float* means, const float* covs, const float* volume,
+                               const float* volume1_grad, float* means_grad, float* covs_grad,
+                               int E, int H1, int W1, int H2, int W2, int radius, void* stream);
+
+/* --------------------------------------------------------------------------
+ * lowMem_defSample            (droid.cpp:124-136, lowMem_defSample.cu:27-134,137-168)
+ * On-the-fly deformable correlation, no volume.  fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C]
+ * channels-last, C a multiple of 32; coords [B,N,H1,W1,2] (last dim x,y);
+ * offset [n_slabs,H1,W1,rd,rd,2]; corr [B,N,rd,rd,H1,W1] indexed [ix][iy].
+ * strict_ref = 1 reproduces the reference's slab indexing offset[b*n] (quirk Q2; with the
+ * only caller's N = 1 every edge reads slab 0); strict_ref = 0 uses offset[b*N+n].
+ * SIDE EFFECT: the centre tap of every slab that is read is zeroed in place.
+ * ------------------------------------------------------------------------ */
+LGU_API int lgu_lowmem_defsample_forward(const float* fmap1, const float* fmap2, const float* coords,
+                                 float* offset, float* corr,
+                                 int B, int N, int H1, int W1, int H2, int W2, int C, int radius,
+                                 int strict_ref, void* stream);
+
+/* altcorr_forward             (src/droid.cpp:193-203, src/altcorr_kernel.cu:27-149,290-319)
+ * The second boundary the backend path crosses (droid_slam/modules/corr.py:202).
+ * corr [B,N,rd*rd,H1,W1], channel = iy + rd*ix. */
+LGU_API int lgu_altcorr_forward(const float* fmap1, const float* fmap2, const float* coords, float* corr,
+                        int B, int N, int H1, int W1, int H2, int W2, int C, int radius, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGU_CORR_H_ */

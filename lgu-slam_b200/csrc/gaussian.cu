@@ -1,0 +1,155 @@
+// gaussian.cu -- gaussianMask forward / backward (stand-alone drop-in variants) for sm_100a.
+//
+// Replaces /root/reference/offersample_LGS/gaussianAttn.cu:19-68,134-163 (forward: dense
+// zeros_like + 81 scattered 4-byte writes per pixel) and :72-131,165-200 (backward: 81x2
+// scalar gathers per thread, accumulators RMW'd in global memory).
+//
+// Forward is bound by its dense output (4*H2*W2 B per source pixel): ONE WARP PER PIXEL streams
+// the pixel's whole H2xW2 slice with 16-byte stores; only the chunks that intersect the
+// (2r+1)^2 window read the volume and evaluate the Gaussian, everything else is a zero store.
+// Backward: lane t owns window tap t, four partial sums are warp-reduced with shuffles.
+// Arithmetic follows the reference's SASS: IEEE divides, s = fma(t2, dy, t1*dx), f = -0.5*s,
+// full-precision expf, ((V*3)*e); fp64 only for the covariance-gradient factor (:120,122).
+#include "common.cuh"
+
+namespace lgu {
+
+constexpr int kGaWarps = 8;
+
+__device__ __forceinline__ float gauss_weight(int x1, int y1, float mx, float my, float c1, float c2) {
+  const float ddx = __fsub_rn((float)x1, mx), ddy = __fsub_rn((float)y1, my);
+  const float t1 = __fdiv_rn(ddx, c1), t2 = __fdiv_rn(ddy, c2);
+  const float s = __fmaf_rn(ddy, t2, __fmul_rn(t1, ddx));
+  return expf(__fmul_rn(s, -0.5f));
+}
+
+__global__ void __launch_bounds__(kGaWarps * 32)
+gaussian_fwd_kernel(const float* __restrict__ means, const float* __restrict__ covs,
+                    const float* __restrict__ volume, float* __restrict__ out, long long npix, int H2, int W2,
+                    int r) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int Q = H2 * W2;
+  const unsigned rd = 2u * (unsigned)r + 1u;
+  for (long long pix = wid; pix < npix; pix += nwarps) {
+    const float2 m = __ldg(reinterpret_cast<const float2*>(means) + pix);
+    const float2 c = __ldg(reinterpret_cast<const float2*>(covs) + pix);
+    const int cx = floor_to_int(m.x), cy = floor_to_int(m.y);
+    // window membership with the reference's wrapping arithmetic: x1 == cx - r + i for some 0 <= i < rd
+    const unsigned bx = (unsigned)cx - (unsigned)r, by = (unsigned)cy - (unsigned)r;
+    const float* V = volume + (size_t)pix * Q;
+    float* O = out + (size_t)pix * Q;
+    if ((W2 & 3) == 0 && ((reinterpret_cast<uintptr_t>(O) | reinterpret_cast<uintptr_t>(V)) & 15) == 0) {
+      const int W4 = W2 >> 2;
+      for (int q4 = lane; q4 < (Q >> 2); q4 += 32) {
+        const int y1 = q4 / W4, x1 = (q4 - y1 * W4) << 2;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const bool row_in = ((unsigned)y1 - by) < rd;
+        // any of x1..x1+3 inside [bx, bx+rd) (mod 2^32)?
+        const bool col_in = (((unsigned)x1 - bx) < rd) || (((unsigned)(x1 + 3) - bx) < rd) ||
+                            ((bx - (unsigned)x1) < 4u);
+        if (row_in && col_in) {
+          const float4 in = __ldg(reinterpret_cast<const float4*>(V) + q4);
+          if (((unsigned)(x1 + 0) - bx) < rd) v.x = __fmul_rn(__fmul_rn(in.x, 3.0f), gauss_weight(x1 + 0, y1, m.x, m.y, c.x, c.y));
+          if (((unsigned)(x1 + 1) - bx) < rd) v.y = __fmul_rn(__fmul_rn(in.y, 3.0f), gauss_weight(x1 + 1, y1, m.x, m.y, c.x, c.y));
+          if (((unsigned)(x1 + 2) - bx) < rd) v.z = __fmul_rn(__fmul_rn(in.z, 3.0f), gauss_weight(x1 + 2, y1, m.x, m.y, c.x, c.y));
+          if (((unsigned)(x1 + 3) - bx) < rd) v.w = __fmul_rn(__fmul_rn(in.w, 3.0f), gauss_weight(x1 + 3, y1, m.x, m.y, c.x, c.y));
+        }
+        __stcs(reinterpret_cast<float4*>(O) + q4, v);
+      }
+    } else {
+      for (int q = lane; q < Q; q += 32) {
+        const int y1 = q / W2, x1 = q - y1 * W2;
+        float v = 0.0f;
+        if (((unsigned)y1 - by) < rd && ((unsigned)x1 - bx) < rd)
+          v = __fmul_rn(__fmul_rn(__ldg(V + q), 3.0f), gauss_weight(x1, y1, m.x, m.y, c.x, c.y));
+        __stcs(O + q, v);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGaWarps * 32)
+gaussian_bwd_kernel(const float* __restrict__ means, const float* __restrict__ covs,
+                    const float* __restrict__ volume, const float* __restrict__ out_grad,
+                    float* __restrict__ means_grad, float* __restrict__ covs_grad, long long npix, int H2, int W2,
+                    int r) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int Q = H2 * W2;
+  const int rd = 2 * r + 1, taps = rd * rd;
+  for (long long pix = wid; pix < npix; pix += nwarps) {
+    const float2 m = __ldg(reinterpret_cast<const float2*>(means) + pix);
+    const float2 c = __ldg(reinterpret_cast<const float2*>(covs) + pix);
+    const int cx = floor_to_int(m.x), cy = floor_to_int(m.y);
+    const float* V = volume + (size_t)pix * Q;
+    const float* G = out_grad + (size_t)pix * Q;
+    float gm0 = 0.0f, gm1 = 0.0f, gc0 = 0.0f, gc1 = 0.0f;
+    // lanes sweep the window row-major in memory (y outer, x inner) so a warp instruction
+    // touches ~3.5 consecutive 36-byte row segments.
+    for (int t = lane; t < taps; t += 32) {
+      const int j = t / rd, i = t - j * rd;          // j: y tap, i: x tap
+      const int x1 = tap_coord(cx, r, i), y1 = tap_coord(cy, r, j);
+      if (in_bounds(y1, x1, H2, W2)) {
+        const float ddx = __fsub_rn((float)x1, m.x), ddy = __fsub_rn((float)y1, m.y);
+        const float t1 = __fdiv_rn(ddx, c.x), t2 = __fdiv_rn(ddy, c.y);
+        const float s = __fmaf_rn(ddy, t2, __fmul_rn(t1, ddx));
+        const float e = expf(__fmul_rn(s, -0.5f));
+        const int q = y1 * W2 + x1;
+        const float v3 = __fmul_rn(__ldg(V + q), 3.0f), g = __ldg(G + q);
+        gm0 = __fmaf_rn(__fmul_rn(v3, __fdiv_rn(__fmul_rn(ddx, e), c.x)), g, gm0);   // gaussianAttn.cu:117
+        gm1 = __fmaf_rn(__fmul_rn(v3, __fdiv_rn(__fmul_rn(ddy, e), c.y)), g, gm1);   // :118
+        const double eh = (double)e * 0.5;                                           // :120,122 (fp64)
+        const float dE1 = (float)(((eh * (double)ddx) * (double)ddx) / (double)__fmul_rn(c.x, c.x));
+        const float dE2 = (float)(((eh * (double)ddy) * (double)ddy) / (double)__fmul_rn(c.y, c.y));
+        gc0 = __fmaf_rn(__fmul_rn(dE1, v3), g, gc0);                                 // :125
+        gc1 = __fmaf_rn(__fmul_rn(dE2, v3), g, gc1);                                 // :126
+      }
+    }
+    gm0 = warp_sum(gm0); gm1 = warp_sum(gm1); gc0 = warp_sum(gc0); gc1 = warp_sum(gc1);
+    if (lane == 0) {
+      reinterpret_cast<float2*>(means_grad)[pix] = make_float2(gm0, gm1);
+      reinterpret_cast<float2*>(covs_grad)[pix] = make_float2(gc0, gc1);
+    }
+  }
+}
+
+static inline unsigned grid_for_warps(long long nwarps_needed, int warps_per_cta, int ctas_per_sm) {
+  long long want = (nwarps_needed + warps_per_cta - 1) / warps_per_cta;
+  long long cap = (long long)kNumSMs * ctas_per_sm;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace lgu
+
+extern "C" int lgu_gaussian_mask_forward(const float* means, const float* covs, const float* volume, float* volume1,
+                                         int E, int H1, int W1, int H2, int W2, int radius, void* stream) {
+  LGU_REQUIRE(means && covs && volume && volume1, "lgu_gaussian_mask_forward: null pointer");
+  LGU_REQUIRE(E >= 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && radius >= 0,
+              "lgu_gaussian_mask_forward: bad sizes E=%d H1=%d W1=%d H2=%d W2=%d r=%d", E, H1, W1, H2, W2, radius);
+  LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_gaussian_mask_forward: H2*W2 too large");
+  if (E == 0) return LGU_OK;
+  const long long npix = (long long)E * H1 * W1;
+  const unsigned grid = lgu::grid_for_warps(npix, lgu::kGaWarps, 8);
+  lgu::gaussian_fwd_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(means, covs, volume, volume1, npix,
+                                                                                 H2, W2, radius);
+  return lgu::check_launch("lgu_gaussian_mask_forward");
+}
+
+extern "C" int lgu_gaussian_mask_backward(const float* means, const float* covs, const float* volume,
+                                          const float* volume1_grad, float* means_grad, float* covs_grad, int E,
+                                          int H1, int W1, int H2, int W2, int radius, void* stream) {
+  LGU_REQUIRE(means && covs && volume && volume1_grad && means_grad && covs_grad,
+              "lgu_gaussian_mask_backward: null pointer");
+  LGU_REQUIRE(E >= 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && radius >= 0,
+              "lgu_gaussian_mask_backward: bad sizes E=%d H1=%d W1=%d H2=%d W2=%d r=%d", E, H1, W1, H2, W2, radius);
+  LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_gaussian_mask_backward: H2*W2 too large");
+  if (E == 0) return LGU_OK;
+  const long long npix = (long long)E * H1 * W1;
+  const unsigned grid = lgu::grid_for_warps(npix, lgu::kGaWarps, 8);
+  lgu::gaussian_bwd_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
+      means, covs, volume, volume1_grad, means_grad, covs_grad, npix, H2, W2, radius);
+  return lgu::check_launch("lgu_gaussian_mask_backward");
+}

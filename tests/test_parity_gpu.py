@@ -1,0 +1,179 @@
+"""GPU parity tests: the sm_100a kernels (called through the C ABI via the operator layer) against the
+CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): index / bounds / gating logic bit-exact (identical zero and NaN patterns,
+identical in-place offset mutation); fp32 values within 1e-5 abs.  The forward lookups are expected to be
+bit-identical (same operation order as the reference's SASS), which is asserted as well."""
+import pytest
+import torch
+
+import inputs
+
+pytestmark = pytest.mark.gpu
+ATOL = 1e-5
+
+
+def cu(t):
+    return t.cuda().contiguous()
+
+
+def same_pattern(a, b):
+    return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(a == 0, b == 0)
+
+
+CASES = [
+    # E, H1, W1, H2, W2, r, probes
+    (2, 6, 8, 6, 8, 3, True),
+    (1, 48, 64, 48, 64, 3, True),      # BASELINE level-0 shape
+    (2, 48, 64, 24, 32, 3, False),     # level 1
+    (3, 48, 64, 12, 16, 3, True),      # level 2
+    (3, 48, 64, 6, 8, 3, False),       # level 3
+    (2, 48, 64, 24, 32, 1, True),      # the r=1 mask lookup
+    (1, 5, 7, 9, 11, 2, True),         # ragged: P not a multiple of 32, odd W2
+    (1, 3, 3, 4, 5, 4, True),
+    (1, 4, 4, 6, 6, 5, False),         # generic-radius path
+    (1, 2, 3, 7, 5, 0, False),         # r = 0
+]
+
+
+@pytest.mark.parametrize("E,H1,W1,H2,W2,r,probes", CASES)
+def test_corr_index_forward(ops, oracle, E, H1, W1, H2, W2, r, probes):
+    c = inputs.volume_case(E, H1, W1, H2, W2, r, seed=100 + r, probes=probes)
+    want, = oracle.corr_index_forward(c["volume"], c["coords"], r)
+    got, = ops.corr_index_forward(cu(c["volume"]), cu(c["coords"]), r)
+    got = got.cpu()
+    assert same_pattern(got, want)
+    assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want)), "forward lookup must be bit-exact"
+
+
+@pytest.mark.parametrize("E,H1,W1,H2,W2,r,probes", CASES)
+@pytest.mark.parametrize("zero_offset", [False, True])
+def test_defcorr_index_forward(ops, oracle, E, H1, W1, H2, W2, r, probes, zero_offset):
+    c = inputs.volume_case(E, H1, W1, H2, W2, r, seed=200 + r, probes=probes, zero_offset=zero_offset)
+    off_cpu = c["offset"].clone()
+    want, = oracle.defCorr_index_forward(c["volume"], c["coords"], off_cpu, r)
+    off_gpu = cu(c["offset"])
+    got, = ops.defCorr_index_forward(cu(c["volume"]), cu(c["coords"]), off_gpu, r)
+    got = got.cpu()
+    assert same_pattern(got, want)
+    assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want)), "forward lookup must be bit-exact"
+    assert torch.equal(off_gpu.cpu(), off_cpu), "in-place centre-tap zeroing (Q5) must match"
+
+
+@pytest.mark.parametrize("E,H1,W1,H2,W2,r,probes", CASES)
+def test_corr_index_backward(ops, oracle, E, H1, W1, H2, W2, r, probes):
+    c = inputs.volume_case(E, H1, W1, H2, W2, r, seed=300 + r, probes=probes)
+    want, = oracle.corr_index_backward(c["volume"], c["coords"], c["corr_grad"], r)
+    got, = ops.corr_index_backward(cu(c["volume"]), cu(c["coords"]), cu(c["corr_grad"]), r)
+    got = got.cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.allclose(got, want, atol=ATOL, rtol=0, equal_nan=True), (got - want).abs().nan_to_num().max()
+
+
+@pytest.mark.parametrize("E,H1,W1,H2,W2,r,probes", CASES)
+def test_defcorr_index_backward(ops, oracle, E, H1, W1, H2, W2, r, probes):
+    c = inputs.volume_case(E, H1, W1, H2, W2, r, seed=400 + r, probes=probes)
+    off_cpu = c["offset"].clone()
+    wv, wo = oracle.defCorr_index_backward(c["volume"], c["coords"], off_cpu, c["corr_grad"], r)
+    off_gpu = cu(c["offset"])
+    gv, go = ops.defCorr_index_backward(cu(c["volume"]), cu(c["coords"]), off_gpu, cu(c["corr_grad"]), r)
+    gv, go = gv.cpu(), go.cpu()
+    assert torch.equal(torch.isnan(gv), torch.isnan(wv))
+    assert torch.allclose(gv, wv, atol=ATOL, rtol=0, equal_nan=True), (gv - wv).abs().nan_to_num().max()
+    assert same_pattern(go, wo), "gated taps must have exactly-zero offset gradients"
+    assert torch.equal(torch.nan_to_num(go), torch.nan_to_num(wo)), "offset_grad follows the reference's op order"
+    assert torch.equal(off_gpu.cpu(), off_cpu)
+
+
+GAUSS = [(2, 6, 8, 6, 8, 4, True), (1, 48, 64, 48, 64, 4, True), (2, 5, 7, 9, 11, 4, True),
+         (1, 4, 4, 10, 12, 2, False), (1, 3, 3, 6, 7, 1, True), (1, 3, 3, 6, 8, 0, False)]
+
+
+@pytest.mark.parametrize("E,H1,W1,H2,W2,r,probes", GAUSS)
+def test_gaussian_mask_forward(ops, oracle, E, H1, W1, H2, W2, r, probes):
+    c = inputs.gaussian_case(E, H1, W1, H2, W2, r, seed=500 + r, probes=probes)
+    want, = oracle.gaussianMask(c["means"], c["covs"], c["volume"], r)
+    got, = ops.gaussianMask(cu(c["means"]), cu(c["covs"]), cu(c["volume"]), r)
+    got = got.cpu()
+    assert torch.equal(got == 0, want == 0), "window placement / bounds logic must be bit-exact"
+    # values: CUDA expf vs glibc expf differ by <= 2 ulp
+    assert torch.allclose(got, want, atol=ATOL, rtol=1e-6)
+
+
+@pytest.mark.parametrize("E,H1,W1,H2,W2,r,probes", GAUSS)
+def test_gaussian_mask_backward(ops, oracle, E, H1, W1, H2, W2, r, probes):
+    c = inputs.gaussian_case(E, H1, W1, H2, W2, r, seed=600 + r, probes=probes)
+    wm, wc = oracle.gaussianMask_backward(c["means"], c["covs"], c["volume"], c["out_grad"], r)
+    gm, gc = ops.gaussianMask_backward(cu(c["means"]), cu(c["covs"]), cu(c["volume"]), cu(c["out_grad"]), r)
+    # sums of <= 81 terms, reduced in a different (tree) order; covs down to 0.05 amplify terms by 1/cov^2
+    assert torch.allclose(gm.cpu(), wm, atol=ATOL, rtol=1e-5), (gm.cpu() - wm).abs().max()
+    assert torch.allclose(gc.cpu(), wc, atol=ATOL, rtol=1e-5), (gc.cpu() - wc).abs().max()
+
+
+LOWMEM = [(3, 1, 6, 8, 6, 8, 128, 3, True), (2, 1, 48, 64, 48, 64, 128, 3, True), (2, 1, 48, 64, 24, 32, 128, 3, False),
+          (2, 2, 5, 7, 4, 6, 64, 2, True), (2, 1, 5, 7, 6, 4, 32, 1, False), (1, 1, 4, 4, 5, 5, 256, 3, False)]
+
+
+@pytest.mark.parametrize("B,N,H1,W1,H2,W2,C,r,probes", LOWMEM)
+@pytest.mark.parametrize("strict", [True, False])
+def test_lowmem_defsample(ops, oracle, B, N, H1, W1, H2, W2, C, r, probes, strict):
+    c = inputs.lowmem_case(B, N, H1, W1, H2, W2, C, r, seed=700 + r, probes=probes)
+    off_cpu = c["offset"].clone()
+    want, = oracle.lowMem_defSample(c["fmap1"], c["fmap2"], c["coords"], off_cpu, r, strict_ref=strict)
+    off_gpu = cu(c["offset"])
+    got, = ops.lowMem_defSample(cu(c["fmap1"]), cu(c["fmap2"]), cu(c["coords"]), off_gpu, r, strict_ref=strict)
+    got = got.cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.allclose(got, want, atol=ATOL, rtol=0, equal_nan=True), (got - want).abs().nan_to_num().max()
+    assert torch.equal(off_gpu.cpu(), off_cpu)
+
+
+@pytest.mark.parametrize("B,N,H1,W1,H2,W2,C,r,probes", LOWMEM)
+def test_altcorr_forward(ops, oracle, B, N, H1, W1, H2, W2, C, r, probes):
+    c = inputs.lowmem_case(B, N, H1, W1, H2, W2, C, r, seed=800 + r, probes=probes)
+    want, = oracle.altcorr_forward(c["fmap1"], c["fmap2"], c["coords"], r)
+    got, = ops.altcorr_forward(cu(c["fmap1"]), cu(c["fmap2"]), cu(c["coords"]), r)
+    got = got.cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.allclose(got, want, atol=ATOL, rtol=0, equal_nan=True), (got - want).abs().nan_to_num().max()
+
+
+def test_empty_edge_set(ops):
+    v = torch.zeros(0, 4, 4, 4, 4, device="cuda")
+    c = torch.zeros(0, 2, 4, 4, device="cuda")
+    out, = ops.corr_index_forward(v, c, 1)
+    assert out.shape == (0, 3, 3, 4, 4)
+
+
+def test_noncontiguous_is_rejected_like_the_reference(ops):
+    v = torch.zeros(1, 4, 4, 4, 8, device="cuda")[..., ::2]
+    c = torch.zeros(1, 2, 4, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="contiguous"):      # droid.cpp:48
+        ops.corr_index_forward(v, c, 1)
+
+
+def test_lookup_is_deterministic(ops):
+    c = inputs.volume_case(2, 48, 64, 24, 32, 3, seed=9)
+    args = (cu(c["volume"]), cu(c["coords"]), cu(c["offset"]), cu(c["corr_grad"]), 3)
+    a = ops.defCorr_index_backward(*args)
+    b = ops.defCorr_index_backward(*args)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_full_size_properties(ops):
+    """BASELINE.json full size (E=48, 48x64, level 0): size-independent properties instead of the oracle --
+    linearity in the volume and <J v, g> = <v, J^T g>."""
+    E, H, W, r = 48, 48, 64, 3
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    vol = torch.randn(E, H, W, H, W, device="cuda", generator=g)
+    c = inputs.make_coords(E, H, W, H, W, inputs.gen(8)).cuda()
+    off = inputs.make_offset(E, H, W, r, inputs.gen(9)).cuda()
+    grad = torch.randn(E, 7, 7, H, W, device="cuda", generator=g)
+    out, = ops.defCorr_index_forward(vol, c, off, r)
+    out2, = ops.defCorr_index_forward(vol * 2, c, off, r)
+    assert torch.equal(out2, out * 2)                                       # exact: scaling by 2
+    gv, go = ops.defCorr_index_backward(vol, c, off, grad, r)
+    lhs = (out.double() * grad.double()).sum().item()
+    rhs = (vol.double() * gv.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * (out.double().abs() * grad.double().abs()).sum().item()
+    assert (gv != 0).sum().item() <= E * H * W * 49 * 4
