@@ -126,11 +126,11 @@ static inline unsigned grid_for_warps(long long nwarps_needed, int warps_per_cta
 
 extern "C" int lgu_gaussian_mask_forward(const float* means, const float* covs, const float* volume, float* volume1,
                                          int E, int H1, int W1, int H2, int W2, int radius, void* stream) {
+  if (E == 0) return LGU_OK;   // empty edge set: nothing to do (pointers may be null)
   LGU_REQUIRE(means && covs && volume && volume1, "lgu_gaussian_mask_forward: null pointer");
   LGU_REQUIRE(E >= 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && radius >= 0,
               "lgu_gaussian_mask_forward: bad sizes E=%d H1=%d W1=%d H2=%d W2=%d r=%d", E, H1, W1, H2, W2, radius);
   LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_gaussian_mask_forward: H2*W2 too large");
-  if (E == 0) return LGU_OK;
   const long long npix = (long long)E * H1 * W1;
   const unsigned grid = lgu::grid_for_warps(npix, lgu::kGaWarps, 8);
   lgu::gaussian_fwd_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(means, covs, volume, volume1, npix,
@@ -141,12 +141,12 @@ extern "C" int lgu_gaussian_mask_forward(const float* means, const float* covs, 
 extern "C" int lgu_gaussian_mask_backward(const float* means, const float* covs, const float* volume,
                                           const float* volume1_grad, float* means_grad, float* covs_grad, int E,
                                           int H1, int W1, int H2, int W2, int radius, void* stream) {
+  if (E == 0) return LGU_OK;   // empty edge set: nothing to do (pointers may be null)
   LGU_REQUIRE(means && covs && volume && volume1_grad && means_grad && covs_grad,
               "lgu_gaussian_mask_backward: null pointer");
   LGU_REQUIRE(E >= 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && radius >= 0,
               "lgu_gaussian_mask_backward: bad sizes E=%d H1=%d W1=%d H2=%d W2=%d r=%d", E, H1, W1, H2, W2, radius);
   LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_gaussian_mask_backward: H2*W2 too large");
-  if (E == 0) return LGU_OK;
   const long long npix = (long long)E * H1 * W1;
   const unsigned grid = lgu::grid_for_warps(npix, lgu::kGaWarps, 8);
   lgu::gaussian_bwd_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(

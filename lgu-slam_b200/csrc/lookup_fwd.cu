@@ -162,21 +162,21 @@ static int launch_lookup_fwd(const float* volume, const float* coords, float* of
 
 extern "C" int lgu_corr_index_forward(const float* volume, const float* coords, float* corr, int E, int H1, int W1,
                                       int H2, int W2, int radius, void* stream) {
+  if (E == 0) return LGU_OK;   // empty edge set: nothing to do (pointers may be null)
   LGU_REQUIRE(volume && coords && corr, "lgu_corr_index_forward: null pointer");
   LGU_REQUIRE(E >= 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && radius >= 0,
               "lgu_corr_index_forward: bad sizes E=%d H1=%d W1=%d H2=%d W2=%d r=%d", E, H1, W1, H2, W2, radius);
   LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_corr_index_forward: H2*W2 too large for 32-bit slice offsets");
-  if (E == 0) return LGU_OK;
   return lgu::launch_lookup_fwd<false>(volume, coords, nullptr, corr, E, H1, W1, H2, W2, radius,
                                        (cudaStream_t)stream);
 }
 
 extern "C" int lgu_defcorr_index_forward(const float* volume, const float* coords, float* offset, float* corr, int E,
                                          int H1, int W1, int H2, int W2, int radius, void* stream) {
+  if (E == 0) return LGU_OK;   // empty edge set: nothing to do (pointers may be null)
   LGU_REQUIRE(volume && coords && offset && corr, "lgu_defcorr_index_forward: null pointer");
   LGU_REQUIRE(E >= 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && radius >= 0,
               "lgu_defcorr_index_forward: bad sizes E=%d H1=%d W1=%d H2=%d W2=%d r=%d", E, H1, W1, H2, W2, radius);
   LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_defcorr_index_forward: H2*W2 too large for 32-bit slice offsets");
-  if (E == 0) return LGU_OK;
   return lgu::launch_lookup_fwd<true>(volume, coords, offset, corr, E, H1, W1, H2, W2, radius, (cudaStream_t)stream);
 }

@@ -200,24 +200,24 @@ static int launch_lowmem(const LowMemArgs& a0, cudaStream_t st, const char* name
 extern "C" int lgu_lowmem_defsample_forward(const float* fmap1, const float* fmap2, const float* coords,
                                             float* offset, float* corr, int B, int N, int H1, int W1, int H2, int W2,
                                             int C, int radius, int strict_ref, void* stream) {
+  if (B == 0) return LGU_OK;   // empty edge set: nothing to do (pointers may be null)
   LGU_REQUIRE(fmap1 && fmap2 && coords && offset && corr, "lgu_lowmem_defsample_forward: null pointer");
   LGU_REQUIRE(B >= 0 && N > 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && C > 0 && radius >= 0,
               "lgu_lowmem_defsample_forward: bad sizes");
   LGU_REQUIRE((C & 31) == 0 && C <= 512, "lgu_lowmem_defsample_forward: C=%d must be a multiple of 32, <= 512", C);
   LGU_REQUIRE(radius <= 4, "lgu_lowmem_defsample_forward: radius %d > 4 unsupported", radius);
-  if (B == 0) return LGU_OK;
   lgu::LowMemArgs a{fmap1, fmap2, coords, offset, corr, B, N, H1, W1, H2, W2, C, radius, strict_ref, 0};
   return lgu::launch_lowmem<true>(a, (cudaStream_t)stream, "lgu_lowmem_defsample_forward");
 }
 
 extern "C" int lgu_altcorr_forward(const float* fmap1, const float* fmap2, const float* coords, float* corr, int B,
                                    int N, int H1, int W1, int H2, int W2, int C, int radius, void* stream) {
+  if (B == 0) return LGU_OK;   // empty edge set: nothing to do (pointers may be null)
   LGU_REQUIRE(fmap1 && fmap2 && coords && corr, "lgu_altcorr_forward: null pointer");
   LGU_REQUIRE(B >= 0 && N > 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && C > 0 && radius >= 0,
               "lgu_altcorr_forward: bad sizes");
   LGU_REQUIRE((C & 31) == 0 && C <= 512, "lgu_altcorr_forward: C=%d must be a multiple of 32, <= 512", C);
   LGU_REQUIRE(radius <= 4, "lgu_altcorr_forward: radius %d > 4 unsupported", radius);
-  if (B == 0) return LGU_OK;
   lgu::LowMemArgs a{fmap1, fmap2, coords, nullptr, corr, B, N, H1, W1, H2, W2, C, radius, 0, 0};
   return lgu::launch_lowmem<false>(a, (cudaStream_t)stream, "lgu_altcorr_forward");
 }
