@@ -112,6 +112,35 @@ LGU_API int lgu_lowmem_defsample_forward(const float* fmap1, const float* fmap2,
 LGU_API int lgu_altcorr_forward(const float* fmap1, const float* fmap2, const float* coords, float* corr,
                         int B, int N, int H1, int W1, int H2, int W2, int C, int radius, void* stream);
 
+/* --------------------------------------------------------------------------
+ * Fused entry points (no single reference op; they replace op SEQUENCES of the
+ * reference's Python glue and are validated against the composition of the
+ * oracle's ops).
+ * ------------------------------------------------------------------------ */
+
+/* CorrBlock.__init__'s data path  (droid_slam/modules/corr.py:61-86 + gaussianMask_cuda.py:84-86):
+ *   V   = (f1/4)^T (f2/4)                       all-pairs volume, tcgen05 / TMEM, fp32 accumulate
+ *   V'  = gaussianMask(means,covs,V,gr)/den + V  learnable Gaussian residual (gr = 0 disables)
+ *   lvl[l+1] = avg_pool2x2(lvl[l])              written in the same pass
+ * fmaps   [T,P,C] fp16, channels-last ("K-major"), P = H*W (multiple of 128), C = 128
+ *         (produced by lgu_pack_fmaps); precision: 1 = single fp16 product (exact for
+ *         fp16-valued inputs, i.e. the inference path); 2 = hi/lo fp16 split, 3 MMAs,
+ *         |error| <= ~2^-21 relative per product (fp32-valued inputs, the training path).
+ * fmaps_lo  residual plane (x - fp16(x)) for precision 2, else NULL.
+ * ii, jj  [E] int32 frame index of the source / target map of each edge.
+ * means,covs [E,H,W,2], den [E,H,W] (= 6.28*sqrt(cov_x*cov_y), formed by the caller), or NULL.
+ * lvl0..lvl3 [E,H,W,H>>l,W>>l] outputs (lvl1..3 may be NULL to skip pooling). */
+LGU_API int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, const int32_t* ii, const int32_t* jj,
+                      const float* means, const float* covs, const float* den,
+                      float* lvl0, float* lvl1, float* lvl2, float* lvl3,
+                      int T, int E, int H, int W, int C, int gauss_radius, int precision,
+                      int round_half, void* stream);
+
+/* fmaps [T,C,P] fp32 or fp16 (NCHW as the encoders emit) -> channels-last fp16 planes
+ * hi [T,P,C] (and lo [T,P,C] = fp16(x/4 - hi) when lo != NULL), pre-scaled by 1/4 (corr.py:148-149). */
+LGU_API int lgu_pack_fmaps(const void* fmaps, int src_is_half, void* hi, void* lo,
+                   int T, int C, int P, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

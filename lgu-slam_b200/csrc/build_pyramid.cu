@@ -1,0 +1,585 @@
+// build_pyramid.cu -- fused all-pairs correlation volume + Gaussian-uncertainty residual + 4-level
+// average pyramid on tcgen05 / TMEM / TMA (sm_100a).
+//
+// Replaces the data path of CorrBlock.__init__ (/root/reference/droid_slam/modules/corr.py:61-86):
+//   torch.matmul (corr.py:144-152) -> .float() -> defCorrSample.gaussianMask (gaussianAttn.cu:19-68)
+//   -> corr1/denominator + corr (gaussianMask_cuda.py:85-86) -> 3x F.avg_pool2d (corr.py:83-86),
+// which moves ~300 MB per edge, by ONE kernel that writes the 50.1 MB pyramid exactly once.
+//
+// Shape contract: source/target grid 48x64-like (W == 64, H % 8 == 0, H*W % 128 == 0), C == 128.
+//
+// Work unit = (edge e, tile of 128 consecutive source pixels).  For a unit the CTA keeps the A tile
+// (128 px x 128 ch fp16, K-major, 128B-swizzled) resident in shared memory and sweeps the target map in
+// 24 chunks of 128 target pixels (2 target rows); two chunks (4 rows, 256 fp32 columns) form one TMEM
+// accumulator half, and the two halves of TMEM (512 columns) are double-buffered between the MMA issuer
+// and the epilogue.  A band of two halves (8 target rows) closes all four pyramid levels locally.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over units):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor loads of A / B tiles, mbarrier expect_tx)
+//   warp 1   : MMA issuer     (tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accumulate in TMEM) + TMEM alloc
+//   warps 2-5: epilogue       (tcgen05.ld 32x32b.x32 -> registers; thread == source pixel == TMEM lane;
+//                              level 0/1 rows staged in 128B-swizzled shared memory and written with TMA
+//                              bulk stores, level 2/3 rows (64 B / 32 B) stored directly; the Gaussian
+//                              window (<= 81 elements per source pixel) is patched in shared memory)
+// Precision: PREC 1 = one fp16 product (exact for fp16-valued feature maps: the inference path);
+//            PREC 2 = hi/lo fp16 split of both operands, 3 MMAs (hi*hi + hi*lo + lo*hi): ~2^-21 relative
+//            per product, for fp32-valued feature maps (the training path).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace lgu {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LGU_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LGU_DONE_%=;\n\t"
+      "bra LGU_WAIT_%=;\n\t"
+      "LGU_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i gets TMEM lane (base + i), columns c .. c+31.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 format, version 1):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (1024 B = 8 rows)
+//   | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// Instruction descriptor: D fp32 (bit 4), A/B fp16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel configuration
+// ---------------------------------------------------------------------------------------------
+constexpr int kBpThreads = 192;
+constexpr int kTileM = 128;      // source pixels per unit
+constexpr int kChunkN = 128;     // target pixels per MMA chunk (2 target rows of 64)
+constexpr int kC = 128;          // channels (K)
+constexpr int kAtomBytes = 128 * 128;   // one 64-channel swizzle atom column of a 128-row tile: 16 KB
+constexpr int kPlaneBytes = 2 * kAtomBytes;   // 128 rows x 128 ch fp16 = 32 KB
+
+template <int PREC>
+struct BpCfg {
+  static constexpr int kPlanes = PREC;                        // hi (+ lo)
+  static constexpr int kStages = PREC == 1 ? 3 : 2;           // B-chunk pipeline depth
+  static constexpr int kStoreBufs = PREC == 1 ? 4 : 2;        // 4 KB staging buffers per epilogue warp
+  static constexpr int kABytes = kPlanes * kPlaneBytes;
+  static constexpr int kStageBytes = kPlanes * kPlaneBytes;
+  static constexpr int kStoreBytes = 4 * kStoreBufs * 4096;
+  static constexpr int kBarOffset = kABytes + kStages * kStageBytes + kStoreBytes;
+  static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + 1 KB alignment slack
+};
+
+struct BpParams {
+  const int32_t* ii;
+  const int32_t* jj;
+  const float* means;   // [E,P,2] or null
+  const float* covs;    // [E,P,2]
+  const float* den;     // [E,P]
+  float* lvl2;          // [E,P,Q/16] or null
+  float* lvl3;          // [E,P,Q/64] or null
+  int E, P, H, gauss_radius, round_half, num_units, has_l1;
+};
+
+// Gaussian residual of one element (gaussianAttn.cu:58-64 + gaussianMask_cuda.py:85-86), fp32, no contraction.
+__device__ __forceinline__ float gauss_residual(float v, int x1, int y1, float mx, float my, float c1, float c2,
+                                                float den) {
+  const float ddx = __fsub_rn((float)x1, mx), ddy = __fsub_rn((float)y1, my);
+  const float t1 = __fdiv_rn(ddx, c1), t2 = __fdiv_rn(ddy, c2);
+  const float s = __fmaf_rn(ddy, t2, __fmul_rn(t1, ddx));
+  const float e = expf(__fmul_rn(s, -0.5f));
+  const float masked = __fmul_rn(__fmul_rn(v, 3.0f), e);
+  return __fadd_rn(__fdiv_rn(masked, den), v);
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(kBpThreads, 1)
+build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                     const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
+                     const BpParams prm) {
+  using Cfg = BpCfg<PREC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                   // [plane][atom][128 rows][128 B]
+  uint8_t* sB = smem + Cfg::kABytes;                    // [stage][plane][atom][128 rows][128 B]
+  uint8_t* sStore = sB + Cfg::kStages * Cfg::kStageBytes;   // [warp][buf][32 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
+  uint64_t* a_full = bars + 0;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;                          // [kStages]
+  uint64_t* b_empty = bars + 2 + Cfg::kStages;          // [kStages]
+  uint64_t* t_full = bars + 2 + 2 * Cfg::kStages;       // [2]
+  uint64_t* t_empty = t_full + 2;                       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = prm.P;
+  const int tiles_m = P / kTileM;
+  const int halves = prm.H / 4;                         // 4 target rows per TMEM half
+  const int Q = P;                                      // target pixels (same grid)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_hi);
+    if (PREC == 2) prefetch_tmap(&map_lo);
+    prefetch_tmap(&map_l0);
+    if (prm.has_l1) prefetch_tmap(&map_l1);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(t_full + b, 1);
+      mbar_init(t_empty + b, 4);                        // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t unit_it = 0, chunk_it = 0;
+      for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x, ++unit_it) {
+        const int e = u / tiles_m, mt = u - e * tiles_m;
+        const int a_row = __ldg(prm.ii + e) * P + mt * kTileM;
+        const int b_row0 = __ldg(prm.jj + e) * Q;
+        mbar_wait(a_empty, (unit_it & 1) ^ 1);
+        mbar_expect_tx(a_full, Cfg::kABytes);
+        tma_load_2d(sA, &map_hi, a_full, 0, a_row);
+        tma_load_2d(sA + kAtomBytes, &map_hi, a_full, 64, a_row);
+        if (PREC == 2) {
+          tma_load_2d(sA + kPlaneBytes, &map_lo, a_full, 0, a_row);
+          tma_load_2d(sA + kPlaneBytes + kAtomBytes, &map_lo, a_full, 64, a_row);
+        }
+        const int nchunks = halves * 2;
+        for (int c = 0; c < nchunks; ++c, ++chunk_it) {
+          const int s = chunk_it % Cfg::kStages;
+          const uint32_t use = chunk_it / Cfg::kStages;
+          mbar_wait(b_empty + s, (use & 1) ^ 1);
+          uint8_t* dst = sB + s * Cfg::kStageBytes;
+          const int b_row = b_row0 + c * kChunkN;
+          mbar_expect_tx(b_full + s, Cfg::kStageBytes);
+          tma_load_2d(dst, &map_hi, b_full + s, 0, b_row);
+          tma_load_2d(dst + kAtomBytes, &map_hi, b_full + s, 64, b_row);
+          if (PREC == 2) {
+            tma_load_2d(dst + kPlaneBytes, &map_lo, b_full + s, 0, b_row);
+            tma_load_2d(dst + kPlaneBytes + kAtomBytes, &map_lo, b_full + s, 64, b_row);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kTileM, kChunkN);
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      uint32_t unit_it = 0, chunk_it = 0, half_it = 0;
+      for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x, ++unit_it) {
+        mbar_wait(a_full, unit_it & 1);
+        for (int h = 0; h < halves; ++h, ++half_it) {
+          const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
+          mbar_wait(t_empty + buf, (buf_use & 1) ^ 1);
+          tc_fence_after();
+          for (int c = 0; c < 2; ++c, ++chunk_it) {
+            const int s = chunk_it % Cfg::kStages;
+            const uint32_t use = chunk_it / Cfg::kStages;
+            mbar_wait(b_full + s, use & 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * 256 + c * kChunkN;
+            const uint32_t bs = b_addr + s * Cfg::kStageBytes;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < (PREC == 1 ? 1 : 3); ++pass) {
+              // pass 0: hi*hi, pass 1: hi*lo, pass 2: lo*hi
+              const uint32_t ap = a_addr + ((pass == 2) ? kPlaneBytes : 0);
+              const uint32_t bp = bs + ((pass == 1) ? kPlaneBytes : 0);
+#pragma unroll
+              for (int k = 0; k < kC / 16; ++k) {
+                const uint32_t koff = (k >> 2) * kAtomBytes + (k & 3) * 32;
+                tc_mma_f16(d_tmem, make_kmajor_sw128_desc(ap + koff), make_kmajor_sw128_desc(bp + koff), idesc, acc);
+                acc = 1;
+              }
+            }
+            tc_commit(b_empty + s);                     // stage reusable once these MMAs have read it
+          }
+          tc_commit(t_full + buf);                      // accumulator half complete
+        }
+        tc_commit(a_empty);                             // A tile reusable
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint8_t* my_store = sStore + (warp - 2) * Cfg::kStoreBufs * 4096;
+    int sbuf = 0;
+    const int gr = prm.gauss_radius;
+    const unsigned rdg = 2u * (unsigned)gr + 1u;
+    const int rsw = lane & 7;                           // 128B swizzle phase of this thread's staging row
+
+    // stage one 32-float row segment per lane and hand the 32x32 tile to the TMA store engine
+    auto store_tile = [&](float (&v)[32], const CUtensorMap* map, int col, int row0, bool patch, int yy, int x0,
+                          float mx, float my, float c1, float c2, float den, unsigned bx) {
+      if (lane == 0) tma_wait_read<Cfg::kStoreBufs - 1>();
+      __syncwarp();
+      float4* rowp = reinterpret_cast<float4*>(my_store + sbuf * 4096 + lane * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) rowp[c ^ rsw] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      if (patch) {
+        // Gaussian window columns bx .. bx+rdg-1 (wrapping) that fall into [x0, x0+32)
+        float* rowf = reinterpret_cast<float*>(rowp);
+        bool touched = false;
+        for (unsigned k = 0; k < rdg; ++k) {
+          const int x = (int)(bx + k);
+          const unsigned idx = (unsigned)(x - x0);
+          if (idx < 32u) {
+            const unsigned pos = (((idx >> 2) ^ (unsigned)rsw) << 2) | (idx & 3u);
+            rowf[pos] = gauss_residual(rowf[pos], x, yy, mx, my, c1, c2, den);
+            touched = true;
+          }
+        }
+        if (touched) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 t = rowp[c ^ rsw];
+            v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(map, my_store + sbuf * 4096, col, row0);
+        tma_commit();
+      }
+      sbuf = (sbuf + 1 == Cfg::kStoreBufs) ? 0 : sbuf + 1;
+    };
+
+    uint32_t half_it = 0;
+    for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x) {
+      const int e = u / tiles_m, mt = u - e * tiles_m;
+      const int row0 = e * P + mt * kTileM + quad * 32;   // first output row (edge-pixel index) of this warp
+      const size_t pix = (size_t)row0 + lane;
+      float mx = 0.f, my = 0.f, c1 = 1.f, c2 = 1.f, den = 1.f;
+      unsigned bx = 0, by = 0;
+      if (gr > 0) {
+        const float2 m = __ldg(reinterpret_cast<const float2*>(prm.means) + pix);
+        const float2 c = __ldg(reinterpret_cast<const float2*>(prm.covs) + pix);
+        mx = m.x; my = m.y; c1 = c.x; c2 = c.y;
+        den = __ldg(prm.den + pix);
+        bx = (unsigned)floor_to_int(mx) - (unsigned)gr;
+        by = (unsigned)floor_to_int(my) - (unsigned)gr;
+      }
+      float l2_prev[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) l2_prev[i] = 0.f;
+
+      for (int h = 0; h < halves; ++h, ++half_it) {
+        const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
+        mbar_wait(t_full + buf, buf_use & 1);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + lane_base + buf * 256;
+        float l1[2][32];
+#pragma unroll
+        for (int rp = 0; rp < 2; ++rp) {
+#pragma unroll
+          for (int xs = 0; xs < 2; ++xs) {
+            float a[32], b[32];
+            tmem_ld32(tcol + (2 * rp) * 64 + xs * 32, a);
+            tmem_ld32(tcol + (2 * rp + 1) * 64 + xs * 32, b);
+            if (rp == 1 && xs == 1) {
+              // last TMEM read of this half: hand the accumulator back to the MMA issuer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(t_empty + buf);
+            }
+            if (prm.round_half) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                a[i] = __half2float(__float2half_rn(a[i]));
+                b[i] = __half2float(__float2half_rn(b[i]));
+              }
+            }
+            const int ya = 4 * h + 2 * rp, yb = ya + 1, x0 = xs * 32;
+            const bool pa = gr > 0 && ((unsigned)ya - by) < rdg;
+            const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
+            store_tile(a, &map_l0, ya * 64 + x0, row0, pa, ya, x0, mx, my, c1, c2, den, bx);
+            store_tile(b, &map_l0, yb * 64 + x0, row0, pb, yb, x0, mx, my, c1, c2, den, bx);
+            // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              l1[rp][xs * 16 + i] =
+                  __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a[2 * i], a[2 * i + 1]), b[2 * i]), b[2 * i + 1]), 0.25f);
+          }
+          if (prm.has_l1)
+            store_tile(l1[rp], &map_l1, (2 * h + rp) * 32, row0, false, 0, 0, 0.f, 0.f, 1.f, 1.f, 1.f, 0u);
+        }
+        if (prm.lvl2 != nullptr) {
+          float l2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            l2[i] = __fmul_rn(
+                __fadd_rn(__fadd_rn(__fadd_rn(l1[0][2 * i], l1[0][2 * i + 1]), l1[1][2 * i]), l1[1][2 * i + 1]), 0.25f);
+          float4* o2 = reinterpret_cast<float4*>(prm.lvl2 + pix * (size_t)(Q >> 4) + h * 16);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) o2[c] = make_float4(l2[4 * c], l2[4 * c + 1], l2[4 * c + 2], l2[4 * c + 3]);
+          if ((h & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) l2_prev[i] = l2[i];
+          } else if (prm.lvl3 != nullptr) {
+            float l3[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              l3[i] = __fmul_rn(
+                  __fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2 * i], l2_prev[2 * i + 1]), l2[2 * i]), l2[2 * i + 1]), 0.25f);
+            float4* o3 = reinterpret_cast<float4*>(prm.lvl3 + pix * (size_t)(Q >> 6) + (h >> 1) * 8);
+            o3[0] = make_float4(l3[0], l3[1], l3[2], l3[3]);
+            o3[1] = make_float4(l3[4], l3[5], l3[6], l3[7]);
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_wait_all();                      // all bulk stores complete before the CTA exits
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fmaps [T,C,P] (fp32 or fp16, NCHW as the encoders emit) -> channels-last fp16 planes [T,P,C]:
+//   hi = fp16(x/4), lo = fp16(x/4 - hi)          (the /4 is corr.py:148-149, exact in binary)
+// ---------------------------------------------------------------------------------------------
+template <typename SRC>
+__global__ void __launch_bounds__(256) pack_fmaps_kernel(const SRC* __restrict__ src, __half* __restrict__ hi,
+                                                         __half* __restrict__ lo, int C, int P) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    tile[r][tx] = (c < C && p < P) ? (float)src[((size_t)t * C + c) * P + p] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    if (p < P && c < C) {
+      const float x = tile[tx][r] * 0.25f;
+      const __half h = __float2half_rn(x);
+      const size_t o = ((size_t)t * P + p) * C + c;
+      hi[o] = h;
+      if (lo != nullptr) lo[o] = __float2half_rn(x - __half2float(h));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] of `elem_bytes`-byte elements, box [box_rows, box_cols], 128B swizzle.
+static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows,
+                       uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return LGU_ERR_LAUNCH;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols);
+    return LGU_ERR_LAUNCH;
+  }
+  return LGU_OK;
+}
+
+template <int PREC>
+static int launch_build(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& m0, const CUtensorMap& m1,
+                        const BpParams& prm, cudaStream_t st) {
+  using Cfg = BpCfg<PREC>;
+  auto kern = build_pyramid_kernel<PREC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("lgu_build_pyramid: cannot opt in to %d B of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = prm.num_units < sms ? prm.num_units : sms;
+  kern<<<grid, kBpThreads, Cfg::kSmemBytes, st>>>(mh, ml, m0, m1, prm);
+  return check_launch("lgu_build_pyramid");
+}
+
+}  // namespace lgu
+
+extern "C" int lgu_pack_fmaps(const void* fmaps, int src_is_half, void* hi, void* lo, int T, int C, int P,
+                              void* stream) {
+  if (T == 0) return LGU_OK;
+  LGU_REQUIRE(fmaps && hi, "lgu_pack_fmaps: null pointer");
+  LGU_REQUIRE(T > 0 && C > 0 && P > 0 && T <= 65535, "lgu_pack_fmaps: bad sizes T=%d C=%d P=%d", T, C, P);
+  const dim3 grid((P + 31) / 32, (C + 31) / 32, T);
+  if (src_is_half)
+    lgu::pack_fmaps_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(fmaps), reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), C, P);
+  else
+    lgu::pack_fmaps_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float*>(fmaps), reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), C, P);
+  return lgu::check_launch("lgu_pack_fmaps");
+}
+
+extern "C" int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, const int32_t* ii, const int32_t* jj,
+                                 const float* means, const float* covs, const float* den, float* lvl0, float* lvl1,
+                                 float* lvl2, float* lvl3, int T, int E, int H, int W, int C, int gauss_radius,
+                                 int precision, int round_half, void* stream) {
+  using namespace lgu;
+  if (E == 0) return LGU_OK;
+  LGU_REQUIRE(fmaps_hi && ii && jj && lvl0, "lgu_build_pyramid: null pointer");
+  LGU_REQUIRE(precision == 1 || precision == 2, "lgu_build_pyramid: precision must be 1 or 2");
+  LGU_REQUIRE(precision == 1 || fmaps_lo != nullptr, "lgu_build_pyramid: precision 2 needs the lo plane");
+  LGU_REQUIRE(T > 0 && E > 0 && gauss_radius >= 0 && gauss_radius <= 15, "lgu_build_pyramid: bad sizes");
+  LGU_REQUIRE(gauss_radius == 0 || (means && covs && den), "lgu_build_pyramid: Gaussian parameters missing");
+  if (!(W == 64 && H > 0 && (H % 8) == 0 && C == 128)) {
+    set_error("lgu_build_pyramid: only W=64, H%%8==0, C=128 grids are implemented (got H=%d W=%d C=%d)", H, W, C);
+    return LGU_ERR_UNSUPPORTED;
+  }
+  LGU_REQUIRE(lvl2 == nullptr || lvl1 != nullptr, "lgu_build_pyramid: lvl2 requires lvl1");
+  LGU_REQUIRE(lvl3 == nullptr || lvl2 != nullptr, "lgu_build_pyramid: lvl3 requires lvl2");
+  const int P = H * W;
+  LGU_REQUIRE((long long)E * P < 2147483647LL && (long long)T * P < 2147483647LL, "lgu_build_pyramid: too many rows");
+
+  CUtensorMap mh, ml, m0, m1;
+  int rc = make_map_2d(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fmaps_hi, (uint64_t)T * P, C, 128, 64);
+  if (rc) return rc;
+  rc = make_map_2d(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, precision == 2 ? fmaps_lo : fmaps_hi, (uint64_t)T * P, C,
+                   128, 64);
+  if (rc) return rc;
+  rc = make_map_2d(&m0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, (uint64_t)E * P, P, 32, 32);
+  if (rc) return rc;
+  rc = make_map_2d(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl1 ? lvl1 : lvl0, (uint64_t)E * P, lvl1 ? P / 4 : P, 32,
+                   32);
+  if (rc) return rc;
+
+  BpParams prm;
+  prm.ii = ii; prm.jj = jj; prm.means = means; prm.covs = covs; prm.den = den;
+  prm.lvl2 = lvl2; prm.lvl3 = lvl3;
+  prm.E = E; prm.P = P; prm.H = H; prm.gauss_radius = gauss_radius; prm.round_half = round_half;
+  prm.num_units = E * (P / kTileM);
+  prm.has_l1 = lvl1 != nullptr;
+  if (precision == 1) return launch_build<1>(mh, ml, m0, m1, prm, (cudaStream_t)stream);
+  return launch_build<2>(mh, ml, m0, m1, prm, (cudaStream_t)stream);
+}

@@ -20,19 +20,21 @@
 
 namespace lgu {
 
-constexpr int kBwTile = 32;  // source pixels per CTA
+constexpr int kBwGroup = 4;  // source pixels per warp (all their loads are issued before any store)
 
-// Deterministic scatter-add of one value per lane into the warp's shared slice.
-// `idx` < 0 means "this lane has nothing to add".
-__device__ __forceinline__ void warp_scatter_add(float* __restrict__ slice, int idx, float val, int lane) {
-  const unsigned key = idx >= 0 ? (unsigned)idx : (0x80000000u | (unsigned)lane);
-  const unsigned peers = __match_any_sync(0xffffffffu, key);
-  const int rank = __popc(peers & ((1u << lane) - 1u));
-  const int rounds = __reduce_max_sync(0xffffffffu, (unsigned)rank);
-  for (int it = 0; it <= rounds; ++it) {
-    if (idx >= 0 && rank == it) slice[idx] += val;
-    __syncwarp();
+// Scatter-add of one value per lane into the warp's shared slice; `idx` < 0: nothing to add.
+// DISTINCT = the caller guarantees that no two lanes of this call share an index (all taps of the pixel
+// carry the same offset, so tap (i,j) -> cell is injective): plain read-modify-write.  Otherwise lanes may
+// collide (learned offsets can map two taps onto one cell) and a shared-memory atomic resolves it.
+// (__match_any_sync-based conflict resolution was measured at ~1100 cycles per call with 32 distinct keys.)
+template <bool DISTINCT>
+__device__ __forceinline__ void warp_scatter_add(float* __restrict__ slice, int idx, float val) {
+  if (DISTINCT) {
+    if (idx >= 0) slice[idx] += val;
+  } else {
+    if (idx >= 0) atomicAdd(slice + idx, val);
   }
+  __syncwarp();
 }
 
 template <int R, bool DEFORM, int WARPS>
@@ -41,7 +43,8 @@ lookup_bwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
                   const float* __restrict__ corr_grad, float* __restrict__ volume_grad,
                   float* __restrict__ offset_grad, int P, int H2, int W2, int tiles_per_edge) {
   constexpr int RD = 2 * R + 1, TAPS = RD * RD, PASSES = (TAPS + 31) / 32;
-  constexpr int PIX_PER_WARP = kBwTile / WARPS;
+  constexpr int PIX_PER_WARP = kBwGroup;
+  constexpr int kBwTile = WARPS * kBwGroup;          // source pixels per CTA
   extern __shared__ __align__(16) float smem[];
   float(*s_g)[kBwTile + 1] = reinterpret_cast<float(*)[kBwTile + 1]>(smem);   // [TAPS][33]
   const int Q = H2 * W2;
@@ -54,9 +57,11 @@ lookup_bwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
 
   // stage the upstream gradient tile (coalesced rows) and clear the slices
   {
-    const bool live = (p0 + lane) < P;
-    const float* g = corr_grad + (size_t)n * TAPS * P + p0 + lane;
-    for (int t = warp; t < TAPS; t += WARPS) s_g[t][lane] = live ? __ldg(g + (size_t)t * P) : 0.0f;
+    // rows of kBwTile floats (64 or 128 B), several tap rows per warp instruction
+    for (int q = threadIdx.x; q < TAPS * kBwTile; q += WARPS * 32) {
+      const int t = q / kBwTile, c = q - t * kBwTile;
+      s_g[t][c] = (p0 + c) < P ? __ldg(corr_grad + ((size_t)n * TAPS + t) * P + p0 + c) : 0.0f;
+    }
     for (int q = lane; q < Qpad; q += 32) slice[q] = 0.0f;
   }
   __syncthreads();
@@ -64,60 +69,119 @@ lookup_bwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
   const float* cx = coords + (size_t)n * 2 * P;
   const float* cy = cx + P;
 
+  // Pixels are walked in groups of GRP: all coords / offset records of a group are requested first
+  // (phase A), then all corner gathers (phase B, deformable only), then each pixel is scattered and
+  // streamed out (phase C).  One phase per pixel left the kernel latency-bound (ncu: serialized
+  // ~5k-cycle long-scoreboard waits).
+  constexpr int GRP = PIX_PER_WARP < 4 ? PIX_PER_WARP : 4;
 #pragma unroll 1
-  for (int k = 0; k < PIX_PER_WARP; ++k) {
-    const int pl = warp * PIX_PER_WARP + k;
-    const int p = p0 + pl;
-    if (p >= P) break;                               // warp-uniform
-    const size_t pix = (size_t)n * P + p;
-    const float x0 = __ldg(cx + p), y0 = __ldg(cy + p);
-    const float* V = DEFORM ? volume + pix * (size_t)Q : nullptr;
-    float2* O = DEFORM ? reinterpret_cast<float2*>(offset) + pix * TAPS : nullptr;
-    float2* GO = DEFORM ? reinterpret_cast<float2*>(offset_grad) + pix * TAPS : nullptr;
-    int ymin = 0x7fffffff, ymax = -1;
-
+  for (int k0 = 0; k0 < PIX_PER_WARP; k0 += GRP) {
+    if (p0 + warp * PIX_PER_WARP + k0 >= P) break;   // warp-uniform
+    float dxs[GRP][PASSES], dys[GRP][PASSES], q[GRP][PASSES][4];
+    int i11s[GRP][PASSES];
+    unsigned gates[GRP][PASSES];                     // bit0 gate, bit1 xo, bit2 yo
+    // ---- phase A
+    float x0[GRP], y0[GRP];
+    float2 o[GRP][PASSES];
+    bool uniform_off[GRP];
 #pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-      const int t = ps * 32 + lane;
-      const bool has_tap = t < TAPS;
-      const int tt = has_tap ? t : 0;
-      const int i = tt / RD, j = tt - i * RD;
-      float dx, dy;
-      int fx, fy;
-      if (DEFORM) {
-        float2 o = make_float2(0.0f, 0.0f);
-        if (has_tap) {
-          if (t == R * RD + R) O[t] = o;             // defCorrSample_kernel.cu:122-123 (Q5)
-          else o = O[t];
+    for (int g = 0; g < GRP; ++g) {
+      const int p = min(p0 + warp * PIX_PER_WARP + k0 + g, P - 1);
+      const size_t pix = (size_t)n * P + p;
+      x0[g] = __ldg(cx + p);
+      y0[g] = __ldg(cy + p);
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        o[g][ps] = make_float2(0.0f, 0.0f);
+        if (DEFORM) {
+          float2* O = reinterpret_cast<float2*>(offset) + pix * TAPS;
+          const int t = ps * 32 + lane;
+          o[g][ps] = O[min(t, TAPS - 1)];
+          if (t == R * RD + R) o[g][ps] = make_float2(0.0f, 0.0f);   // defCorrSample_kernel.cu:122-123 (Q5), stored below
         }
-        const float px = __fadd_rn(o.x, x0), py = __fadd_rn(o.y, y0);
-        fx = floor_to_int(px);
-        fy = floor_to_int(py);
-        dx = __fsub_rn(px, (float)fx);
-        dy = __fsub_rn(py, (float)fy);
-      } else {
-        dx = __fsub_rn(x0, floorf(x0));
-        dy = __fsub_rn(y0, floorf(y0));
-        fx = floor_to_int(x0);
-        fy = floor_to_int(y0);
       }
-      const int x1 = tap_coord(fx, R, i), y1 = tap_coord(fy, R, j);
-      const int x2 = wrap_inc(x1), y2 = wrap_inc(y1);
-      const bool gate = has_tap && in_bounds(y1, x1, H2, W2);
-      const bool xo = gate && (x2 >= 0 && x2 < W2), yo = gate && (y2 >= 0 && y2 < H2);
-      const float g = s_g[tt][pl];
-      const float omdx = __fsub_rn(1.0f, dx), omdy = __fsub_rn(1.0f, dy);
-      const int i11 = y1 * W2 + x1;
-
+    }
+    // all taps of a pixel share one offset (always true for the plain lookup, and for the zero-offset
+    // pyramid levels)?  then tap -> cell is injective and the scatter needs no atomics
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) {
+      bool same = true;
       if (DEFORM) {
-        float q11 = 0.0f, q21 = 0.0f, q12 = 0.0f, q22 = 0.0f;
-        if (gate) q11 = __ldg(V + i11);
-        if (xo) q21 = __ldg(V + i11 + 1);
-        if (yo) q12 = __ldg(V + i11 + W2);
-        if (xo && yo) q22 = __ldg(V + i11 + W2 + 1);
-        if (has_tap) {
+        const float ox0 = __shfl_sync(0xffffffffu, o[g][0].x, 0), oy0 = __shfl_sync(0xffffffffu, o[g][0].y, 0);
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps)
+          same = same && (ps * 32 + lane >= TAPS || (o[g][ps].x == ox0 && o[g][ps].y == oy0));
+        same = __all_sync(0xffffffffu, same);
+      }
+      uniform_off[g] = same;
+    }
+    // ---- phase B
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) {
+      const int p = min(p0 + warp * PIX_PER_WARP + k0 + g, P - 1);
+      const float* V = DEFORM ? volume + ((size_t)n * P + p) * (size_t)Q : nullptr;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int t = ps * 32 + lane;
+        const bool has_tap = t < TAPS;
+        const int tt = has_tap ? t : 0;
+        const int i = tt / RD, j = tt - i * RD;
+        float dx, dy;
+        int fx, fy;
+        if (DEFORM) {
+          const float px = __fadd_rn(o[g][ps].x, x0[g]), py = __fadd_rn(o[g][ps].y, y0[g]);
+          fx = floor_to_int(px);
+          fy = floor_to_int(py);
+          dx = __fsub_rn(px, (float)fx);
+          dy = __fsub_rn(py, (float)fy);
+        } else {
+          dx = __fsub_rn(x0[g], floorf(x0[g]));
+          dy = __fsub_rn(y0[g], floorf(y0[g]));
+          fx = floor_to_int(x0[g]);
+          fy = floor_to_int(y0[g]);
+        }
+        const int x1 = tap_coord(fx, R, i), y1 = tap_coord(fy, R, j);
+        const int x2 = wrap_inc(x1), y2 = wrap_inc(y1);
+        const bool gate = has_tap && in_bounds(y1, x1, H2, W2);
+        const bool xo = gate && (x2 >= 0 && x2 < W2), yo = gate && (y2 >= 0 && y2 < H2);
+        const int i11 = gate ? y1 * W2 + x1 : 0;
+        dxs[g][ps] = dx;
+        dys[g][ps] = dy;
+        i11s[g][ps] = i11;
+        gates[g][ps] = (gate ? 1u : 0u) | (xo ? 2u : 0u) | (yo ? 4u : 0u);
+        if (DEFORM) {   // unconditional loads from always-valid addresses; masked in phase C
+          q[g][ps][0] = __ldg(V + i11);
+          q[g][ps][1] = __ldg(V + (xo ? i11 + 1 : i11));
+          q[g][ps][2] = __ldg(V + (yo ? i11 + W2 : i11));
+          q[g][ps][3] = __ldg(V + ((xo && yo) ? i11 + W2 + 1 : i11));
+        }
+      }
+    }
+    // ---- phase C
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) {
+      const int pl = warp * PIX_PER_WARP + k0 + g;
+      const int p = p0 + pl;
+      if (p >= P) break;                               // warp-uniform
+      const size_t pix = (size_t)n * P + p;
+      float2* GO = DEFORM ? reinterpret_cast<float2*>(offset_grad) + pix * TAPS : nullptr;
+      if (DEFORM && lane == 0)   // in-place zeroing of the centre tap, after every load of this warp has been issued
+        reinterpret_cast<float2*>(offset)[pix * TAPS + R * RD + R] = make_float2(0.0f, 0.0f);
+      int ymin = 0x7fffffff, ymax = -1;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int t = ps * 32 + lane;
+        const bool has_tap = t < TAPS;
+        const bool gate = gates[g][ps] & 1u, xo = gates[g][ps] & 2u, yo = gates[g][ps] & 4u;
+        const float dx = dxs[g][ps], dy = dys[g][ps];
+        const float omdx = __fsub_rn(1.0f, dx), omdy = __fsub_rn(1.0f, dy);
+        const int i11 = i11s[g][ps];
+        const float gq = s_g[has_tap ? t : 0][pl];
+        if (DEFORM && has_tap) {
           float2 go = make_float2(0.0f, 0.0f);
           if (gate) {
+            const float q11 = q[g][ps][0], q21 = xo ? q[g][ps][1] : 0.0f, q12 = yo ? q[g][ps][2] : 0.0f,
+                        q22 = (xo && yo) ? q[g][ps][3] : 0.0f;
             // defCorrSample_kernel.cu:156-157 in the reference's SASS operation order
             float ty = __fmaf_rn(-q11, omdx, -__fmul_rn(dx, q21));
             ty = __fmaf_rn(omdx, q12, ty);
@@ -125,53 +189,62 @@ lookup_bwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
             float tx = __fmaf_rn(omdy, q21, -__fmul_rn(q11, omdy));
             tx = __fmaf_rn(-dy, q12, tx);
             tx = __fmaf_rn(dy, q22, tx);
-            go.x = __fmul_rn(tx, g);
-            go.y = __fmul_rn(ty, g);
+            go.x = __fmul_rn(tx, gq);
+            go.y = __fmul_rn(ty, gq);
           }
           GO[t] = go;
         }
+        if (gate) {
+          const int y1 = i11 / W2;
+          ymin = min(ymin, y1);
+          ymax = max(ymax, yo ? y1 + 1 : y1);
+        }
+        const float w11 = __fmul_rn(__fmul_rn(omdy, omdx), gq), w21 = __fmul_rn(__fmul_rn(omdy, dx), gq);
+        const float w12 = __fmul_rn(__fmul_rn(dy, omdx), gq), w22 = __fmul_rn(__fmul_rn(dy, dx), gq);
+        if (uniform_off[g]) {
+          warp_scatter_add<true>(slice, gate ? i11 : -1, w11);
+          warp_scatter_add<true>(slice, xo ? i11 + 1 : -1, w21);
+          warp_scatter_add<true>(slice, yo ? i11 + W2 : -1, w12);
+          warp_scatter_add<true>(slice, (xo && yo) ? i11 + W2 + 1 : -1, w22);
+        } else {
+          warp_scatter_add<false>(slice, gate ? i11 : -1, w11);
+          warp_scatter_add<false>(slice, xo ? i11 + 1 : -1, w21);
+          warp_scatter_add<false>(slice, yo ? i11 + W2 : -1, w12);
+          warp_scatter_add<false>(slice, (xo && yo) ? i11 + W2 + 1 : -1, w22);
+        }
       }
 
-      if (gate) {
-        ymin = min(ymin, y1);
-        ymax = max(ymax, yo ? y2 : y1);
-      }
-      warp_scatter_add(slice, gate ? i11 : -1, __fmul_rn(__fmul_rn(omdy, omdx), g), lane);
-      warp_scatter_add(slice, xo ? i11 + 1 : -1, __fmul_rn(__fmul_rn(omdy, dx), g), lane);
-      warp_scatter_add(slice, yo ? i11 + W2 : -1, __fmul_rn(__fmul_rn(dy, omdx), g), lane);
-      warp_scatter_add(slice, (xo && yo) ? i11 + W2 + 1 : -1, __fmul_rn(__fmul_rn(dy, dx), g), lane);
-    }
-
-    // stream the slice out (and re-zero it); rows outside [ymin,ymax] are known zeros
-    ymin = __reduce_min_sync(0xffffffffu, ymin);
-    ymax = __reduce_max_sync(0xffffffffu, ymax);
-    const int lo = (ymax >= 0) ? ymin * W2 : 0x7fffffff;    // first touched element
-    const int hi = (ymax >= 0) ? (ymax + 1) * W2 : 0;       // one past the last
-    float* G = volume_grad + pix * (size_t)Q;
-    if ((Q & 3) == 0 && ((reinterpret_cast<uintptr_t>(G) & 15) == 0)) {
-      float4* G4 = reinterpret_cast<float4*>(G);
-      float4* S4 = reinterpret_cast<float4*>(slice);
-      const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      for (int q4 = lane; q4 < (Q >> 2); q4 += 32) {
-        const int e0 = q4 << 2;
-        float4 v = z;
-        if (e0 + 3 >= lo && e0 < hi) {
-          v = S4[q4];
-          S4[q4] = z;
+      // stream the slice out (and re-zero it); rows outside [ymin,ymax] are known zeros
+      ymin = __reduce_min_sync(0xffffffffu, ymin);
+      ymax = __reduce_max_sync(0xffffffffu, ymax);
+      const int lo = (ymax >= 0) ? ymin * W2 : 0x7fffffff;    // first touched element
+      const int hi = (ymax >= 0) ? (ymax + 1) * W2 : 0;       // one past the last
+      float* G = volume_grad + pix * (size_t)Q;
+      if ((Q & 3) == 0 && ((reinterpret_cast<uintptr_t>(G) & 15) == 0)) {
+        float4* G4 = reinterpret_cast<float4*>(G);
+        float4* S4 = reinterpret_cast<float4*>(slice);
+        const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int q4 = lane; q4 < (Q >> 2); q4 += 32) {
+          const int e0 = q4 << 2;
+          float4 v = z;
+          if (e0 + 3 >= lo && e0 < hi) {
+            v = S4[q4];
+            S4[q4] = z;
+          }
+          __stcs(G4 + q4, v);
         }
-        __stcs(G4 + q4, v);
-      }
-    } else {
-      for (int q = lane; q < Q; q += 32) {
-        float v = 0.0f;
-        if (q >= lo && q < hi) {
-          v = slice[q];
-          slice[q] = 0.0f;
+      } else {
+        for (int qq = lane; qq < Q; qq += 32) {
+          float v = 0.0f;
+          if (qq >= lo && qq < hi) {
+            v = slice[qq];
+            slice[qq] = 0.0f;
+          }
+          __stcs(G + qq, v);
         }
-        __stcs(G + q, v);
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -244,6 +317,7 @@ static int launch_bwd_cfg(const float* volume, const float* coords, float* offse
                           float* volume_grad, float* offset_grad, int E, int P, int H2, int W2, cudaStream_t st) {
   constexpr int TAPS = (2 * R + 1) * (2 * R + 1);
   const int Q = H2 * W2, Qpad = (Q + 3) & ~3;
+  constexpr int kBwTile = WARPS * kBwGroup;
   const size_t smem = (size_t)(((TAPS * (kBwTile + 1) + 3) & ~3) + WARPS * Qpad) * sizeof(float);
   auto kern = lookup_bwd_kernel<R, DEFORM, WARPS>;
   if (smem > 48 * 1024) {
@@ -278,7 +352,7 @@ static int launch_lookup_bwd(const float* volume, const float* coords, float* of
                              float* volume_grad, float* offset_grad, int E, int H1, int W1, int H2, int W2, int r,
                              cudaStream_t st) {
   const int P = H1 * W1;
-  const long long nblk = (long long)E * ((P + kBwTile - 1) / kBwTile);
+  const long long nblk = (long long)E * ((P + 7) / 8);   // smallest tile is 2 warps x 4 pixels
   LGU_REQUIRE(nblk < 2147483647LL, "lookup backward: grid too large (%lld CTAs)", nblk);
   int rc = -1;
   switch (r) {

@@ -17,6 +17,7 @@
 //   * index logic is the reference's, bit for bit: F2I.FLOOR saturating conversion,
 //     wrapping tap arithmetic, whole tap gated on the top-left corner (quirk Q3),
 //     x2/y2 corners gated individually, centre offset tap zeroed in place (Q5).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace lgu {
@@ -26,49 +27,64 @@ constexpr int kLkThreads = kLkWarps * 32;
 constexpr int kLkTile = 32;                       // source pixels per CTA
 constexpr int kLkPixPerWarp = kLkTile / kLkWarps; // 4
 
-template <bool DEFORM>
-struct TapSample {
+// Address / weight set-up of one tap (index logic of defCorrSample_kernel.cu:56-67 and
+// corrSample_kernel.cu:52-60, bit for bit): returns the gate and the four corner indices, which are
+// always valid addresses inside the pixel's slice (gated-off corners alias the top-left / slice start),
+// so that the loads can be issued unconditionally and early.
+struct TapAddr {
   float dx, dy;
-  int x1, y1;
+  int i11, i21, i12, i22;
+  bool gate, xo, yo;
 };
 
-// One tap of one pixel: returns the blended value (0 when gated off).
 template <bool DEFORM>
-__device__ __forceinline__ float sample_tap(const float* __restrict__ V, float x0, float y0, float ox, float oy,
-                                            int i, int j, int r, int H2, int W2) {
-  float dx, dy;
+__device__ __forceinline__ TapAddr tap_setup(float x0, float y0, float ox, float oy, int i, int j, int r, int H2,
+                                             int W2) {
+  TapAddr a;
   int fx, fy;
   if (DEFORM) {
     const float px = __fadd_rn(ox, x0), py = __fadd_rn(oy, y0);   // defCorrSample_kernel.cu:56-57
     fx = floor_to_int(px);
     fy = floor_to_int(py);
-    dx = __fsub_rn(px, (float)fx);                                 // :60-61 (via the int)
-    dy = __fsub_rn(py, (float)fy);
+    a.dx = __fsub_rn(px, (float)fx);                               // :60-61 (via the int)
+    a.dy = __fsub_rn(py, (float)fy);
   } else {
-    dx = __fsub_rn(x0, floorf(x0));                                // corrSample_kernel.cu:52-53
-    dy = __fsub_rn(y0, floorf(y0));
+    a.dx = __fsub_rn(x0, floorf(x0));                              // corrSample_kernel.cu:52-53
+    a.dy = __fsub_rn(y0, floorf(y0));
     fx = floor_to_int(x0);
     fy = floor_to_int(y0);
   }
   const int x1 = tap_coord(fx, r, i), y1 = tap_coord(fy, r, j);
   const int x2 = wrap_inc(x1), y2 = wrap_inc(y1);
-  if (!in_bounds(y1, x1, H2, W2)) return 0.0f;                     // whole tap gated on top-left (Q3)
-  const bool xo = (x2 >= 0 && x2 < W2), yo = (y2 >= 0 && y2 < H2);
-  const float* row1 = V + y1 * W2;
-  const float* row2 = row1 + W2;
-  const float q11 = __ldg(row1 + x1);
-  const float q21 = xo ? __ldg(row1 + x2) : 0.0f;
-  const float q12 = yo ? __ldg(row2 + x1) : 0.0f;
-  const float q22 = (xo && yo) ? __ldg(row2 + x2) : 0.0f;
-  return blend4(q11, q21, q12, q22, dx, dy);
+  a.gate = in_bounds(y1, x1, H2, W2);                              // whole tap gated on top-left (Q3)
+  a.xo = a.gate && (x2 >= 0 && x2 < W2);
+  a.yo = a.gate && (y2 >= 0 && y2 < H2);
+  a.i11 = a.gate ? y1 * W2 + x1 : 0;
+  a.i21 = a.xo ? a.i11 + 1 : a.i11;
+  a.i12 = a.yo ? a.i11 + W2 : a.i11;
+  a.i22 = (a.xo && a.yo) ? a.i11 + W2 + 1 : a.i11;
+  return a;
 }
 
-// R > 0: compile-time radius (taps fully unrolled, smem-transposed coalesced stores).
-template <int R, bool DEFORM>
-__global__ void __launch_bounds__(kLkThreads)
+// One tap of one pixel (generic-radius path): returns the blended value (0 when gated off).
+template <bool DEFORM>
+__device__ __forceinline__ float sample_tap(const float* __restrict__ V, float x0, float y0, float ox, float oy,
+                                            int i, int j, int r, int H2, int W2) {
+  const TapAddr a = tap_setup<DEFORM>(x0, y0, ox, oy, i, j, r, H2, W2);
+  const float q11 = __ldg(V + a.i11), q21 = __ldg(V + a.i21), q12 = __ldg(V + a.i12), q22 = __ldg(V + a.i22);
+  return a.gate ? blend4(q11, a.xo ? q21 : 0.0f, a.yo ? q12 : 0.0f, (a.xo && a.yo) ? q22 : 0.0f, a.dx, a.dy) : 0.0f;
+}
+
+// R > 0: compile-time radius.  The warp's 4 pixels x PASSES tap groups are processed in three
+// branch-free phases so that every global load of a phase is in flight at once (the kernel is
+// latency-bound otherwise: ncu showed 16 serialized ~5k-cycle waits per warp with one phase per tap group):
+//   A: coords + offset records (coalesced float2 rows)   B: 4 corner gathers per tap   C: blend + smem transpose
+template <int R, bool DEFORM, int EXP = 0>
+__global__ void __launch_bounds__(kLkThreads, 2)
 lookup_fwd_kernel(const float* __restrict__ volume, const float* __restrict__ coords, float* __restrict__ offset,
                   float* __restrict__ corr, int P, int W1, int H2, int W2, int tiles_per_edge) {
   constexpr int RD = 2 * R + 1, TAPS = RD * RD, PASSES = (TAPS + 31) / 32;
+  constexpr int CENTER = R * RD + R;
   __shared__ float s_out[TAPS][kLkTile + 1];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -78,26 +94,59 @@ lookup_fwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
   const float* cx = coords + (size_t)n * 2 * P;
   const float* cy = cx + P;
 
+  // ---- phase A: coords and offsets of all 4 pixels
+  float x0[kLkPixPerWarp], y0[kLkPixPerWarp];
+  float2 o[kLkPixPerWarp][PASSES];
+  const float* V[kLkPixPerWarp];
+#pragma unroll
+  for (int k = 0; k < kLkPixPerWarp; ++k) {
+    const int p = min(p0 + warp * kLkPixPerWarp + k, P - 1);   // tail pixels recompute the last one (never stored)
+    const size_t pix = (size_t)n * P + p;
+    x0[k] = __ldg(cx + p);
+    y0[k] = __ldg(cy + p);
+    V[k] = volume + pix * Q;
+    if (DEFORM) {
+      float2* O = reinterpret_cast<float2*>(offset) + pix * TAPS;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int t = ps * 32 + lane;
+        o[k][ps] = O[min(t, TAPS - 1)];
+        if (t == CENTER) o[k][ps] = make_float2(0.0f, 0.0f);   // the centre tap reads as zero (Q5) ...
+      }
+    } else {
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) o[k][ps] = make_float2(0.0f, 0.0f);
+    }
+  }
+  // ---- phase B: set up every tap and issue all gathers
+  TapAddr ta[kLkPixPerWarp][PASSES];
+  float q[kLkPixPerWarp][PASSES][4];
+#pragma unroll
+  for (int k = 0; k < kLkPixPerWarp; ++k) {
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int t = min(ps * 32 + lane, TAPS - 1);
+      const int i = t / RD, j = t - i * RD;                       // i: x tap, j: y tap (quirk Q1)
+      ta[k][ps] = tap_setup<DEFORM>(x0[k], y0[k], o[k][ps].x, o[k][ps].y, i, j, R, H2, W2);
+      if (EXP & 2) { q[k][ps][0] = q[k][ps][1] = q[k][ps][2] = q[k][ps][3] = 1.0f; } else {
+      q[k][ps][0] = __ldg(V[k] + ta[k][ps].i11);
+      q[k][ps][1] = __ldg(V[k] + ta[k][ps].i21);
+      q[k][ps][2] = __ldg(V[k] + ta[k][ps].i12);
+      q[k][ps][3] = __ldg(V[k] + ta[k][ps].i22); }
+    }
+  }
+  // ---- phase C: blend, transpose through shared memory
 #pragma unroll
   for (int k = 0; k < kLkPixPerWarp; ++k) {
     const int pl = warp * kLkPixPerWarp + k;
-    const int p = min(p0 + pl, P - 1);          // tail pixels recompute the last one (never stored)
-    const size_t pix = (size_t)n * P + p;
-    const float x0 = __ldg(cx + p), y0 = __ldg(cy + p);
-    const float* V = volume + pix * Q;
-    float2* O = DEFORM ? reinterpret_cast<float2*>(offset) + pix * TAPS : nullptr;
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) {
       const int t = ps * 32 + lane;
-      if (t < TAPS) {
-        const int i = t / RD, j = t - i * RD;   // i: x tap, j: y tap (quirk Q1)
-        float2 o = make_float2(0.0f, 0.0f);
-        if (DEFORM) {
-          if (t == R * RD + R) O[t] = o;        // in-place zeroing of the centre tap (Q5)
-          else o = O[t];
-        }
-        s_out[t][pl] = sample_tap<DEFORM>(V, x0, y0, o.x, o.y, i, j, R, H2, W2);
-      }
+      const TapAddr& a = ta[k][ps];
+      const float val = a.gate ? blend4(q[k][ps][0], a.xo ? q[k][ps][1] : 0.0f, a.yo ? q[k][ps][2] : 0.0f,
+                                        (a.xo && a.yo) ? q[k][ps][3] : 0.0f, a.dx, a.dy)
+                               : 0.0f;
+      if (t < TAPS) s_out[t][pl] = val;
     }
   }
   __syncthreads();
@@ -105,7 +154,13 @@ lookup_fwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
   float* out = corr + (size_t)n * TAPS * P + p0 + lane;
 #pragma unroll 1
   for (int t = warp; t < TAPS; t += kLkWarps)
-    if (live) out[(size_t)t * P] = s_out[t][lane];
+    if (live && !((EXP & 4) && s_out[t][lane] != 12345.f)) out[(size_t)t * P] = s_out[t][lane];
+  // ... and is zeroed in the caller's tensor LAST: a global store ahead of the gathers of the same warp
+  // stalls them (measured 2.7x on the whole kernel), and no other warp reads this pixel's record.
+  if (DEFORM && !(EXP & 1) && lane < kLkPixPerWarp) {
+    const int p = p0 + warp * kLkPixPerWarp + lane;
+    if (p < P) reinterpret_cast<float2*>(offset)[((size_t)n * P + p) * TAPS + CENTER] = make_float2(0.0f, 0.0f);
+  }
 }
 
 // Any radius (slow path, rarely used): same mapping, direct strided stores.
@@ -145,7 +200,16 @@ static int launch_lookup_fwd(const float* volume, const float* coords, float* of
   switch (r) {
     case 1: lookup_fwd_kernel<1, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
     case 2: lookup_fwd_kernel<2, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
-    case 3: lookup_fwd_kernel<3, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
+    case 3: {
+      const char* ex = getenv("LGU_EXP");
+      const int exv = ex ? atoi(ex) : 0;
+      if (exv == 1) lookup_fwd_kernel<3, DEFORM, 1><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
+      else if (exv == 2) lookup_fwd_kernel<3, DEFORM, 2><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
+      else if (exv == 4) lookup_fwd_kernel<3, DEFORM, 4><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
+      else if (exv == 7) lookup_fwd_kernel<3, DEFORM, 7><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
+      else lookup_fwd_kernel<3, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
+      break;
+    }
     case 4: lookup_fwd_kernel<4, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
     default: {
       const long long npix = (long long)E * P;

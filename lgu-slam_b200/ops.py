@@ -175,3 +175,66 @@ def altcorr_forward(fmap1, fmap2, coords, radius):
                                             _i(H2), _i(W2), _i(C), _i(radius), _stream(fmap1))
     _lib.check(st, "altcorr_forward")
     return [corr]
+
+
+# ----------------------------------------------------------------------------------------------
+# Fused ops (no single reference operator; they replace sequences of the reference's Python glue)
+# ----------------------------------------------------------------------------------------------
+def pack_fmaps(fmaps, split=False):
+    """fmaps [T,C,H,W] (fp32 or fp16 CUDA, as the encoders emit) -> channels-last fp16 planes for the
+    tcgen05 build: hi [T,H*W,C] = fp16(x/4) and, if split, lo = fp16(x/4 - hi) (else None).
+    The /4 is CorrBlock.corr's pre-scale (corr.py:148-149)."""
+    if not (isinstance(fmaps, torch.Tensor) and fmaps.is_cuda and fmaps.dim() == 4 and fmaps.is_contiguous()):
+        raise RuntimeError("fmaps must be a contiguous CUDA tensor [T,C,H,W]")
+    if fmaps.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError(f"fmaps: expected float32 or float16, got {fmaps.dtype}")
+    T, C, H, W = fmaps.shape
+    hi = torch.empty(T, H * W, C, dtype=torch.float16, device=fmaps.device)
+    lo = torch.empty_like(hi) if split else None
+    with torch.cuda.device(fmaps.device):
+        st = _lib.lib().lgu_pack_fmaps(_p(fmaps), _i(fmaps.dtype == torch.float16), _p(hi),
+                                       _p(lo) if split else ctypes.c_void_p(0), _i(T), _i(C), _i(H * W),
+                                       _stream(fmaps))
+    _lib.check(st, "pack_fmaps")
+    return hi, lo
+
+
+def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_levels=4, gauss_radius=4,
+                  precision=None, round_half=False):
+    """CorrBlock.__init__'s data path (corr.py:61-86) in one tcgen05/TMA kernel: all-pairs volume of edge
+    (ii[e] -> jj[e]) + Gaussian residual (gaussianMask_cuda.py:84-86) + num_levels-level average pyramid.
+    hi/lo from pack_fmaps; ii, jj int32 [E]; means, covs [E,H,W,2]; den [E,H,W] = 6.28*sqrt(cov_x*cov_y).
+    Returns [lvl0 [E,H,W,H,W], lvl1 [E,H,W,H/2,W/2], ...]."""
+    if hi.dtype != torch.float16 or not hi.is_cuda or hi.dim() != 3 or not hi.is_contiguous():
+        raise RuntimeError("hi must be a contiguous CUDA fp16 tensor [T,H*W,C] (see pack_fmaps)")
+    T, P, C = hi.shape
+    if P != H * W:
+        raise RuntimeError(f"hi has {P} pixels per map, expected H*W = {H * W}")
+    if precision is None:
+        precision = 2 if lo is not None else 1
+    if precision == 2 and (lo is None or lo.shape != hi.shape or lo.dtype != torch.float16):
+        raise RuntimeError("precision 2 needs the lo plane from pack_fmaps(split=True)")
+    for t, name in ((ii, "ii"), (jj, "jj")):
+        if not (t.is_cuda and t.dtype == torch.int32 and t.dim() == 1 and t.is_contiguous()):
+            raise RuntimeError(f"{name} must be a contiguous CUDA int32 vector")
+    E = ii.numel()
+    if jj.numel() != E:
+        raise RuntimeError("ii and jj must have the same length")
+    use_gauss = gauss_radius > 0 and means is not None
+    if use_gauss:
+        _chk(means, "means", 4); _chk(covs, "covs", 4); _chk(den, "den", 3)
+        if tuple(means.shape) != (E, H, W, 2) or tuple(covs.shape) != (E, H, W, 2) or tuple(den.shape) != (E, H, W):
+            raise RuntimeError("means/covs must be [E,H,W,2] and den [E,H,W]")
+    if not 1 <= num_levels <= 4:
+        raise RuntimeError("num_levels must be in 1..4")
+    lv = [torch.empty(E, H, W, H >> l, W >> l, dtype=torch.float32, device=hi.device) for l in range(num_levels)]
+    null = ctypes.c_void_p(0)
+    ptr = [_p(t) for t in lv] + [null] * (4 - num_levels)
+    with torch.cuda.device(hi.device):
+        st = _lib.lib().lgu_build_pyramid(_p(hi), _p(lo) if precision == 2 else null, _p(ii), _p(jj),
+                                          _p(means) if use_gauss else null, _p(covs) if use_gauss else null,
+                                          _p(den) if use_gauss else null, ptr[0], ptr[1], ptr[2], ptr[3],
+                                          _i(T), _i(E), _i(H), _i(W), _i(C), _i(gauss_radius if use_gauss else 0),
+                                          _i(precision), _i(1 if round_half else 0), _stream(hi))
+    _lib.check(st, "build_pyramid")
+    return lv

@@ -1,0 +1,52 @@
+"""Minimal single-op driver for ncu captures:  python tools/prof_one.py <op> [--edges E] [--lvl L] [--iters N]
+ops: fwd | fwd1 | bwd | gauss | gauss_bwd"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import inputs  # noqa: E402
+import lgu_slam_b200  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("op")
+    ap.add_argument("--edges", type=int, default=48)
+    ap.add_argument("--lvl", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=3)
+    a = ap.parse_args()
+    ops = lgu_slam_b200.ops
+    E, H, W, r = a.edges, 48, 64, 3
+    H2, W2 = H >> a.lvl, W >> a.lvl
+    dev = "cuda"
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    vol = torch.randn(E, H, W, H2, W2, device=dev, generator=g)
+    coords = inputs.make_coords(E, H, W, H2, W2, inputs.gen(2)).to(dev)
+    off = inputs.make_offset(E, H, W, r, inputs.gen(7), zero=(a.lvl >= 2)).to(dev)
+    grad = torch.randn(E, 7, 7, H, W, device=dev, generator=g)
+    c = inputs.gaussian_case(1, H, W, H2, W2, 4, seed=3)
+    means = c["means"].to(dev).expand(E, -1, -1, -1).contiguous()
+    covs = c["covs"].to(dev).expand(E, -1, -1, -1).contiguous()
+    for _ in range(a.iters):
+        if a.op == "fwd":
+            ops.defCorr_index_forward(vol, coords, off, r)
+        elif a.op == "bwd":
+            ops.defCorr_index_backward(vol, coords, off, grad, r)
+        elif a.op == "gauss":
+            ops.gaussianMask(means, covs, vol, 4)
+        elif a.op == "gauss_bwd":
+            ops.gaussianMask_backward(means, covs, vol, vol, 4)
+        elif a.op == "fwd1":
+            ops.corr_index_forward(vol, coords, 1)
+        else:
+            raise SystemExit("unknown op")
+    torch.cuda.synchronize()
+    print("done", a.op)
+
+
+if __name__ == "__main__":
+    main()
