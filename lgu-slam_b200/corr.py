@@ -1,0 +1,296 @@
+"""Host-side mirror of the reference's correlation frontend, on the sm_100a operator layer.
+
+Same class names, constructor arguments, call signatures, return values and in-place side effects as
+/root/reference/droid_slam/modules/corr.py (CorrSampler :10-24, DefCorrSampler :26-42, CorrBlock :53-152,
+AltCorrBlock :155-249) and /root/reference/droid_slam/gaussianMask_cuda.py (GaussianMaskCuda :7-23,
+GaussianMask :35-88), so `factor_graph.py`, `droid_net.py` and `motion_filter.py` can import them from here
+instead.  What differs is underneath:
+
+  * CorrBlock.__init__ runs ONE fused tcgen05/TMA kernel (ops.build_pyramid) for the volume, the Gaussian
+    residual and the 4-level pyramid instead of matmul -> .float() -> gaussianMask -> div -> add -> 3 pools;
+    the per-op path (`fused=False`) is kept and is what the fused path is tested against;
+  * every lookup goes through the C ABI in include/lgu_corr.h; there is no CPU path.
+
+The learned heads (ofsMap / ofs_residual convs, the GaussianMask MLP) stay torch modules, as in the reference.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+GAUSS_RADIUS = 4          # gaussianMask_cuda.py:84 (a 9x9 window, not the lookup radius)
+MASK_RADIUS = 1           # corr.py:94,202: the uncertainty mask is an r=1 lookup on level 1
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions (same contracts as the reference's)
+# ------------------------------------------------------------------------------------------------
+class CorrSampler(torch.autograd.Function):
+    """corr.py:10-24: plain bilinear window lookup; gradient for the volume only."""
+
+    @staticmethod
+    def forward(ctx, volume, coords, radius):
+        ctx.save_for_backward(volume, coords)
+        ctx.radius = radius
+        corr, = ops.corr_index_forward(volume, coords, radius)
+        return corr
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        volume, coords = ctx.saved_tensors
+        grad_volume, = ops.corr_index_backward(volume, coords, grad_output.contiguous(), ctx.radius)
+        return grad_volume, None, None
+
+
+class DefCorrSampler(torch.autograd.Function):
+    """corr.py:26-42: deformable lookup; gradients for the volume and the offsets, none for coords.
+    The offset tensor handed in is mutated (centre tap zeroed, quirk Q5) and that mutated tensor is what
+    backward sees, as in the reference."""
+
+    @staticmethod
+    def forward(ctx, volume, coords, offset, radius):
+        offset = offset.float()
+        volume = volume.float()
+        ctx.save_for_backward(volume, coords, offset)
+        ctx.radius = radius
+        corr, = ops.defCorr_index_forward(volume, coords, offset, radius)
+        return corr
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        volume, coords, offset = ctx.saved_tensors
+        grad_volume, grad_offset = ops.defCorr_index_backward(volume, coords, offset, grad_output.contiguous(),
+                                                              ctx.radius)
+        return grad_volume, None, grad_offset, None
+
+
+class GaussianMaskCuda(torch.autograd.Function):
+    """gaussianMask_cuda.py:7-23: gradients for mean and cov only (the reference returns None for corr)."""
+
+    @staticmethod
+    def forward(ctx, mean, cov, corr, radius):
+        mean = mean.float()
+        cov = cov.float()
+        ctx.save_for_backward(mean, cov, corr)
+        ctx.radius = radius
+        corr1, = ops.gaussianMask(mean, cov, corr, radius)
+        return corr1
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        mean, cov, corr = ctx.saved_tensors
+        gm, gc = ops.gaussianMask_backward(mean, cov, corr, grad_output.contiguous(), ctx.radius)
+        return gm, gc, None, None
+
+
+def per_Corr_Normalization(x, normalIndex, eps=1e-5):
+    """corr.py:44-51 / gaussianMask_cuda.py:26-33: standardise over `normalIndex` (biased variance + eps)."""
+    mean = torch.mean(x, dim=normalIndex, keepdim=True)
+    std = torch.sqrt(torch.var(x, dim=normalIndex, unbiased=False, keepdim=True) + eps)
+    return (x - mean) / std
+
+
+# ------------------------------------------------------------------------------------------------
+# GaussianMask module
+# ------------------------------------------------------------------------------------------------
+class GaussianMask(nn.Module):
+    """gaussianMask_cuda.py:35-88.  Parameter names (map, meanMap, covMap) match the reference so its
+    checkpoints load; `params()` exposes (mean, cov, det) for the fused build."""
+
+    def __init__(self, h, w):
+        super().__init__()
+        self.meanMap = nn.Linear(16, 2)
+        self.covMap = nn.Linear(16, 2)
+        self.map = nn.Linear(256, 16)
+        nn.init.zeros_(self.meanMap.weight)
+        nn.init.zeros_(self.meanMap.bias)
+        for lin in (self.covMap, self.map):
+            nn.init.normal_(lin.weight, 0.0, math.sqrt(2.0 / lin.out_features))
+            nn.init.zeros_(lin.bias)
+        self.mapA = nn.Sequential(self.map, nn.Tanh())
+        ys, xs = torch.meshgrid(torch.arange(h).float(), torch.arange(w).float(), indexing="ij")
+        self.coord = torch.stack([xs, ys], dim=-1)       # [h,w,2], channel 0 = x (plain attribute, like the reference)
+
+    def params(self, x):
+        """x [E,h,w,256] -> mean [E,h,w,2] (pixel grid + learned shift), cov [E,h,w,2] in (0.05, 5.05), det [E,h*w]."""
+        b, h, w, _ = x.shape
+        tt = self.mapA(x)
+        mean_ofs = self.meanMap(tt).view(b, h, w, 2)
+        c = per_Corr_Normalization(self.covMap(tt).view(b, h * w, 2), [1, 2])
+        c = torch.sigmoid(c) * 5 + 0.05
+        det = c[:, :, 0] * c[:, :, 1]
+        cov = c.view(b, h, w, 2).float()
+        mean = self.coord.to(device=x.device, dtype=cov.dtype).expand(b, h, w, 2) + mean_ofs
+        return mean, cov, det
+
+    def forward(self, x, corr):
+        b, h, w, _ = x.shape
+        mean, cov, det = self.params(x)
+        corr1 = GaussianMaskCuda.apply(mean.contiguous(), cov.contiguous(), corr, GAUSS_RADIUS)
+        corr1 = corr1 / (6.28 * torch.sqrt(det).view(b, h, w, 1, 1)) + corr
+        return corr1, mean, det
+
+
+# ------------------------------------------------------------------------------------------------
+# offsets (corr.py:117-135 / 217-235)
+# ------------------------------------------------------------------------------------------------
+def _generate_offsets(ofsMap, ofs_residual, t):
+    """t [E,256,h,w] -> 4 per-level offset tensors [E,h,w,98]; levels 2 and 3 are zeros."""
+    _, _, h, w = t.shape
+    o0 = ofsMap(t)
+    o1 = F.interpolate(ofs_residual(F.avg_pool2d(t, kernel_size=2, stride=2)), (h, w))
+    o0 = torch.tanh(per_Corr_Normalization(o0, [1, 2, 3])) * 4
+    o1 = (torch.tanh(per_Corr_Normalization(o1, [1, 2, 3])) * 4 + o0) / 2
+    o0 = o0.permute(0, 2, 3, 1)
+    o1 = o1.permute(0, 2, 3, 1)
+    z = torch.zeros_like(o0)
+    return [o0, o1, z.detach(), z.clone().detach()]
+
+
+# ------------------------------------------------------------------------------------------------
+# CorrBlock
+# ------------------------------------------------------------------------------------------------
+class CorrBlock:
+    """corr.py:53-152.  Attributes kept: corr_pyramid (list of [E,h,w,h>>l,w>>l]), offset (list of [E,h,w,98]),
+    mean_n, theta, num_levels, radius.  `fused=None` picks the fused build whenever no gradient can flow into it
+    (inference: torch.no_grad, as FactorGraph / MotionFilter run) and the per-op autograd path otherwise."""
+
+    def __init__(self, ofsMap, ofs_residual, GA, fmap1, fmap2, num_levels=4, radius=3, fused=None,
+                 autocast_rounding=None):
+        self.num_levels = num_levels
+        self.radius = radius
+        self.GA = GA
+        self.ofsMap = ofsMap
+        self.ofs_residual = ofs_residual
+        b, n, c, h, w = fmap1.shape
+        E = b * n
+        needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad or any(
+            p.requires_grad for p in GA.parameters()))
+        if fused is None:
+            fused = not needs_grad and w == 64 and h % 8 == 0 and c == 128
+        # under autocast the reference's matmul emits fp16 (factor_graph.py:90, corr.py:64); reproduce on request
+        if autocast_rounding is None:
+            autocast_rounding = False
+
+        t = torch.cat((fmap1.reshape(E, c, h, w), fmap2.reshape(E, c, h, w)), dim=1)
+        self.offset = _generate_offsets(ofsMap, ofs_residual, t.float())
+        self.t = t.permute(0, 2, 3, 1).contiguous()
+
+        if fused:
+            mean, cov, det = GA.params(self.t.float())
+            frames = torch.cat((fmap1.reshape(E, c, h, w), fmap2.reshape(E, c, h, w)), dim=0).contiguous()
+            split = frames.dtype == torch.float32
+            hi, lo = ops.pack_fmaps(frames, split=split)
+            idx = torch.arange(2 * E, dtype=torch.int32, device=frames.device)
+            den = (6.28 * torch.sqrt(det)).view(E, h, w).float().contiguous()
+            self.corr_pyramid = ops.build_pyramid(hi, lo, idx[:E].contiguous(), idx[E:].contiguous(), h, w,
+                                                  means=mean.float().contiguous(), covs=cov.contiguous(), den=den,
+                                                  num_levels=num_levels, gauss_radius=GAUSS_RADIUS,
+                                                  round_half=autocast_rounding)
+        else:
+            corr = CorrBlock.corr(fmap1, fmap2).view(E, h, w, h, w).float()
+            corr, mean, det = GA(self.t.float(), corr)
+            self.corr_pyramid = []
+            cur = corr.reshape(E * h * w, 1, h, w)
+            for i in range(num_levels):
+                self.corr_pyramid.append(cur.view(E, h, w, h >> i, w >> i))
+                cur = F.avg_pool2d(cur, 2, stride=2)
+        self.mean_n = mean.view(b, n, h, w, 2)
+        self.theta = 2 * det.view(b, n, h, w)
+
+    def __call__(self, coords):
+        batch, num, ht, wd, _ = coords.shape
+        E, rd = batch * num, 2 * self.radius + 1
+        coords = coords.permute(0, 1, 4, 2, 3).contiguous().view(E, 2, ht, wd)
+
+        m = CorrSampler.apply(self.corr_pyramid[1], coords / 2, MASK_RADIUS)
+        var = torch.var(m.permute(0, 3, 4, 1, 2), dim=[3, 4])
+        self.offset[1] = self.offset[1] * torch.sigmoid(var).view(E, ht, wd, 1)     # cumulative per call (quirk Q7)
+
+        out = []
+        for i in range(self.num_levels):
+            o = self.offset[i].contiguous().view(E, ht, wd, rd, rd, 2)
+            corr = DefCorrSampler.apply(self.corr_pyramid[i], coords / 2 ** i, o, self.radius)
+            out.append(corr.view(batch, num, -1, ht, wd))
+        return torch.cat(out, dim=2), self.mean_n, self.theta
+
+    def cat(self, other):
+        for i in range(self.num_levels):
+            self.corr_pyramid[i] = torch.cat([self.corr_pyramid[i], other.corr_pyramid[i]], 0)
+            self.offset[i] = torch.cat([self.offset[i], other.offset[i]], 0)
+        return self
+
+    def __getitem__(self, index):
+        for i in range(self.num_levels):
+            self.corr_pyramid[i] = self.corr_pyramid[i][index]
+            self.offset[i] = self.offset[i][index]
+        return self
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        """corr.py:144-152, all-pairs correlation through torch (the differentiable per-op path)."""
+        batch, num, dim, ht, wd = fmap1.shape
+        f1 = fmap1.reshape(batch * num, dim, ht * wd) / 4.0
+        f2 = fmap2.reshape(batch * num, dim, ht * wd) / 4.0
+        return torch.matmul(f1.transpose(1, 2), f2).view(batch, num, 1, ht * wd, ht, wd)
+
+
+# ------------------------------------------------------------------------------------------------
+# AltCorrBlock (backend, no volume)
+# ------------------------------------------------------------------------------------------------
+class AltCorrBlock:
+    """corr.py:155-249: on-the-fly correlation for global BA.  `strict_ref=True` keeps the reference's
+    offset-slab indexing (quirk Q2: with S == 1 every edge of a chunk reads edge 0's offsets)."""
+
+    def __init__(self, ofsMap, ofs_residual, GA, fmaps, num_levels=4, radius=3, strict_ref=True):
+        self.num_levels = num_levels
+        self.radius = radius
+        self.GA = GA
+        self.ofsMap = ofsMap
+        self.ofs_residual = ofs_residual
+        self.strict_ref = strict_ref
+        self.offset = []
+        B, N, C, H, W = fmaps.shape
+        cur = fmaps.reshape(B * N, C, H, W) / 4.0
+        self.pyramid = []
+        for i in range(num_levels):
+            self.pyramid.append(cur.permute(0, 2, 3, 1).contiguous().view(B, N, H >> i, W >> i, C))
+            cur = F.avg_pool2d(cur, 2, stride=2)
+
+    def corr_fn(self, coords, ii, jj):
+        B, N, H, W, S, _ = coords.shape
+        rd = 2 * self.radius + 1
+        coords = coords.permute(0, 1, 4, 2, 3, 5)
+        f1 = self.pyramid[0][:, ii]
+        f1 = f1.reshape((B * N,) + f1.shape[2:])
+        f2 = self.pyramid[0][:, jj]
+        f2 = f2.reshape((B * N,) + f2.shape[2:])
+        t = torch.cat(((f1 * 4.0).permute(0, 3, 1, 2), (f2 * 4.0).permute(0, 3, 1, 2)), dim=1).float()
+        self.offset = _generate_offsets(self.ofsMap, self.ofs_residual, t)
+        f1 = f1.float().contiguous()
+
+        out = []
+        for i in range(self.num_levels):
+            f2_i = self.pyramid[i][:, jj]
+            f2_i = f2_i.reshape((B * N,) + f2_i.shape[2:]).float().contiguous()
+            coords_i = (coords / 2 ** i).reshape(B * N, S, H, W, 2).contiguous()
+            if i == 1:
+                m, = ops.altcorr_forward(f1, f2_i, coords_i, MASK_RADIUS)
+                m = m.permute(0, 1, 3, 4, 2).contiguous().view(N, H, W, 3, 3)       # corr.py:203 (assumes B == S == 1)
+                self.offset[1] = self.offset[1] * torch.sigmoid(torch.var(m, dim=[3, 4])).view(B * N, H, W, 1)
+            o = self.offset[i].contiguous().view(B * N, H, W, rd, rd, 2).float()
+            corr, = ops.lowMem_defSample(f1, f2_i, coords_i, o, self.radius, strict_ref=self.strict_ref)
+            out.append(corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2))
+        return torch.cat(out, dim=2)
+
+    def __call__(self, coords, ii, jj):
+        squeeze = coords.dim() == 5
+        if squeeze:
+            coords = coords.unsqueeze(dim=-2)
+        corr = self.corr_fn(coords, ii, jj)
+        if squeeze:
+            corr = corr.squeeze(dim=-1)
+        return corr.contiguous()

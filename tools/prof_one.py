@@ -1,5 +1,5 @@
 """Minimal single-op driver for ncu captures:  python tools/prof_one.py <op> [--edges E] [--lvl L] [--iters N]
-ops: fwd | fwd1 | bwd | gauss | gauss_bwd"""
+ops: fwd | fwd1 | bwd | gauss | gauss_bwd | build"""
 import argparse
 import os
 import sys
@@ -40,6 +40,14 @@ def main():
             ops.gaussianMask(means, covs, vol, 4)
         elif a.op == "gauss_bwd":
             ops.gaussianMask_backward(means, covs, vol, vol, 4)
+        elif a.op == "build":
+            if "bp" not in globals():
+                global bp
+                fc = inputs.frontend_case(E=E, T=20, seed=5, half_fmaps=True)
+                hi, _ = ops.pack_fmaps(fc["fmaps"].half().to(dev))
+                den = (6.28 * torch.sqrt(fc["covs"][..., 0] * fc["covs"][..., 1])).to(dev).contiguous()
+                bp = (hi, fc["ii"].to(dev), fc["jj"].to(dev), fc["means"].to(dev), fc["covs"].to(dev), den)
+            ops.build_pyramid(bp[0], None, bp[1], bp[2], H, W, means=bp[3], covs=bp[4], den=bp[5])
         elif a.op == "fwd1":
             ops.corr_index_forward(vol, coords, 1)
         else:
