@@ -8,8 +8,8 @@ the hot path over that edge batch:
 
     pack      fmaps [T,128,48,64] -> channels-last fp16 planes            (1 launch, ours)
     build     all-pairs volume + Gaussian residual + 4-level pyramid       (1 launch, tcgen05/TMA, ours)
-    lookup    r=1 mask lookup on level 1 + 4 x deformable r=3 lookups      (5 launches, ours; torch glue as in
-              CorrBlock.__call__, corr.py:88-109: permute, /2^l, var, sigmoid, mul, cat)
+    lookup    r=1 mask lookup on level 1 -> var -> sigmoid -> offset[1] *= mask -> 4 x deformable r=3 lookups -> cat
+              (CorrBlock.__call__, corr.py:88-109)                         (1 launch, TMA-staged, ours)
     lookup^T  4 x defCorr_index_backward + corr_index_backward             (5 launches, ours; dense volume grads)
     gauss^T   gaussianMask_backward                                        (1 launch, ours)
 
@@ -46,7 +46,8 @@ def algorithmic_bytes_per_edge():
     d = {
         "pack": 2 * C * P * 2 * 2 / 1.0 * 0 + (C * P * 2 + C * P * 2),      # read fp16 NCHW + write fp16 NHWC (per frame, ~per edge)
         "build": 2 * P * C * 2 + 16 * P + 4 * P * sum(QS),
-        "lookup_fwd": P * ((8 + 64 + 36) + sum(8 + 8 * TAPS + g + 4 * TAPS for g in gather)),
+        # fused 4-level lookup: coords once, offsets of levels 0-1 only (read + off1 written back), gathers, 196-ch out
+        "lookup_fwd": P * (8 + 2 * 8 * TAPS + 8 * TAPS + sum(gather) + 64 + 4 * LEVELS * TAPS),
         "lookup_bwd": P * ((8 + 36 + 4 * QS[1]) + sum(8 + 8 * TAPS + 4 * TAPS + 8 * TAPS + g + 4 * q
                                                       for g, q in zip(gather, QS))),
         "gauss_bwd": P * (2 * 81 * 4 + 32),
@@ -126,12 +127,14 @@ class Workload:
         self.host = make_host_inputs(E, T, seed, pin=True)
         self.d = {k: v.to(device) for k, v in self.host.items()}
         self.zero_off = torch.zeros(E, H, W, 2 * TAPS, device=device)
+        self.zero_off2 = torch.zeros(E, H, W, 2 * TAPS, device=device)
         g = torch.Generator(device=device); g.manual_seed(seed)
         # inputs of the Gaussian backward: the raw (pre-Gaussian) volume and the upstream gradient
         hi, _ = self.ops.pack_fmaps(self.d["fmaps"])
         self.v_raw = self.ops.build_pyramid(hi, None, self.d["ii"], self.d["jj"], H, W, num_levels=1, gauss_radius=0)[0]
         self.g_vol = torch.randn(E, H, W, H, W, device=device, generator=g)
-        self.launches_per_step = 13
+        self.g_mask = torch.randn(E, 3, 3, H, W, device=device, generator=g)   # upstream grad of the r=1 mask lookup
+        self.launches_per_step = 9
         self.ev = None
 
     def step(self, d=None, record=None):
@@ -150,20 +153,17 @@ class Workload:
         pyr = ops.build_pyramid(hi, None, d["ii"], d["jj"], H, W, means=d["means"], covs=d["covs"], den=d["den"],
                                 num_levels=LEVELS, gauss_radius=GR, precision=1)
         mark("build")
-        # ---- CorrBlock.__call__ (corr.py:88-109)
+        # ---- CorrBlock.__call__ (corr.py:88-109): one fused TMA-staged launch (mask lookup + 4 deformable levels)
+        off0, off1 = d["off0"].clone(), d["off1"].clone()          # the block's per-edge offset state (mutated, Q5/Q7)
+        corr = ops.corr_lookup_fused(pyr, d["coords"], off0, off1, R)
+        mark("lookup_fwd")
+        # ---- backward of the lookups (corr.py:19-24,37-42), per-level operators, dense volume grads
         c = d["coords"].permute(0, 3, 1, 2).contiguous()
         cl = [(c / 2 ** l).contiguous() for l in range(LEVELS)]
-        m, = ops.corr_index_forward(pyr[1], cl[1], 1)
-        mask = torch.sigmoid(torch.var(m.permute(0, 3, 4, 1, 2), dim=[3, 4])).view(E, H, W, 1)
-        offs = [d["off0"].clone(), d["off1"] * mask, self.zero_off.clone(), self.zero_off.clone()]
-        offs = [o.view(E, H, W, 2 * R + 1, 2 * R + 1, 2) for o in offs]
-        outs = [ops.defCorr_index_forward(pyr[l], cl[l], offs[l], R)[0].view(E, TAPS, H, W) for l in range(LEVELS)]
-        corr = torch.cat(outs, dim=1)
-        mark("lookup_fwd")
-        # ---- backward of the lookups (corr.py:19-24,37-42)
+        offs = [o.view(E, H, W, 2 * R + 1, 2 * R + 1, 2) for o in (off0, off1, self.zero_off, self.zero_off2)]
         gl = d["corr_grad"].view(E, LEVELS, 2 * R + 1, 2 * R + 1, H, W)
         grads = [ops.defCorr_index_backward(pyr[l], cl[l], offs[l], gl[:, l].contiguous(), R) for l in range(LEVELS)]
-        gmask, = ops.corr_index_backward(pyr[1], cl[1], m, 1)      # upstream grad of the mask lookup: same shape as m
+        gmask, = ops.corr_index_backward(pyr[1], cl[1], self.g_mask, 1)
         mark("lookup_bwd")
         gm, gc = ops.gaussianMask_backward(d["means"], d["covs"], self.v_raw, self.g_vol, GR)
         mark("gauss_bwd")

@@ -144,8 +144,8 @@ def _generate_offsets(ofsMap, ofs_residual, t):
     o1 = F.interpolate(ofs_residual(F.avg_pool2d(t, kernel_size=2, stride=2)), (h, w))
     o0 = torch.tanh(per_Corr_Normalization(o0, [1, 2, 3])) * 4
     o1 = (torch.tanh(per_Corr_Normalization(o1, [1, 2, 3])) * 4 + o0) / 2
-    o0 = o0.permute(0, 2, 3, 1)
-    o1 = o1.permute(0, 2, 3, 1)
+    o0 = o0.permute(0, 2, 3, 1).contiguous()        # [E,h,w,98]: the layout the kernels read, materialised once
+    o1 = o1.permute(0, 2, 3, 1).contiguous()
     z = torch.zeros_like(o0)
     return [o0, o1, z.detach(), z.clone().detach()]
 
@@ -201,9 +201,26 @@ class CorrBlock:
         self.mean_n = mean.view(b, n, h, w, 2)
         self.theta = 2 * det.view(b, n, h, w)
 
+    def _can_fuse_lookup(self, coords):
+        if torch.is_grad_enabled() and (coords.requires_grad or any(
+                t.requires_grad for t in self.corr_pyramid + self.offset)):
+            return False
+        ht, wd = coords.shape[2:4]
+        return (self.num_levels == 4 and self.radius == 3 and wd % 32 == 0 and ht % 8 == 0
+                and all(t.dtype == torch.float32 for t in self.corr_pyramid))
+
     def __call__(self, coords):
         batch, num, ht, wd, _ = coords.shape
         E, rd = batch * num, 2 * self.radius + 1
+        if self._can_fuse_lookup(coords):
+            # one TMA-staged launch: mask lookup + var + sigmoid + offset[1] *= mask + 4 deformable lookups + cat
+            for i in (0, 1):
+                if not (self.offset[i].is_contiguous() and self.offset[i].dtype == torch.float32):
+                    self.offset[i] = self.offset[i].float().contiguous()
+            pyr = [t if t.is_contiguous() else t.contiguous() for t in self.corr_pyramid]
+            out = ops.corr_lookup_fused(pyr, coords.reshape(E, ht, wd, 2).float().contiguous(), self.offset[0],
+                                        self.offset[1], self.radius)
+            return out.view(batch, num, -1, ht, wd), self.mean_n, self.theta
         coords = coords.permute(0, 1, 4, 2, 3).contiguous().view(E, 2, ht, wd)
 
         m = CorrSampler.apply(self.corr_pyramid[1], coords / 2, MASK_RADIUS)

@@ -238,3 +238,35 @@ def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_lev
                                           _i(precision), _i(1 if round_half else 0), _stream(hi))
     _lib.check(st, "build_pyramid")
     return lv
+
+
+def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False):
+    """CorrBlock.__call__'s data path (corr.py:88-109) in one TMA-staged kernel.
+    pyramid: 4 tensors [E,H,W,H>>l,W>>l]; coords [E,H,W,2] (x,y; level-0 units); off0, off1 [E,H,W,98] or
+    [E,H,W,7,7,2] -- both mutated in place: centre taps zeroed (Q5), off1 multiplied by this call's uncertainty
+    mask (Q7).  Returns corr [E,196,H,W] (and the mask [E,H,W] if return_mask)."""
+    if len(pyramid) != 4:
+        raise RuntimeError("corr_lookup_fused needs a 4-level pyramid")
+    E, H, W = pyramid[0].shape[:3]
+    for l, t in enumerate(pyramid):
+        _chk(t, f"pyramid[{l}]", 5)
+        if tuple(t.shape) != (E, H, W, H >> l, W >> l):
+            raise RuntimeError(f"pyramid[{l}] shape {tuple(t.shape)} != {(E, H, W, H >> l, W >> l)}")
+    _chk(coords, "coords", 4)
+    if tuple(coords.shape) != (E, H, W, 2):
+        raise RuntimeError(f"coords shape {tuple(coords.shape)} != {(E, H, W, 2)}")
+    rd = 2 * int(radius) + 1
+    for name, o in (("off0", off0), ("off1", off1)):
+        if not (isinstance(o, torch.Tensor) and o.is_cuda and o.is_contiguous() and o.dtype == torch.float32):
+            raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor")
+        if o.numel() != E * H * W * rd * rd * 2:
+            raise RuntimeError(f"{name} has {o.numel()} elements, expected {E * H * W * rd * rd * 2}")
+    corr = torch.empty(E, 4 * rd * rd, H, W, dtype=torch.float32, device=coords.device)
+    mask = torch.empty(E, H, W, dtype=torch.float32, device=coords.device) if return_mask else None
+    with torch.cuda.device(coords.device):
+        st = _lib.lib().lgu_corr_lookup_fused(_p(pyramid[0]), _p(pyramid[1]), _p(pyramid[2]), _p(pyramid[3]),
+                                              _p(coords), _p(off0), _p(off1), _p(corr),
+                                              _p(mask) if return_mask else ctypes.c_void_p(0),
+                                              _i(E), _i(H), _i(W), _i(4), _i(radius), _stream(coords))
+    _lib.check(st, "corr_lookup_fused")
+    return (corr, mask) if return_mask else corr

@@ -1,0 +1,125 @@
+"""GPU tests of the host-side mirror (lgu-slam_b200/corr.py): CorrBlock / AltCorrBlock / GaussianMask keep the
+reference's interface (corr.py:53-152,155-249; gaussianMask_cuda.py:35-88) and their fused inference paths agree
+with their own per-operator (autograd) paths, which in turn are the reference's op sequence on the parity-tested
+operators."""
+import pytest
+import torch
+import torch.nn as nn
+
+import inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _modules(dev, seed=0):
+    import lgu_slam_b200
+    from importlib import import_module
+    corr = import_module("lgu-slam_b200.corr")
+    torch.manual_seed(seed)
+    ofsMap = nn.Conv2d(256, 98, 3, padding=1).to(dev)
+    ofs_residual = nn.Conv2d(256, 98, 3, padding=1).to(dev)
+    GA = corr.GaussianMask(48, 64).to(dev)
+    with torch.no_grad():      # the reference zero-initialises meanMap (droid_net.py:149-156); use live values here
+        GA.meanMap.weight.normal_(0, 0.3)
+        GA.meanMap.bias.normal_(0, 0.3)
+    return corr, ofsMap, ofs_residual, GA
+
+
+def test_corrblock_fused_inference_matches_per_op_path():
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev)
+    g = inputs.gen(7)
+    b, n = 1, 3
+    fmap1 = torch.randn(b, n, 128, 48, 64, generator=g).half().float().to(dev)
+    fmap2 = torch.randn(b, n, 128, 48, 64, generator=g).half().float().to(dev)
+    coords = inputs.make_coords(n, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(b, n, 48, 64, 2).to(dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            blk_f = corr.CorrBlock(ofsMap, ofs_residual, GA, fmap1, fmap2, fused=True)
+            blk_p = corr.CorrBlock(ofsMap, ofs_residual, GA, fmap1, fmap2, fused=False)
+            for l in range(4):
+                assert blk_f.corr_pyramid[l].shape == (n, 48, 64, 48 >> l, 64 >> l)
+                err = (blk_f.corr_pyramid[l] - blk_p.corr_pyramid[l]).abs().max().item()
+                assert err <= 2e-5, f"pyramid level {l}: {err}"
+            assert torch.allclose(blk_f.mean_n, blk_p.mean_n) and torch.allclose(blk_f.theta, blk_p.theta)
+            # lookups: fused launch vs per-op autograd functions on the SAME pyramid
+            blk_p.corr_pyramid = [t.clone() for t in blk_f.corr_pyramid]
+            blk_p._can_fuse_lookup = lambda c: False
+            for it in range(2):                                     # second call checks the cumulative mask (Q7)
+                out_f, mean_f, theta_f = blk_f(coords)
+                out_p, _, _ = blk_p(coords)
+                assert out_f.shape == (b, n, 196, 48, 64)
+                assert (out_f - out_p).abs().max().item() <= 1e-5, f"call {it}"
+                assert (blk_f.offset[1] - blk_p.offset[1].reshape(blk_f.offset[1].shape)).abs().max().item() <= 1e-5
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_corrblock_training_path_has_gradients():
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 1)
+    g = inputs.gen(8)
+    fmap1 = torch.randn(1, 2, 128, 48, 64, generator=g).to(dev).requires_grad_()
+    fmap2 = torch.randn(1, 2, 128, 48, 64, generator=g).to(dev).requires_grad_()
+    coords = inputs.make_coords(2, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, 2, 48, 64, 2).to(dev)
+    blk = corr.CorrBlock(ofsMap, ofs_residual, GA, fmap1, fmap2)
+    out, mean_n, theta = blk(coords)
+    assert out.shape == (1, 2, 196, 48, 64) and mean_n.shape == (1, 2, 48, 64, 2) and theta.shape == (1, 2, 48, 64)
+    (out.square().mean() + mean_n.mean() + theta.mean()).backward()
+    for t in (fmap1, fmap2, ofsMap.weight, ofs_residual.weight, GA.covMap.weight, GA.meanMap.weight, GA.map.weight):
+        assert t.grad is not None and torch.isfinite(t.grad).all() and t.grad.abs().sum() > 0
+
+
+def test_corrblock_cat_and_getitem_keep_edge_order():
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 2)
+    g = inputs.gen(9)
+    f1 = torch.randn(1, 3, 128, 48, 64, generator=g).half().float().to(dev)
+    f2 = torch.randn(1, 3, 128, 48, 64, generator=g).half().float().to(dev)
+    coords = inputs.make_coords(3, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, 3, 48, 64, 2).to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False       # the offset convs: TF32 would differ between batch sizes (~1e-3)
+    with torch.no_grad():
+        whole = corr.CorrBlock(ofsMap, ofs_residual, GA, f1, f2)
+        a = corr.CorrBlock(ofsMap, ofs_residual, GA, f1[:, :2], f2[:, :2])
+        b_ = corr.CorrBlock(ofsMap, ofs_residual, GA, f1[:, 2:], f2[:, 2:])
+        joined = a.cat(b_)
+        o_whole, _, _ = whole(coords)
+        o_join, _, _ = joined(coords)
+        # per-edge normalisation of the offsets makes edges independent, so the concatenated block equals the whole
+        # (up to cuDNN choosing different fp32 conv algorithms for different batch sizes)
+        assert (o_whole - o_join).abs().max().item() <= 1e-3
+        keep = torch.tensor([True, False, True], device=dev)
+        sub = whole[keep]
+        assert sub.corr_pyramid[0].shape[0] == 2 and sub.offset[1].shape[0] == 2
+    torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_altcorrblock_interface_and_shapes(oracle):
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 3)
+    g = inputs.gen(10)
+    T = 5
+    fmaps = torch.randn(1, T, 128, 48, 64, generator=g).half().to(dev)
+    ii = torch.tensor([0, 1, 2, 3], device=dev)
+    jj = torch.tensor([1, 2, 3, 4], device=dev)
+    coords = inputs.make_coords(4, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, 4, 48, 64, 2).to(dev)
+    with torch.no_grad():
+        blk = corr.AltCorrBlock(ofsMap, ofs_residual, GA, fmaps)
+        out = blk(coords, ii, jj)
+        assert out.shape == (1, 4, 196, 48, 64) and torch.isfinite(out).all()
+        # zero-offset levels (2, 3) equal the oracle's lowMem sampler on the same pooled maps
+        # AltCorrBlock keeps the buffer's dtype (fp16, depth_video.py:36): each pooled level is rounded to fp16
+        f = fmaps.float().cpu()[0] / 4.0
+        pyr = [f]
+        for _ in range(3):
+            pyr.append(torch.nn.functional.avg_pool2d(pyr[-1], 2, 2).half().float())
+        f1 = pyr[0][ii.cpu()].permute(0, 2, 3, 1).contiguous()
+        for l in (2, 3):
+            f2 = pyr[l][jj.cpu()].permute(0, 2, 3, 1).contiguous()
+            c = (coords.cpu()[0] / 2 ** l).view(4, 1, 48, 64, 2).contiguous()
+            want, = oracle.lowMem_defSample(f1, f2, c, torch.zeros(4, 48, 64, 7, 7, 2), 3)
+            got = out[0, :, 49 * l:49 * (l + 1)].cpu()
+            assert (got - want.view(4, 49, 48, 64)).abs().max().item() <= 1e-4

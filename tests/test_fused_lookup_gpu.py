@@ -1,0 +1,111 @@
+"""GPU parity of the fused 4-level lookup (lgu_corr_lookup_fused, one TMA-staged launch) against the oracle's
+composition of the reference ops (CorrBlock.__call__, corr.py:88-109): r=1 mask lookup on level 1 -> var -> sigmoid
+-> offset[1] *= mask -> four deformable r=3 lookups -> cat.
+
+Bars: levels 0, 2, 3 (their offsets do not depend on the mask) bit-exact, including the zero pattern of gated
+taps; level 1 within 1e-5 abs (its offsets are scaled by sigmoid(var), whose fp32 rounding differs between
+torch's Welford reduction and the kernel's two-pass variance by a few ulp); the in-place side effects on the
+offsets (Q5 centre-tap zeroing, Q7 cumulative mask) match within 1e-6."""
+import pytest
+import torch
+
+import inputs
+
+pytestmark = pytest.mark.gpu
+ATOL = 1e-5
+
+
+def _case(E, seed, big_offsets=False, probes=False):
+    c = inputs.frontend_case(E=E, T=max(3, E // 2), seed=seed, half_fmaps=True)
+    if big_offsets:   # offsets beyond the staged box (|o| >= 4): exercises the direct-global slow path
+        g = inputs.gen(seed + 1)
+        c["offsets"][0] = (9.0 * torch.randn(E, 48, 64, 98, generator=g)).contiguous()
+        c["offsets"][1] = (7.0 * torch.randn(E, 48, 64, 98, generator=g)).contiguous()
+    if probes:
+        co = c["coords"]
+        co[0, 0, 0] = torch.tensor([float("nan"), 3.0])
+        co[0, 0, 1] = torch.tensor([float("inf"), -float("inf")])
+        co[0, 0, 2] = torch.tensor([1e30, -1e30])
+        co[0, 0, 3] = torch.tensor([-0.0, 47.0])
+        co[0, 0, 4] = torch.tensor([63.0, 47.999])
+        co[0, 0, 5] = torch.tensor([-1.0, -1.0])
+        co[0, 0, 6] = torch.tensor([2147483648.0, 5.0])
+    return c
+
+
+def _pyramid(oracle, c):
+    f1 = c["fmaps"][c["ii"].long()].contiguous()
+    f2 = c["fmaps"][c["jj"].long()].contiguous()
+    return oracle.build_pyramid(f1, f2, c["means"], c["covs"], 4, 4, False)
+
+
+@pytest.mark.parametrize("E,seed,big,probes", [(2, 51, False, False), (3, 52, False, True), (2, 53, True, True)])
+def test_fused_lookup_matches_oracle_composition(ops, oracle, E, seed, big, probes):
+    c = _case(E, seed, big, probes)
+    pyr = _pyramid(oracle, c)
+    offs = [o.clone() for o in c["offsets"]]
+    want = oracle.corr_block_lookup(pyr, c["coords"], offs, 3)          # mutates offs like the reference
+    dev = "cuda"
+    off0, off1 = c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+    got, mask = ops.corr_lookup_fused([p.to(dev) for p in pyr], c["coords"].to(dev), off0, off1, 3, return_mask=True)
+    got = got.cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    for l in (0, 2, 3):
+        a, b = got[:, 49 * l:49 * (l + 1)], want[:, 49 * l:49 * (l + 1)]
+        assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), f"level {l} must be bit-exact"
+    a, b = got[:, 49:98], want[:, 49:98]
+    err = (torch.nan_to_num(a) - torch.nan_to_num(b)).abs().max().item()
+    assert err <= ATOL, f"level 1: max abs err {err}"
+    # side effects
+    assert torch.equal(off0.cpu(), offs[0]), "off0: centre tap zeroed in place, nothing else touched"
+    o1 = off1.cpu()
+    assert torch.equal(torch.isnan(o1), torch.isnan(offs[1]))
+    assert (torch.nan_to_num(o1) - torch.nan_to_num(offs[1])).abs().max().item() <= 1e-5
+    assert mask.shape == (E, 48, 64)
+
+
+def test_fused_lookup_is_cumulative_like_the_reference(ops, oracle):
+    """Two consecutive calls: offset[1] is re-multiplied by each call's mask (quirk Q7)."""
+    c = _case(2, 54)
+    pyr = _pyramid(oracle, c)
+    offs = [o.clone() for o in c["offsets"]]
+    g = inputs.gen(99)
+    coords2 = (c["coords"] + 0.7 * torch.randn(c["coords"].shape, generator=g)).contiguous()
+    oracle.corr_block_lookup(pyr, c["coords"], offs, 3)
+    want2 = oracle.corr_block_lookup(pyr, coords2, offs, 3)
+    dev = "cuda"
+    off0, off1 = c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+    pg = [p.to(dev) for p in pyr]
+    ops.corr_lookup_fused(pg, c["coords"].to(dev), off0, off1, 3)
+    got2 = ops.corr_lookup_fused(pg, coords2.to(dev), off0, off1, 3).cpu()
+    assert (got2 - want2).abs().max().item() <= ATOL
+
+
+def test_fused_lookup_equals_per_level_operators(ops):
+    """Against the product's own drop-in operators at the full frontend size (E=48): identical results."""
+    E = 48
+    c = inputs.frontend_case(E=E, T=20, seed=55, half_fmaps=True)
+    dev = "cuda"
+    hi, _ = ops.pack_fmaps(c["fmaps"].half().to(dev))
+    den = (6.28 * torch.sqrt(c["covs"][..., 0] * c["covs"][..., 1])).to(dev).contiguous()
+    pyr = ops.build_pyramid(hi, None, c["ii"].to(dev), c["jj"].to(dev), 48, 64, means=c["means"].to(dev),
+                            covs=c["covs"].to(dev), den=den)
+    coords = c["coords"].to(dev)
+    off0, off1 = c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+    got, mask = ops.corr_lookup_fused(pyr, coords, off0.clone(), off1.clone(), 3, return_mask=True)
+    cc = coords.permute(0, 3, 1, 2).contiguous()
+    m, = ops.corr_index_forward(pyr[1], (cc / 2).contiguous(), 1)
+    mk = torch.sigmoid(torch.var(m.permute(0, 3, 4, 1, 2), dim=[3, 4]))
+    assert (mk - mask).abs().max().item() <= 1e-6
+    offs = [off0.clone(), off1 * mask.view(E, 48, 64, 1), torch.zeros_like(off0), torch.zeros_like(off0)]
+    for l in range(4):
+        want, = ops.defCorr_index_forward(pyr[l], (cc / 2 ** l).contiguous(), offs[l].view(E, 48, 64, 7, 7, 2), 3)
+        assert torch.equal(got[:, 49 * l:49 * (l + 1)], want.view(E, 49, 48, 64)), f"level {l}"
+
+
+def test_fused_lookup_unsupported_configuration_is_reported(ops):
+    dev = "cuda"
+    pyr = [torch.zeros(1, 8, 16, 8 >> l, 16 >> l, device=dev) for l in range(4)]
+    with pytest.raises(RuntimeError, match="W%32"):
+        ops.corr_lookup_fused(pyr, torch.zeros(1, 8, 16, 2, device=dev), torch.zeros(1, 8, 16, 98, device=dev),
+                              torch.zeros(1, 8, 16, 98, device=dev), 3)

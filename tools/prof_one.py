@@ -48,6 +48,13 @@ def main():
                 den = (6.28 * torch.sqrt(fc["covs"][..., 0] * fc["covs"][..., 1])).to(dev).contiguous()
                 bp = (hi, fc["ii"].to(dev), fc["jj"].to(dev), fc["means"].to(dev), fc["covs"].to(dev), den)
             ops.build_pyramid(bp[0], None, bp[1], bp[2], H, W, means=bp[3], covs=bp[4], den=bp[5])
+        elif a.op == "fused":
+            if "fz" not in globals():
+                global fz
+                fc = inputs.frontend_case(E=E, T=20, seed=5, half_fmaps=True)
+                pyr = [torch.randn(E, H, W, H >> l, W >> l, device=dev, generator=g) for l in range(4)]
+                fz = (pyr, fc["coords"].to(dev), fc["offsets"][0].to(dev), fc["offsets"][1].to(dev))
+            ops.corr_lookup_fused(fz[0], fz[1], fz[2], fz[3].clone(), 3)
         elif a.op == "fwd1":
             ops.corr_index_forward(vol, coords, 1)
         else:

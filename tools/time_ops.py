@@ -1,0 +1,76 @@
+"""CUDA-event timing of single operators at the frontend size:  python tools/time_ops.py [--edges 48] [ops...]"""
+import argparse, os, statistics, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import inputs, lgu_slam_b200
+ops = lgu_slam_b200.ops
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b) * 1e3)
+    return statistics.median(ts), min(ts)
+
+def main():
+    ap = argparse.ArgumentParser(); ap.add_argument("--edges", type=int, default=48); ap.add_argument("which", nargs="*")
+    a = ap.parse_args(); E, H, W = a.edges, 48, 64; dev = "cuda"; P = H * W
+    c = inputs.frontend_case(E=E, T=20, seed=5, half_fmaps=True)
+    fm = c["fmaps"].half().to(dev)
+    ii, jj = c["ii"].to(dev), c["jj"].to(dev)
+    means, covs = c["means"].to(dev), c["covs"].to(dev)
+    den = (6.28 * torch.sqrt(covs[..., 0] * covs[..., 1])).contiguous()
+    hi, _ = ops.pack_fmaps(fm)
+    pyr = ops.build_pyramid(hi, None, ii, jj, H, W, means=means, covs=covs, den=den)
+    coords = c["coords"].to(dev)
+    off0, off1 = c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+    cc = coords.permute(0, 3, 1, 2).contiguous()
+    cl = [(cc / 2 ** l).contiguous() for l in range(4)]
+    offs = [off0.view(E, H, W, 7, 7, 2), off1.view(E, H, W, 7, 7, 2), torch.zeros(E, H, W, 7, 7, 2, device=dev), torch.zeros(E, H, W, 7, 7, 2, device=dev)]
+    grad = torch.randn(E, 7, 7, H, W, device=dev)
+    GB = lambda b, us: b / us / 1e3
+    res = {}
+    def rep(name, us, bytes_):
+        print(f"{name:28s} median {us[0]:8.1f} us  min {us[1]:8.1f} us   alg {bytes_/1e6:8.1f} MB  -> {GB(bytes_, us[0]):7.1f} GB/s ({GB(bytes_, us[0])/6552*100:4.1f}% of 6552)")
+    w = set(a.which)
+    def on(k): return not w or k in w
+    if on("build"):
+        rep("build_pyramid", timeit(lambda: ops.build_pyramid(hi, None, ii, jj, H, W, means=means, covs=covs, den=den)), E * 51.757e6)
+    if on("fused"):
+        o1 = off1.clone()
+        rep("corr_lookup_fused", timeit(lambda: ops.corr_lookup_fused(pyr, coords, off0, o1, 3)), E * P * 3656)
+    if on("fwd"):
+        gath = [49 * 16, 49 * 16, 256, 256]
+        for l in range(4):
+            rep(f"defCorr_index_forward l{l}", timeit(lambda: ops.defCorr_index_forward(pyr[l], cl[l], offs[l], 3)), E * P * (8 + 392 + gath[l] + 196))
+        rep("corr_index_forward r1 l1", timeit(lambda: ops.corr_index_forward(pyr[1], cl[1], 1)), E * P * (8 + 64 + 36))
+    if on("bwd"):
+        gath = [49 * 16, 49 * 16, 256, 256]
+        for l in range(4):
+            Q = (H >> l) * (W >> l)
+            rep(f"defCorr_index_backward l{l}", timeit(lambda: ops.defCorr_index_backward(pyr[l], cl[l], offs[l], grad, 3)), E * P * (8 + 392 + 196 + 392 + gath[l] + 4 * Q))
+        g1 = torch.randn(E, 3, 3, H, W, device=dev)
+        rep("corr_index_backward r1 l1", timeit(lambda: ops.corr_index_backward(pyr[1], cl[1], g1, 1)), E * P * (8 + 36 + 4 * 768))
+    if on("gauss"):
+        vol = pyr[0]
+        rep("gaussianMask", timeit(lambda: ops.gaussianMask(means, covs, vol, 4)), E * P * (81 * 4 + 4 * P + 16))
+        rep("gaussianMask_backward", timeit(lambda: ops.gaussianMask_backward(means, covs, vol, vol, 4)), E * P * (2 * 81 * 4 + 32))
+    if on("lowmem"):
+        B = E
+        lc = inputs.lowmem_case(B=B, N=1, H1=H, W1=W, H2=H, W2=W, C=128, r=3, seed=3)
+        f1 = lc["fmap1"].to(dev); co = lc["coords"].to(dev); of = lc["offset"].to(dev)
+        f2s = [lc["fmap2"].to(dev)]
+        for l in range(1, 4):
+            f2s.append(torch.nn.functional.avg_pool2d(f2s[-1].permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous())
+        for l in range(4):
+            Ql = (H >> l) * (W >> l)
+            cl_ = (co / 2 ** l).contiguous()
+            rep(f"lowMem_defSample l{l}", timeit(lambda: ops.lowMem_defSample(f1, f2s[l], cl_, of, 3), iters=5), B * (4 * P * 128 + 4 * Ql * 128 + P * (8 + 392 + 196)))
+        cl_ = (co / 2).contiguous()
+        rep("altcorr_forward r1 l1", timeit(lambda: ops.altcorr_forward(f1, f2s[1], cl_, 1), iters=5), B * (4 * P * 128 + 4 * 768 * 128 + P * (8 + 36)))
+
+if __name__ == "__main__":
+    main()
