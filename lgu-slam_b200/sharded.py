@@ -1,0 +1,169 @@
+"""Edge-sharded backend correlation over the GPUs of one box (torch.distributed, NCCL over NVLink 5 / NVSwitch).
+
+The reference is single-GPU (README.md:22).  Its global-BA path (`FactorGraph.update_lowmem`,
+/root/reference/droid_slam/factor_graph.py:255-302) walks the edge set in CHUNKS -- all edges whose source frame
+lies in [i, i+8) (`:272-279`) -- and calls `AltCorrBlock` once per chunk.  Factor-graph edges are independent
+(SURVEY.md section 8e), so the chunks are the shardable unit.  Sharding at chunk granularity -- never splitting
+a chunk -- keeps every per-chunk quantity of the reference identical on N GPUs, including the reference's
+offset-slab quirk Q2 (every edge of a chunk reads the offsets of the chunk's first edge).
+
+Collectives (only these; the lookups themselves exchange nothing):
+  1. once per backend call: all-gather of the keyframe feature maps (fp16, 786 KB / frame) so that every rank
+     holds the whole buffer and builds its own channels-last pyramid;
+  2. per BA step (optional): return of the per-edge outputs [E_local,196,H,W] -- either left sharded
+     (`gather=None`; the GRU update can run data-parallel on them), gathered on one rank (`gather="dst"`)
+     or on every rank (`gather="all"`).
+
+Everything here is host logic on top of `torch.distributed`; the `compute` callable is the AltCorrBlock of
+lgu-slam_b200/corr.py on a GPU box and may be any function with the same signature in CPU (gloo) tests.
+"""
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+FRAMES_PER_CHUNK = 8          # factor_graph.py:272 (`s = 8`)
+
+
+@dataclass
+class EdgePlan:
+    """Assignment of reference chunks to ranks.  All index tensors are int64 on the CPU."""
+    world_size: int
+    chunk_edges: List[torch.Tensor]                 # per chunk: positions (into the edge list) of its edges, ascending
+    chunk_owner: List[int]                          # per chunk: owning rank
+    rank_chunks: List[List[int]] = field(default_factory=list)      # per rank: its chunk ids, in reference order
+    rank_edges: List[torch.Tensor] = field(default_factory=list)    # per rank: edge positions, chunk by chunk
+
+    @property
+    def num_edges(self):
+        return int(sum(e.numel() for e in self.chunk_edges))
+
+    def counts(self):
+        return [int(e.numel()) for e in self.rank_edges]
+
+
+def reference_chunks(ii: torch.Tensor, jj: torch.Tensor, frames_per_chunk: int = FRAMES_PER_CHUNK):
+    """The reference's chunking rule (factor_graph.py:272-279): for i in range(0, jj.max()+1, 8):
+    v = (ii >= i) & (ii < i+8).  Returns the non-empty chunks as lists of edge positions, in loop order."""
+    ii = ii.detach().to("cpu", torch.int64)
+    jj = jj.detach().to("cpu", torch.int64)
+    if ii.numel() == 0:
+        return []
+    chunks = []
+    for i in range(0, int(jj.max()) + 1, frames_per_chunk):
+        v = torch.nonzero((ii >= i) & (ii < i + frames_per_chunk)).flatten()
+        if v.numel():
+            chunks.append(v)
+    return chunks
+
+
+def partition_edges(ii: torch.Tensor, jj: torch.Tensor, world_size: int,
+                    frames_per_chunk: int = FRAMES_PER_CHUNK) -> EdgePlan:
+    """Longest-processing-time assignment of reference chunks to ranks (cost = edge count; ties by chunk order, so
+    the plan is deterministic and identical on every rank without communication)."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    chunks = reference_chunks(ii, jj, frames_per_chunk)
+    owner = [0] * len(chunks)
+    load = [0] * world_size
+    for c in sorted(range(len(chunks)), key=lambda c: (-chunks[c].numel(), c)):
+        r = min(range(world_size), key=lambda r: (load[r], r))
+        owner[c] = r
+        load[r] += chunks[c].numel()
+    plan = EdgePlan(world_size, chunks, owner)
+    for r in range(world_size):
+        mine = [c for c in range(len(chunks)) if owner[c] == r]
+        plan.rank_chunks.append(mine)
+        plan.rank_edges.append(torch.cat([chunks[c] for c in mine]) if mine else torch.zeros(0, dtype=torch.int64))
+    return plan
+
+
+def all_gather_frames(local: torch.Tensor, group=None) -> torch.Tensor:
+    """Collective 1: every rank contributes its contiguous block of keyframe feature maps [T_r, ...] (T_r may
+    differ between ranks); returns the whole buffer [sum T_r, ...] on every rank."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    n = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    tmax = max(counts)
+    padded = local
+    if local.shape[0] != tmax:
+        padded = torch.zeros((tmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[:local.shape[0]] = local
+    out = torch.empty((world * tmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    if all(c == tmax for c in counts):
+        return out
+    return torch.cat([out[r * tmax:r * tmax + counts[r]] for r in range(world)], dim=0)
+
+
+class ShardedBackendCorr:
+    """Runs `compute(coords[:, v], ii[v], jj[v])` (AltCorrBlock.__call__, corr.py:238-249) for the chunks this
+    rank owns and returns the per-edge outputs sharded or gathered.
+
+    compute: callable(coords [1,e,H,W,2], ii [e], jj [e]) -> [1,e,CH,H,W] on `coords.device`."""
+
+    def __init__(self, compute: Callable, group=None):
+        self.compute = compute
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.plan: Optional[EdgePlan] = None
+
+    def set_edges(self, ii, jj, frames_per_chunk=FRAMES_PER_CHUNK):
+        self.plan = partition_edges(ii, jj, self.world, frames_per_chunk)
+        return self.plan
+
+    def local_lookup(self, coords, ii, jj):
+        """This rank's share: outputs [1,E_local,CH,H,W] in the order of plan.rank_edges[rank] (None if it owns none)."""
+        assert self.plan is not None, "call set_edges(ii, jj) first"
+        outs = []
+        for c in self.plan.rank_chunks[self.rank]:
+            v = self.plan.chunk_edges[c].to(coords.device)
+            outs.append(self.compute(coords[:, v], ii[v], jj[v]))
+        return torch.cat(outs, dim=1) if outs else None
+
+    def __call__(self, coords, ii, jj, gather="all", dst=0):
+        """gather=None: (local outputs, their edge positions).  gather="all": full [1,E,CH,H,W] in the original edge
+        order on every rank.  gather="dst": the same on rank `dst`, None elsewhere."""
+        local = self.local_lookup(coords, ii, jj)
+        mine = self.plan.rank_edges[self.rank]
+        if gather is None:
+            return local, mine
+        if self.world == 1:
+            return self._reorder([local], coords.device)
+        counts = self.plan.counts()
+        emax = max(counts)
+        shape = self._out_shape(local, coords)
+        pad = torch.zeros((emax,) + shape, dtype=torch.float32, device=coords.device)
+        if local is not None:
+            pad[:local.shape[1]] = local[0]
+        if gather == "all":
+            buf = torch.empty((self.world * emax,) + shape, dtype=torch.float32, device=coords.device)
+            dist.all_gather_into_tensor(buf, pad, group=self.group)
+            parts = [buf[r * emax:r * emax + counts[r]][None] for r in range(self.world)]
+            return self._reorder(parts, coords.device)
+        if gather == "dst":
+            bufs = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == dst else None
+            dist.gather(pad, bufs, dst=dst, group=self.group)
+            if self.rank != dst:
+                return None
+            return self._reorder([bufs[r][:counts[r]][None] for r in range(self.world)], coords.device)
+        raise ValueError("gather must be None, 'all' or 'dst'")
+
+    def _out_shape(self, local, coords):
+        # every rank must agree on the per-edge output shape even if it owns no edge: probe it collectively
+        shp = torch.tensor(list(local.shape[2:]) if local is not None else [0, 0, 0], device=coords.device)
+        dist.all_reduce(shp, op=dist.ReduceOp.MAX, group=self.group)
+        return tuple(int(x) for x in shp.tolist())
+
+    def _reorder(self, parts, device):
+        order = torch.cat(self.plan.rank_edges).to(device)
+        full = torch.cat([p for p in parts if p is not None and p.shape[1] > 0], dim=1)
+        out = torch.empty_like(full)
+        out[:, order] = full
+        return out

@@ -1,0 +1,166 @@
+"""CPU tests of the edge-sharded backend plumbing (lgu-slam_b200/sharded.py): the partitioner alone, and the
+world_size-2 path over `gloo` with the CPU oracle standing in for the GPU sampler (tests may use the oracle; the
+product path on a GPU box passes AltCorrBlock).  Sharded == single-process, bit for bit, in the original edge order."""
+import importlib
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+
+def _sharded():
+    # import the module file directly: the package __init__ would load the CUDA library, which is irrelevant here
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("lgu_sharded", os.path.join(ROOT, "lgu-slam_b200", "sharded.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["lgu_sharded"] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def _edges(T, E, seed):
+    g = torch.Generator().manual_seed(seed)
+    ii = torch.randint(0, T, (E,), generator=g)
+    jj = (ii + torch.randint(-3, 4, (E,), generator=g)).clamp(0, T - 1)
+    return ii, jj
+
+
+def test_reference_chunking_rule():
+    sh = _sharded()
+    ii = torch.tensor([0, 9, 3, 17, 8, 7, 16, 2])
+    jj = torch.tensor([1, 8, 4, 16, 9, 6, 17, 3])
+    chunks = sh.reference_chunks(ii, jj)
+    # factor_graph.py:272-279: i = 0, 8, 16 (range(0, jj.max()+1, 8)); v = (ii >= i) & (ii < i+8)
+    assert [c.tolist() for c in chunks] == [[0, 2, 5, 7], [1, 4], [3, 6]]
+    # edges whose source frame is beyond the last loop start are never visited by the reference loop either
+    assert sh.reference_chunks(torch.tensor([20]), torch.tensor([3])) == []
+    assert sh.reference_chunks(torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long)) == []
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_partition_covers_every_edge_once_and_balances(world):
+    sh = _sharded()
+    ii, jj = _edges(T=256, E=4096, seed=world)
+    plan = sh.partition_edges(ii, jj, world)
+    allpos = torch.cat(plan.rank_edges)
+    visited = torch.cat(sh.reference_chunks(ii, jj))
+    assert sorted(allpos.tolist()) == sorted(visited.tolist())
+    assert len(set(allpos.tolist())) == allpos.numel()
+    # chunks are never split
+    for c, own in enumerate(plan.chunk_owner):
+        assert set(plan.chunk_edges[c].tolist()) <= set(plan.rank_edges[own].tolist())
+    counts = plan.counts()
+    assert max(counts) - min(counts) <= max(e.numel() for e in plan.chunk_edges)     # LPT bound
+    assert max(counts) <= 1.25 * (sum(counts) / world) + 1
+    # deterministic: same plan from the same edge list
+    plan2 = sh.partition_edges(ii.clone(), jj.clone(), world)
+    assert plan2.chunk_owner == plan.chunk_owner
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_compute(pyr_levels):
+    """AltCorrBlock.__call__-shaped stand-in on the CPU oracle: zero offsets, 2 levels, r=1 (small and fast)."""
+    from oracle import oracle as orc
+
+    def compute(coords, ii, jj):
+        e, H, W = coords.shape[1:4]
+        outs = []
+        for l, f in enumerate(pyr_levels):
+            f1 = pyr_levels[0][ii].contiguous()
+            f2 = f[jj].contiguous()
+            c = (coords[0] / 2 ** l).reshape(e, 1, H, W, 2).contiguous()
+            o, = orc.lowMem_defSample(f1, f2, c, torch.zeros(e, H, W, 3, 3, 2), 1)
+            outs.append(o.view(e, 9, H, W))
+        return torch.cat(outs, dim=1)[None]
+    return compute
+
+
+def _case(T=20, E=37, H=6, W=8, C=32, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    fmaps = torch.randn(T, H, W, C, generator=g)
+    ii, jj = _edges(T, E, seed)
+    coords = torch.rand(1, E, H, W, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])
+    return fmaps, ii, jj, coords
+
+
+def _levels(fmaps):
+    l1 = torch.nn.functional.avg_pool2d(fmaps.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
+    return [fmaps.contiguous(), l1]
+
+
+def _worker(rank, world, port, gather, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = _sharded()
+        fmaps, ii, jj, coords = _case()
+        T = fmaps.shape[0]
+        # each rank starts with its own contiguous block of keyframes (uneven on purpose)
+        cut = [0, 7, T] if world == 2 else [0, T]
+        full = sh.all_gather_frames(fmaps[cut[rank]:cut[rank + 1]].contiguous())
+        assert torch.equal(full, fmaps)
+        eng = sh.ShardedBackendCorr(_oracle_compute(_levels(full)))
+        plan = eng.set_edges(ii, jj)
+        out = eng(coords, ii, jj, gather=gather)
+        if gather is None:
+            local, pos = out
+            q.put((rank, "local", local, pos))
+        elif out is not None:
+            q.put((rank, "full", out, None))
+        else:
+            q.put((rank, "none", None, None))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gather", ["all", "dst", None])
+def test_world_size_2_gloo_equals_single_process(gather):
+    fmaps, ii, jj, coords = _case()
+    sh = _sharded()
+    want_plan = sh.partition_edges(ii, jj, 1)
+    compute = _oracle_compute(_levels(fmaps))
+    visited = want_plan.rank_edges[0]
+    want = torch.zeros(1, visited.numel(), 18, 6, 8)
+    # single process, chunk by chunk in reference order
+    ref = torch.cat([compute(coords[:, v], ii[v], jj[v]) for v in want_plan.chunk_edges], dim=1)
+    want[:, visited] = ref if visited.numel() == ii.numel() else want
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, gather, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got.sort(key=lambda t: t[0])
+    full = torch.empty_like(ref)
+    full[:, visited] = ref                      # expected output in ORIGINAL edge order
+    if gather == "all":
+        for _, kind, out, _ in got:
+            assert kind == "full" and torch.equal(out, full)
+    elif gather == "dst":
+        assert got[0][1] == "full" and torch.equal(got[0][2], full) and got[1][1] == "none"
+    else:
+        seen = torch.zeros(ii.numel(), dtype=torch.bool)
+        for _, kind, local, pos in got:
+            assert kind == "local"
+            assert torch.equal(local, full[:, pos])
+            seen[pos] = True
+        assert seen.all()
