@@ -10,7 +10,8 @@ the hot path over that edge batch:
     build     all-pairs volume + Gaussian residual + 4-level pyramid       (1 launch, tcgen05/TMA, ours)
     lookup    r=1 mask lookup on level 1 -> var -> sigmoid -> offset[1] *= mask -> 4 x deformable r=3 lookups -> cat
               (CorrBlock.__call__, corr.py:88-109)                         (1 launch, TMA-staged, ours)
-    lookup^T  4 x defCorr_index_backward + corr_index_backward             (5 launches, ours; dense volume grads)
+    lookup^T  backward of the above: dense gradients of all 4 pyramid levels (mask path folded into level 1)
+              + offset gradients of levels 0-1                             (1 launch, ours)
     gauss^T   gaussianMask_backward                                        (1 launch, ours)
 
 `value` = E / step time with every input resident in HBM (CUDA events, max over ranks); `e2e` = the same step
@@ -48,8 +49,10 @@ def algorithmic_bytes_per_edge():
         "build": 2 * P * C * 2 + 16 * P + 4 * P * sum(QS),
         # fused 4-level lookup: coords once, offsets of levels 0-1 only (read + off1 written back), gathers, 196-ch out
         "lookup_fwd": P * (8 + 2 * 8 * TAPS + 8 * TAPS + sum(gather) + 64 + 4 * LEVELS * TAPS),
-        "lookup_bwd": P * ((8 + 36 + 4 * QS[1]) + sum(8 + 8 * TAPS + 4 * TAPS + 8 * TAPS + g + 4 * q
-                                                      for g, q in zip(gather, QS))),
+        # fused backward: coords, 2 offset records + mask, 196-ch upstream grad, level-0/1 gathers (+ mask taps),
+        # dense gradient slices of all 4 levels written once, 2 offset-gradient records
+        "lookup_bwd": P * (8 + 2 * 8 * TAPS + 4 + 4 * LEVELS * TAPS + gather[0] + gather[1] + 64 + 4 * sum(QS)
+                           + 2 * 8 * TAPS),
         "gauss_bwd": P * (2 * 81 * 4 + 32),
     }
     return d
@@ -134,7 +137,7 @@ class Workload:
         self.v_raw = self.ops.build_pyramid(hi, None, self.d["ii"], self.d["jj"], H, W, num_levels=1, gauss_radius=0)[0]
         self.g_vol = torch.randn(E, H, W, H, W, device=device, generator=g)
         self.g_mask = torch.randn(E, 3, 3, H, W, device=device, generator=g)   # upstream grad of the r=1 mask lookup
-        self.launches_per_step = 9
+        self.launches_per_step = 5
         self.ev = None
 
     def step(self, d=None, record=None):
@@ -154,21 +157,16 @@ class Workload:
                                 num_levels=LEVELS, gauss_radius=GR, precision=1)
         mark("build")
         # ---- CorrBlock.__call__ (corr.py:88-109): one fused TMA-staged launch (mask lookup + 4 deformable levels)
-        off0, off1 = d["off0"].clone(), d["off1"].clone()          # the block's per-edge offset state (mutated, Q5/Q7)
-        corr = ops.corr_lookup_fused(pyr, d["coords"], off0, off1, R)
+        off1 = d["off1"].clone()                                   # the block's per-edge offset state (mutated, Q7)
+        corr, mask = ops.corr_lookup_fused(pyr, d["coords"], d["off0"], off1, R, return_mask=True)
         mark("lookup_fwd")
-        # ---- backward of the lookups (corr.py:19-24,37-42), per-level operators, dense volume grads
-        c = d["coords"].permute(0, 3, 1, 2).contiguous()
-        cl = [(c / 2 ** l).contiguous() for l in range(LEVELS)]
-        offs = [o.view(E, H, W, 2 * R + 1, 2 * R + 1, 2) for o in (off0, off1, self.zero_off, self.zero_off2)]
-        gl = d["corr_grad"].view(E, LEVELS, 2 * R + 1, 2 * R + 1, H, W)
-        grads = [ops.defCorr_index_backward(pyr[l], cl[l], offs[l], gl[:, l].contiguous(), R) for l in range(LEVELS)]
-        gmask, = ops.corr_index_backward(pyr[1], cl[1], self.g_mask, 1)
+        # ---- its backward (what autograd runs for corr.py:88-109): one launch, dense gradients of all 4 levels
+        grads = ops.corr_lookup_fused_backward(pyr, d["coords"], d["off0"], off1, mask, d["corr_grad"])
         mark("lookup_bwd")
         gm, gc = ops.gaussianMask_backward(d["means"], d["covs"], self.v_raw, self.g_vol, GR)
         mark("gauss_bwd")
-        return dict(corr=corr, offset_grad0=grads[0][1], offset_grad1=grads[1][1], means_grad=gm, covs_grad=gc,
-                    _keep=(grads, gmask))
+        return dict(corr=corr, offset_grad0=grads[4], offset_grad1=grads[5], means_grad=gm, covs_grad=gc,
+                    _keep=grads)
 
     def step_e2e(self):
         """Same step from pinned host buffers: H2D of every per-step input, D2H of the results a caller consumes."""

@@ -138,16 +138,33 @@ LGU_API int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, const 
 
 /* CorrBlock.__call__'s data path  (droid_slam/modules/corr.py:88-109) in one launch:
  *   m      = sigmoid(var_9taps(corr_index_forward(lvl1, coords/2, 1)))        corr.py:94-97
- *   off1  <- off1 * m   (in place; the reference's cumulative `self.offset[1] *= mask`, quirk Q7)
+ *   off1  <- off1 * m   (in place, every tap; the reference's cumulative `self.offset[1] *= mask`, quirk Q7)
  *   corr[:, l*49:(l+1)*49] = defCorr_index_forward(lvl_l, coords/2^l, off_l, 3)   corr.py:101-105
- * with off_2 = off_3 = 0 (corr.py:131-132), so those levels read no offsets at all.
+ * with off_2 = off_3 = 0 (corr.py:131-132), so those levels read no offsets at all.  The centre tap of off0 /
+ * off1 is READ as 0 (quirk Q5) but not zeroed in memory: inside CorrBlock the reference zeroes a temporary
+ * (`.contiguous()` of a permuted view), so its stored centre values survive too -- and its autograd uses them.
  * lvl0..lvl3 [E,H,W,H>>l,W>>l] (16-byte aligned), coords [E,H,W,2] (x,y interleaved, level-0 units -- the
- * layout CorrBlock.__call__ receives, before its permute), off0/off1 [E,H,W,7,7,2] (centre taps zeroed in
- * place, Q5), corr [E,196,H,W], mask_out [E,H,W] or NULL.  Pyramid patches are staged with TMA box loads.
+ * layout CorrBlock.__call__ receives, before its permute), off0/off1 [E,H,W,7,7,2], corr [E,196,H,W],
+ * mask_out [E,H,W] or NULL.  Pyramid patches are staged with TMA box loads.
  * Implemented for num_levels == 4, radius == 3, W % 32 == 0, H % 8 == 0 (LGU_ERR_UNSUPPORTED otherwise). */
 LGU_API int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
-                          const float* coords, float* off0, float* off1, float* corr, float* mask_out,
+                          const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                           int E, int H, int W, int num_levels, int radius, void* stream);
+
+/* Backward of lgu_corr_lookup_fused = what autograd runs for corr.py:88-109 in training (4 x
+ * defCorr_index_backward, the offset[1]*mask / sigmoid / var chain, corr_index_backward), in one launch:
+ *   gv0..gv3      dense gradients of the pyramid levels (each written exactly once; level 1 includes the mask path)
+ *   off0_grad     gradient of off0;   off1_grad  gradient of off1 BEFORE the mask multiply (offset[1]_in)
+ * inputs: off1_out = off1 after the forward (post-mask), mask = the forward's mask_out, corr_grad [E,196,H,W],
+ * off1_out_grad [E,H,W,7,7,2] = upstream gradient on the post-mask offsets from later calls (NULL if none).
+ * Levels 2-3 get no offset gradient (their offsets are detached zeros, corr.py:131-134); coords get none
+ * (corr.py:42). */
+LGU_API int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lvl1, const float* coords,
+                                   const float* off0, const float* off1_out, const float* mask,
+                                   const float* corr_grad, const float* off1_out_grad,
+                                   float* gv0, float* gv1, float* gv2, float* gv3,
+                                   float* off0_grad, float* off1_grad,
+                                   int E, int H, int W, int num_levels, int radius, void* stream);
 
 /* fmaps [T,C,P] fp32 or fp16 (NCHW as the encoders emit) -> channels-last fp16 planes
  * hi [T,P,C] (and lo [T,P,C] = fp16(x/4 - hi) when lo != NULL), pre-scaled by 1/4 (corr.py:148-149). */

@@ -86,6 +86,29 @@ class GaussianMaskCuda(torch.autograd.Function):
         return gm, gc, None, None
 
 
+class FusedCorrLookup(torch.autograd.Function):
+    """CorrBlock.__call__'s whole data path (corr.py:88-109) as ONE differentiable op: forward = one TMA-staged
+    launch, backward = one launch (lgu_corr_lookup_fused_backward).  Inputs: the 4 pyramid levels, coords [E,H,W,2],
+    off0, off1 [E,H,W,98].  Outputs: corr [E,196,H,W] and the post-mask offsets offset[1]*mask (which the block
+    keeps for its next call, quirk Q7).  Gradients: pyramid levels, off0, off1; none for coords (corr.py:42)."""
+
+    @staticmethod
+    def forward(ctx, lvl0, lvl1, lvl2, lvl3, coords, off0, off1):
+        off1_out = off1.detach().clone()                    # the kernel updates offset[1] in place
+        corr, mask = ops.corr_lookup_fused([lvl0, lvl1, lvl2, lvl3], coords, off0, off1_out, 3, return_mask=True)
+        ctx.save_for_backward(lvl0, lvl1, lvl2, lvl3, coords, off0, off1_out, mask)
+        ctx.mark_non_differentiable(mask)
+        return corr, off1_out, mask
+
+    @staticmethod
+    def backward(ctx, g_corr, g_off1_out, _g_mask):
+        lvl0, lvl1, lvl2, lvl3, coords, off0, off1_out, mask = ctx.saved_tensors
+        up = g_off1_out.contiguous() if g_off1_out is not None else None
+        gv0, gv1, gv2, gv3, g0, g1 = ops.corr_lookup_fused_backward([lvl0, lvl1, lvl2, lvl3], coords, off0, off1_out,
+                                                                    mask, g_corr.contiguous(), up)
+        return gv0, gv1, gv2, gv3, None, g0.view_as(off0), g1.view_as(off1_out)
+
+
 def per_Corr_Normalization(x, normalIndex, eps=1e-5):
     """corr.py:44-51 / gaussianMask_cuda.py:26-33: standardise over `normalIndex` (biased variance + eps)."""
     mean = torch.mean(x, dim=normalIndex, keepdim=True)
@@ -159,7 +182,8 @@ class CorrBlock:
     (inference: torch.no_grad, as FactorGraph / MotionFilter run) and the per-op autograd path otherwise."""
 
     def __init__(self, ofsMap, ofs_residual, GA, fmap1, fmap2, num_levels=4, radius=3, fused=None,
-                 autocast_rounding=None):
+                 autocast_rounding=None, fused_lookup=True):
+        self.fused_lookup = fused_lookup
         self.num_levels = num_levels
         self.radius = radius
         self.GA = GA
@@ -202,12 +226,12 @@ class CorrBlock:
         self.theta = 2 * det.view(b, n, h, w)
 
     def _can_fuse_lookup(self, coords):
-        if torch.is_grad_enabled() and (coords.requires_grad or any(
-                t.requires_grad for t in self.corr_pyramid + self.offset)):
-            return False
         ht, wd = coords.shape[2:4]
-        return (self.num_levels == 4 and self.radius == 3 and wd % 32 == 0 and ht % 8 == 0
+        return (self.fused_lookup and self.num_levels == 4 and self.radius == 3 and wd % 32 == 0 and ht % 8 == 0
                 and all(t.dtype == torch.float32 for t in self.corr_pyramid))
+
+    def _needs_grad(self, coords):
+        return torch.is_grad_enabled() and any(t.requires_grad for t in self.corr_pyramid + self.offset[:2])
 
     def __call__(self, coords):
         batch, num, ht, wd, _ = coords.shape
@@ -218,8 +242,12 @@ class CorrBlock:
                 if not (self.offset[i].is_contiguous() and self.offset[i].dtype == torch.float32):
                     self.offset[i] = self.offset[i].float().contiguous()
             pyr = [t if t.is_contiguous() else t.contiguous() for t in self.corr_pyramid]
-            out = ops.corr_lookup_fused(pyr, coords.reshape(E, ht, wd, 2).float().contiguous(), self.offset[0],
-                                        self.offset[1], self.radius)
+            c = coords.detach().reshape(E, ht, wd, 2).float().contiguous()
+            if self._needs_grad(coords):                     # training: differentiable fused op (1 + 1 launches)
+                out, self.offset[1], _ = FusedCorrLookup.apply(pyr[0], pyr[1], pyr[2], pyr[3], c, self.offset[0],
+                                                               self.offset[1])
+            else:                                            # inference: offset[1] updated in place
+                out = ops.corr_lookup_fused(pyr, c, self.offset[0], self.offset[1], self.radius)
             return out.view(batch, num, -1, ht, wd), self.mean_n, self.theta
         coords = coords.permute(0, 1, 4, 2, 3).contiguous().view(E, 2, ht, wd)
 

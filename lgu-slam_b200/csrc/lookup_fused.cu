@@ -22,110 +22,19 @@
 // Index logic is the reference's, bit for bit (defCorrSample_kernel.cu:56-67, corrSample_kernel.cu:52-60;
 // quirks Q1, Q3, Q5, Q7): levels 0, 2, 3 are bit-identical to defCorr_index_forward; level 1 differs only through
 // the fp32 rounding of the 9-tap variance / sigmoid that scales its offsets.
-#include <cuda.h>
-#include "common.cuh"
+#include "fused_common.cuh"
 
 namespace lgu {
-
-namespace fl {
-constexpr int kWarps = 8, kThreads = kWarps * 32, kTile = 32, kPixPerWarp = kTile / kWarps;
-constexpr int R = 3, RD = 7, TAPS = 49, LEVELS = 4, CH = LEVELS * TAPS;
-constexpr int kBW01 = 20, kBH01 = 16, kBW23 = 12, kBH23 = 8;
-constexpr int kOff0 = 0, kOff1 = kBW01 * kBH01, kOff2 = 2 * kBW01 * kBH01, kOff3 = kOff2 + kBW23 * kBH23;
-constexpr int kSlotFloats = kOff3 + kBW23 * kBH23;                 // 832 floats = 3328 B (26 x 128 B)
-constexpr int kSlotBytes = kSlotFloats * 4;
-constexpr int kSlots = 2;
-constexpr int kOutPitch = kTile + 1;
-constexpr int kSmemBoxes = kWarps * kSlots * kSlotBytes;           // 53,248 B
-constexpr int kSmemOut = CH * kOutPitch * 4;                       // 25,872 B
-constexpr int kSmemBytes = kSmemBoxes + kSmemOut + kWarps * kSlots * 8;
-}  // namespace fl
 
 struct FusedLookupParams {
   const float* lvl[4];
   const float* coords;   // [E,P,2] (x,y) level-0 units
-  float* off0;           // [E,P,49,2]  centre tap zeroed in place (Q5)
-  float* off1;           // [E,P,49,2]  <- off1 * mask (Q7), centre tap zeroed
+  const float* off0;     // [E,P,49,2]  read only (its centre tap is read as 0, Q5)
+  float* off1;           // [E,P,49,2]  <- off1 * mask (Q7), every tap; the centre tap is read as 0
   float* out;            // [E,196,P]
   float* mask_out;       // [E,P] or null: the sigmoid(var) mask of this call
   int P, tiles_per_edge;
   int H2[4], W2[4];
-};
-
-__device__ __forceinline__ uint32_t fl_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void fl_mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fl_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fl_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fl_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void fl_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "FL_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra FL_DONE_%=;\n\t"
-      "bra FL_WAIT_%=;\n\t"
-      "FL_DONE_%=:\n\t}" ::"r"(fl_smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fl_tma_box(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          fl_smem_u32(dst)),
-      "l"(map), "r"(fl_smem_u32(bar)), "r"(x), "r"(y), "r"(z)
-      : "memory");
-}
-
-// Box origin of a level: columns start at (floor(c) - reach) rounded down to a multiple of 4 (16-byte TMA
-// alignment), clamped so that saturated float->int conversions cannot overflow the TMA coordinate arithmetic.
-__device__ __forceinline__ int box_origin_x(int f, int reach, int W2) {
-  const int v = max(min(f, W2 + 64), -64) - reach;
-  return v & ~3;
-}
-__device__ __forceinline__ int box_origin_y(int f, int reach, int H2) { return max(min(f, H2 + 64), -64) - reach; }
-
-// One bilinear tap against the staged box.  Branch-free fast path: the four corners are read from shared memory at
-// a clamped (always valid) index; out-of-bounds corners were zero-filled by the TMA unit, so no per-corner select
-// is needed when the 2x2 footprint lies inside the box.  `miss` flags the lanes whose footprint is outside the box
-// (|offset| >= 4) and that still pass the reference's top-left gate: the caller patches those from global memory.
-struct Tap {
-  float dx, dy, q11, q21, q12, q22;
-  int x1, y1;
-  bool gate, miss;
-};
-
-template <int BW, int BH>
-__device__ __forceinline__ void tap_fetch(Tap& t, const float* __restrict__ box, int xb, int yb, int fx, int fy, int i,
-                                          int j, int r, int H2, int W2) {
-  t.x1 = tap_coord(fx, r, i);
-  t.y1 = tap_coord(fy, r, j);
-  t.gate = ((unsigned)t.x1 < (unsigned)W2) && ((unsigned)t.y1 < (unsigned)H2);    // top-left gate (Q3)
-  const unsigned rx = (unsigned)t.x1 - (unsigned)xb, ry = (unsigned)t.y1 - (unsigned)yb;
-  const bool inbox = rx < (unsigned)(BW - 1) && ry < (unsigned)(BH - 1);
-  t.miss = t.gate && !inbox;
-  const float* b = box + (inbox ? ry * BW + rx : 0u);
-  t.q11 = b[0]; t.q21 = b[1]; t.q12 = b[BW]; t.q22 = b[BW + 1];
-}
-// Slow path for flagged lanes: same gating as the reference (x2 / y2 corners gated individually).
-__device__ __forceinline__ void tap_patch_from_global(Tap& t, const float* __restrict__ V, int H2, int W2) {
-  if (t.miss) {
-    const int x2 = wrap_inc(t.x1), y2 = wrap_inc(t.y1);
-    const bool xo = (unsigned)x2 < (unsigned)W2, yo = (unsigned)y2 < (unsigned)H2;
-    const float* g = V + (size_t)t.y1 * W2 + t.x1;
-    t.q11 = __ldg(g);
-    t.q21 = xo ? __ldg(g + 1) : 0.0f;
-    t.q12 = yo ? __ldg(g + W2) : 0.0f;
-    t.q22 = (xo && yo) ? __ldg(g + W2 + 1) : 0.0f;
-  }
-}
-__device__ __forceinline__ float tap_value(const Tap& t) {
-  return t.gate ? blend4(t.q11, t.q21, t.q12, t.q22, t.dx, t.dy) : 0.0f;
-}
-
-struct FusedMaps {
-  CUtensorMap m[4];
 };
 
 __global__ void __launch_bounds__(fl::kThreads, 2)
@@ -280,9 +189,10 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
       const float var = __shfl_sync(0xffffffffu, ss, 0) * 0.125f;
       m = 1.0f / (1.0f + expf(-var));
     }
-    // offset[1] <- offset[1] * mask (Q7), centre tap zeroed (Q5)
+    // offset[1] <- offset[1] * mask (Q7) for every tap; the lookup itself reads the centre tap as 0 (Q5)
     o10 = make_float2(__fmul_rn(o10.x, m), __fmul_rn(o10.y, m));
     o11 = make_float2(__fmul_rn(o11.x, m), __fmul_rn(o11.y, m));
+    const float2 o10_store = o10;
     if (lane == CENTER) o10 = make_float2(0.0f, 0.0f);
 
     deform_level(box + kOff1, V1, prm.H2[1], prm.W2[1], x1c, y1c, o10, o11, so + TAPS * kOutPitch);
@@ -297,9 +207,8 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     // ---------------- in-place side effects on the caller's offsets
     if (live) {
       float2* O1 = reinterpret_cast<float2*>(prm.off1) + pix * TAPS;
-      O1[t0] = o10;
+      O1[t0] = o10_store;
       if (has1) O1[t1] = o11;
-      if (lane == CENTER) reinterpret_cast<float2*>(prm.off0)[pix * TAPS + CENTER] = make_float2(0.0f, 0.0f);
       if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[pix] = m;
     }
     __syncwarp();                                               // every lane is done with this slot
@@ -318,42 +227,10 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     if (live) __stcs(out + (size_t)ch * P, srow[ch * kOutPitch]);
 }
 
-typedef CUresult (*FlEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int make_slice_map(CUtensorMap* map, const float* base, long long nslices, int H2, int W2, int bw, int bh) {
-  static FlEncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<FlEncodeTiledFn>(p);
-  }
-  if (fn == nullptr) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return LGU_ERR_LAUNCH;
-  }
-  const cuuint64_t dims[3] = {(cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)nslices};
-  const cuuint64_t strides[2] = {(cuuint64_t)W2 * 4, (cuuint64_t)W2 * H2 * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
-  const cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (slices=%lld H2=%d W2=%d box=%dx%d)", (int)r, nslices, H2,
-              W2, bw, bh);
-    return LGU_ERR_LAUNCH;
-  }
-  return LGU_OK;
-}
-
 }  // namespace lgu
 
 extern "C" int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
-                                     const float* coords, float* off0, float* off1, float* corr, float* mask_out,
+                                     const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                      int E, int H, int W, int num_levels, int radius, void* stream) {
   using namespace lgu;
   if (E == 0) return LGU_OK;

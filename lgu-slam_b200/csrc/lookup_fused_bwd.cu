@@ -1,0 +1,456 @@
+// lookup_fused_bwd.cu -- backward of CorrBlock.__call__'s data path in ONE launch (sm_100a).
+//
+// Replaces what autograd runs for /root/reference/droid_slam/modules/corr.py:88-109 in training:
+//   4 x defCorr_index_backward (defCorrSample_kernel.cu:93-162; each zero-fills and RMWs a dense volume_grad and
+//   writes a dense offset_grad, also for the detached zero offsets of levels 2-3)
+//   + (offset[1] * mask)^T + sigmoid^T + var^T (torch)  + corr_index_backward (corrSample_kernel.cu:84-136; one
+//   more dense level-1 volume_grad that autograd then adds to the first)
+// by one kernel that writes every pyramid level's dense gradient slice exactly once, with the mask path already
+// accumulated into level 1, and offset gradients only for the two levels that have offsets.
+//
+// Per source pixel (one warp, lane = tap):
+//   * TMA box loads stage the level-0 / level-1 footprints (needed for the offset gradients and to recompute the
+//     9 mask taps), 2-slot mbarrier ring as in the forward;
+//   * the upstream gradient tile [196 x 32 pixels] is loaded with 128-byte rows and transposed through smem;
+//   * corner contributions are accumulated into per-warp BOX-shaped shared accumulators (20x16, 20x16, 12x8, 12x8
+//     floats: the same footprint the forward gathers from) -- shared-memory reductions for the deformable levels
+//     (taps may collide), plain read-modify-write per corner phase for the zero-offset levels and the mask taps;
+//   * each level's dense H2 x W2 slice is then streamed out once with 16-byte st.cs: zeros outside the box, the
+//     accumulator inside (re-zeroed on the fly).  Taps outside the box (|offset| >= 4) are added with global
+//     atomics after the slice has been written.
+// Gradient algebra (what autograd computes for the reference graph):
+//   gO_l      = defCorr offset gradient of level l (defCorrSample_kernel.cu:156-157), l = 0, 1
+//   g_off1_in = (gO_1 + g_off1_out) * m                       (offset[1]_out = offset[1]_in * m, corr.py:99)
+//   g_m       = sum_taps (gO_1 + g_off1_out) . offset[1]_in   = sum(...) . offset[1]_out / m
+//   g_var     = g_m * m * (1 - m)                             (sigmoid, corr.py:97)
+//   g_v[k]    = g_var * 2 (v[k] - mean) / 8                   (unbiased 9-tap variance, corr.py:96)
+//   gV_1     += corr_index_backward(g_v)                      (corrSample_kernel.cu:84-136)
+#include "fused_common.cuh"
+
+namespace lgu {
+
+namespace flb {
+using namespace fl;
+constexpr int kInSlotFloats = 2 * kBW01 * kBH01;                 // level-0 + level-1 input boxes: 640 floats
+constexpr int kInSlotBytes = kInSlotFloats * 4;                  // 2560 B
+constexpr int kAccFloats = kSlotFloats;                          // 832 floats: acc0 | acc1 | acc2 | acc3
+constexpr int kWarpFloats = kSlots * kInSlotFloats + kAccFloats; // 2112 floats = 8448 B
+constexpr int kSmemWarp = kWarps * kWarpFloats * 4;              // 67,584 B
+constexpr int kSmemG = CH * kOutPitch * 4;                       // 25,872 B
+constexpr int kSmemBytes = kSmemWarp + kSmemG + kWarps * kSlots * 8;
+}  // namespace flb
+
+struct FusedLookupBwdParams {
+  const float* lvl[2];       // level 0 / 1 volumes (slow path only; the fast path reads the TMA boxes)
+  const float* coords;       // [E,P,2]
+  const float* off0;         // [E,P,49,2]  as used by the forward (centre tap reads as 0)
+  const float* off1;         // [E,P,49,2]  post-mask offsets (offset[1]_out of the forward)
+  const float* mask;         // [E,P]       m of the forward
+  const float* g_out;        // [E,196,P]   upstream gradient of corr
+  const float* g_off1_out;   // [E,P,49,2]  upstream gradient of offset[1]_out (later calls), or null
+  float* gv[4];              // dense volume gradients [E,P,H2,W2]
+  float* g_off0;             // [E,P,49,2]
+  float* g_off1;             // [E,P,49,2]  gradient of offset[1]_in
+  int P, tiles_per_edge;
+  int H2[4], W2[4];
+};
+
+// Scatter one corner phase of all lanes into a box accumulator.  ATOMIC: lanes may collide (learned offsets).
+template <bool ATOMIC>
+__device__ __forceinline__ void acc_add(float* acc, bool on, unsigned idx, float val) {
+  if (on) {
+    if (ATOMIC) atomicAdd(acc + idx, val);
+    else acc[idx] += val;
+  }
+  if (!ATOMIC) __syncwarp();
+}
+
+// Geometry of one tap for the backward: gates, box index, bilinear fractions.
+struct BTap {
+  float dx, dy;
+  int x1, y1;
+  unsigned idx;
+  bool gate, xo, yo, inbox;
+};
+template <int BW, int BH>
+__device__ __forceinline__ void btap_setup(BTap& t, int xb, int yb, int fx, int fy, int i, int j, int r, int H2, int W2) {
+  t.x1 = tap_coord(fx, r, i);
+  t.y1 = tap_coord(fy, r, j);
+  const int x2 = wrap_inc(t.x1), y2 = wrap_inc(t.y1);
+  t.gate = ((unsigned)t.x1 < (unsigned)W2) && ((unsigned)t.y1 < (unsigned)H2);
+  t.xo = t.gate && ((unsigned)x2 < (unsigned)W2);
+  t.yo = t.gate && ((unsigned)y2 < (unsigned)H2);
+  const unsigned rx = (unsigned)t.x1 - (unsigned)xb, ry = (unsigned)t.y1 - (unsigned)yb;
+  t.inbox = rx < (unsigned)(BW - 1) && ry < (unsigned)(BH - 1);
+  t.idx = t.inbox ? ry * BW + rx : 0u;
+}
+// Accumulate the <= 4 corner contributions of a tap (weights as in defCorrSample_kernel.cu:145-154 /
+// corrSample_kernel.cu:118-131).  Footprints outside the box are deferred (returned true) to the global slow path.
+template <int BW, bool ATOMIC>
+__device__ __forceinline__ void btap_scatter(float* acc, const BTap& t, bool active, float g) {
+  const float omdx = __fsub_rn(1.0f, t.dx), omdy = __fsub_rn(1.0f, t.dy);
+  const bool on = active && t.gate && t.inbox;
+  acc_add<ATOMIC>(acc, on, t.idx, __fmul_rn(__fmul_rn(omdy, omdx), g));
+  acc_add<ATOMIC>(acc, on && t.xo, t.idx + 1, __fmul_rn(__fmul_rn(omdy, t.dx), g));
+  acc_add<ATOMIC>(acc, on && t.yo, t.idx + BW, __fmul_rn(__fmul_rn(t.dy, omdx), g));
+  acc_add<ATOMIC>(acc, on && t.xo && t.yo, t.idx + BW + 1, __fmul_rn(__fmul_rn(t.dy, t.dx), g));
+}
+__device__ __forceinline__ void btap_scatter_global(float* G, const BTap& t, bool active, float g, int W2) {
+  if (active && t.gate && !t.inbox) {
+    const float omdx = __fsub_rn(1.0f, t.dx), omdy = __fsub_rn(1.0f, t.dy);
+    float* p = G + (size_t)t.y1 * W2 + t.x1;
+    atomicAdd(p, __fmul_rn(__fmul_rn(omdy, omdx), g));
+    if (t.xo) atomicAdd(p + 1, __fmul_rn(__fmul_rn(omdy, t.dx), g));
+    if (t.yo) atomicAdd(p + W2, __fmul_rn(__fmul_rn(t.dy, omdx), g));
+    if (t.xo && t.yo) atomicAdd(p + W2 + 1, __fmul_rn(__fmul_rn(t.dy, t.dx), g));
+  }
+}
+// Offset gradient of a tap (defCorrSample_kernel.cu:156-157, the reference's SASS operation order).
+__device__ __forceinline__ float2 offset_grad(float q11, float q21, float q12, float q22, float dx, float dy, float g) {
+  const float omdx = __fsub_rn(1.0f, dx), omdy = __fsub_rn(1.0f, dy);
+  float ty = __fmaf_rn(-q11, omdx, -__fmul_rn(dx, q21));
+  ty = __fmaf_rn(omdx, q12, ty);
+  ty = __fmaf_rn(dx, q22, ty);
+  float tx = __fmaf_rn(omdy, q21, -__fmul_rn(q11, omdy));
+  tx = __fmaf_rn(-dy, q12, tx);
+  tx = __fmaf_rn(dy, q22, tx);
+  return make_float2(__fmul_rn(tx, g), __fmul_rn(ty, g));
+}
+
+// Stream one level's dense gradient slice: zeros outside the accumulator box, the accumulator (then re-zeroed) inside.
+template <int BW, int BH>
+__device__ __forceinline__ void write_slice(float* __restrict__ G, float* acc, int xb, int yb, int H2, int W2, int lane) {
+  const int W4 = W2 >> 2, n4 = H2 * W4;
+  float4* G4 = reinterpret_cast<float4*>(G);
+  const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  for (int q4 = lane; q4 < n4; q4 += 32) {
+    const int y = q4 / W4, x = (q4 - y * W4) << 2;
+    const unsigned ry = (unsigned)(y - yb), rx = (unsigned)(x - xb);
+    float4 v = z;
+    if (ry < (unsigned)BH && rx < (unsigned)BW) {              // xb % 4 == 0: the float4 lies entirely inside
+      float4* a = reinterpret_cast<float4*>(acc + ry * BW + rx);
+      v = *a;
+      *a = z;
+    }
+    __stcs(G4 + q4, v);
+  }
+}
+
+__global__ void __launch_bounds__(fl::kThreads, 2)
+lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupBwdParams prm) {
+  using namespace flb;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wmem = reinterpret_cast<float*>(smem) + warp * kWarpFloats;
+  float* inbox = wmem;                                           // [slot][lvl0 | lvl1]
+  float* acc = wmem + kSlots * kInSlotFloats;                    // acc0 | acc1 | acc2 | acc3 (offsets kOff0..3)
+  float* s_g = reinterpret_cast<float*>(smem + kSmemWarp);       // [CH][kOutPitch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemWarp + kSmemG) + warp * kSlots;
+
+  const int P = prm.P;
+  const int n = blockIdx.x / prm.tiles_per_edge;
+  const int p0 = (blockIdx.x - n * prm.tiles_per_edge) * kTile;
+  const int pw = p0 + warp * kPixPerWarp;
+
+  if (lane == 0) {
+    fl_mbar_init(bars + 0, 1);
+    fl_mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  float2 cmine = make_float2(0.0f, 0.0f);
+  if (lane < kPixPerWarp)
+    cmine = __ldg(reinterpret_cast<const float2*>(prm.coords) + (size_t)n * P + min(pw + lane, P - 1));
+
+  auto issue = [&](int k, float cx, float cy) {                 // lane 0 only
+    const int slot = k & 1;
+    const int pix = n * P + min(pw + k, P - 1);
+    float* dst = inbox + slot * kInSlotFloats;
+    fl_mbar_expect_tx(bars + slot, kInSlotBytes);
+    float sx = cx, sy = cy;
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      const int xb = box_origin_x(floor_to_int(sx), 7, prm.W2[l]), yb = box_origin_y(floor_to_int(sy), 7, prm.H2[l]);
+      fl_tma_box(dst + l * kBW01 * kBH01, &maps.m[l], bars + slot, xb, yb, pix);
+      sx = __fmul_rn(sx, 0.5f);
+      sy = __fmul_rn(sy, 0.5f);
+    }
+  };
+  {
+    const float c0x = __shfl_sync(0xffffffffu, cmine.x, 0), c0y = __shfl_sync(0xffffffffu, cmine.y, 0);
+    const float c1x = __shfl_sync(0xffffffffu, cmine.x, 1), c1y = __shfl_sync(0xffffffffu, cmine.y, 1);
+    if (lane == 0) {
+      issue(0, c0x, c0y);
+      issue(1, c1x, c1y);
+    }
+  }
+
+  // upstream gradient tile: 196 rows of 32 pixels (128 B), transposed through shared memory; clear the accumulators
+  {
+    const float* g = prm.g_out + (size_t)n * CH * P + p0 + lane;
+    for (int ch = warp; ch < CH; ch += kWarps) s_g[ch * kOutPitch + lane] = __ldg(g + (size_t)ch * P);
+    for (int q = lane; q < kAccFloats; q += 32) acc[q] = 0.0f;
+  }
+  __syncthreads();
+
+  const int t0 = lane, t1 = lane + 32;
+  const int i0 = t0 / RD, j0 = t0 - i0 * RD;
+  const int t1c = min(t1, TAPS - 1);
+  const int i1 = t1c / RD, j1 = t1c - i1 * RD;
+  const bool has1 = t1 < TAPS;
+  constexpr int CENTER = R * RD + R;
+  const int mi = min(lane, 8) / 3, mj = min(lane, 8) - mi * 3;
+
+  float2 a0, a1, b0, b1, u0, u1;                                // off0 / off1 / upstream g_off1_out of taps t0, t1
+  float mk;
+  auto load_offsets = [&](int k) {
+    const size_t pix = (size_t)n * P + min(pw + k, P - 1);
+    const float2* O0 = reinterpret_cast<const float2*>(prm.off0) + pix * TAPS;
+    const float2* O1 = reinterpret_cast<const float2*>(prm.off1) + pix * TAPS;
+    a0 = O0[t0]; a1 = O0[t1c]; b0 = O1[t0]; b1 = O1[t1c];
+    u0 = u1 = make_float2(0.0f, 0.0f);
+    if (prm.g_off1_out != nullptr) {
+      const float2* U = reinterpret_cast<const float2*>(prm.g_off1_out) + pix * TAPS;
+      u0 = U[t0]; u1 = U[t1c];
+    }
+    mk = __ldg(prm.mask + pix);
+  };
+  load_offsets(0);
+
+#pragma unroll 1
+  for (int k = 0; k < kPixPerWarp; ++k) {
+    const int slot = k & 1;
+    const size_t pix = (size_t)n * P + min(pw + k, P - 1);
+    const int pl = warp * kPixPerWarp + k;
+    const float x0 = __shfl_sync(0xffffffffu, cmine.x, k), y0 = __shfl_sync(0xffffffffu, cmine.y, k);
+    float2 o00 = a0, o01 = a1, o10 = b0, o11 = b1;
+    const float2 o10_raw = b0;                                  // the stored centre tap still multiplies g_m (see header)
+    const float2 up0 = u0, up1 = u1;
+    const float m = mk;
+    if (lane == CENTER) { o00 = make_float2(0.0f, 0.0f); o10 = make_float2(0.0f, 0.0f); }    // Q5
+    if (k + 1 < kPixPerWarp) load_offsets(k + 1);
+
+    fl_mbar_wait(bars + slot, (k >> 1) & 1);
+    const float* box0 = inbox + slot * kInSlotFloats;
+    const float* box1 = box0 + kBW01 * kBH01;
+    const float* sg = s_g + pl;
+
+    const float x1c = __fmul_rn(x0, 0.5f), y1c = __fmul_rn(y0, 0.5f);
+    const float x2c = __fmul_rn(x1c, 0.5f), y2c = __fmul_rn(y1c, 0.5f);
+    const float x3c = __fmul_rn(x2c, 0.5f), y3c = __fmul_rn(y2c, 0.5f);
+    float* G0 = prm.gv[0] + pix * (size_t)(prm.H2[0] * prm.W2[0]);
+    float* G1 = prm.gv[1] + pix * (size_t)(prm.H2[1] * prm.W2[1]);
+
+    // ---------------- deformable levels 0 and 1: offset gradients + scatter
+    BTap ta0, tb0, ta1, tb1;                                    // kept for the global slow path after the slice write
+    float ga0, gb0, ga1, gb1;
+    float gm_part = 0.0f;
+    const int xb0 = box_origin_x(floor_to_int(x0), 7, prm.W2[0]), yb0 = box_origin_y(floor_to_int(y0), 7, prm.H2[0]);
+    const int xb1 = box_origin_x(floor_to_int(x1c), 7, prm.W2[1]), yb1 = box_origin_y(floor_to_int(y1c), 7, prm.H2[1]);
+    auto deform_bwd = [&](int l, const float* bx, int xb, int yb, float cx, float cy, float2 oa, float2 ob, BTap& ta,
+                          BTap& tb, float& ga, float& gb, float2& goa, float2& gob) {
+      const int H2 = prm.H2[l], W2 = prm.W2[l];
+      {
+        const float px = __fadd_rn(oa.x, cx), py = __fadd_rn(oa.y, cy);
+        const int fx = floor_to_int(px), fy = floor_to_int(py);
+        ta.dx = __fsub_rn(px, (float)fx); ta.dy = __fsub_rn(py, (float)fy);
+        btap_setup<kBW01, kBH01>(ta, xb, yb, fx, fy, i0, j0, R, H2, W2);
+      }
+      {
+        const float px = __fadd_rn(ob.x, cx), py = __fadd_rn(ob.y, cy);
+        const int fx = floor_to_int(px), fy = floor_to_int(py);
+        tb.dx = __fsub_rn(px, (float)fx); tb.dy = __fsub_rn(py, (float)fy);
+        btap_setup<kBW01, kBH01>(tb, xb, yb, fx, fy, i1, j1, R, H2, W2);
+      }
+      ga = sg[(l * TAPS + t0) * kOutPitch];
+      gb = sg[(l * TAPS + t1c) * kOutPitch];
+      // corner values (zero-filled out of bounds by the TMA unit) for the offset gradient
+      float qa[4], qb[4];
+      {
+        const float* b = bx + ta.idx;
+        qa[0] = b[0]; qa[1] = b[1]; qa[2] = b[kBW01]; qa[3] = b[kBW01 + 1];
+        b = bx + tb.idx;
+        qb[0] = b[0]; qb[1] = b[1]; qb[2] = b[kBW01]; qb[3] = b[kBW01 + 1];
+      }
+      const bool miss = (ta.gate && !ta.inbox) || (has1 && tb.gate && !tb.inbox);
+      if (__any_sync(0xffffffffu, miss)) {                      // |offset| >= 4: read the corners from global
+        const float* V = prm.lvl[l] + pix * (size_t)(H2 * W2);
+        if (ta.gate && !ta.inbox) {
+          const float* g = V + (size_t)ta.y1 * W2 + ta.x1;
+          qa[0] = __ldg(g); qa[1] = ta.xo ? __ldg(g + 1) : 0.0f; qa[2] = ta.yo ? __ldg(g + W2) : 0.0f;
+          qa[3] = (ta.xo && ta.yo) ? __ldg(g + W2 + 1) : 0.0f;
+        }
+        if (tb.gate && !tb.inbox) {
+          const float* g = V + (size_t)tb.y1 * W2 + tb.x1;
+          qb[0] = __ldg(g); qb[1] = tb.xo ? __ldg(g + 1) : 0.0f; qb[2] = tb.yo ? __ldg(g + W2) : 0.0f;
+          qb[3] = (tb.xo && tb.yo) ? __ldg(g + W2 + 1) : 0.0f;
+        }
+      }
+      goa = ta.gate ? offset_grad(qa[0], qa[1], qa[2], qa[3], ta.dx, ta.dy, ga) : make_float2(0.0f, 0.0f);
+      gob = (has1 && tb.gate) ? offset_grad(qb[0], qb[1], qb[2], qb[3], tb.dx, tb.dy, gb) : make_float2(0.0f, 0.0f);
+      float* ac = acc + (l == 0 ? kOff0 : kOff1);
+      btap_scatter<kBW01, true>(ac, ta, true, ga);
+      btap_scatter<kBW01, true>(ac, tb, has1, gb);
+    };
+    {
+      float2 goa, gob;
+      deform_bwd(0, box0, xb0, yb0, x0, y0, o00, o01, ta0, tb0, ga0, gb0, goa, gob);
+      float2* GO = reinterpret_cast<float2*>(prm.g_off0) + pix * TAPS;
+      GO[t0] = goa;
+      if (has1) GO[t1] = gob;
+    }
+    {
+      float2 goa, gob;
+      deform_bwd(1, box1, xb1, yb1, x1c, y1c, o10, o11, ta1, tb1, ga1, gb1, goa, gob);
+      goa.x += up0.x; goa.y += up0.y;                           // + upstream gradient on offset[1]_out (later calls)
+      if (has1) { gob.x += up1.x; gob.y += up1.y; }
+      // g_m partial: (gO_1 + upstream) . offset[1]_out  (divided by m below).  The centre tap is READ as 0 by the
+      // lookup (Q5) but autograd's mul backward multiplies by the stored, unzeroed value -- reproduced here.
+      gm_part = __fmaf_rn(goa.x, o10_raw.x, __fmul_rn(goa.y, o10_raw.y));
+      if (has1) gm_part += __fmaf_rn(gob.x, o11.x, __fmul_rn(gob.y, o11.y));
+      float2* GO = reinterpret_cast<float2*>(prm.g_off1) + pix * TAPS;
+      GO[t0] = make_float2(__fmul_rn(goa.x, m), __fmul_rn(goa.y, m));
+      if (has1) GO[t1] = make_float2(__fmul_rn(gob.x, m), __fmul_rn(gob.y, m));
+    }
+    __syncwarp();                                               // shared atomics of this warp are done
+
+    // ---------------- mask path: g_m -> sigmoid -> 9-tap variance -> level-1 scatter (r = 1 plain lookup)
+    BTap tm;
+    float gvk;
+    {
+      const int H2 = prm.H2[1], W2 = prm.W2[1];
+      const int fx = floor_to_int(x1c), fy = floor_to_int(y1c);
+      tm.dx = __fsub_rn(x1c, floorf(x1c));
+      tm.dy = __fsub_rn(y1c, floorf(y1c));
+      btap_setup<kBW01, kBH01>(tm, xb1, yb1, fx, fy, mi, mj, 1, H2, W2);
+      float q[4];
+      const float* b = box1 + tm.idx;
+      q[0] = b[0]; q[1] = b[1]; q[2] = b[kBW01]; q[3] = b[kBW01 + 1];
+      if (__any_sync(0xffffffffu, tm.gate && !tm.inbox)) {
+        if (tm.gate && !tm.inbox) {
+          const float* g = prm.lvl[1] + pix * (size_t)(H2 * W2) + (size_t)tm.y1 * W2 + tm.x1;
+          q[0] = __ldg(g); q[1] = tm.xo ? __ldg(g + 1) : 0.0f; q[2] = tm.yo ? __ldg(g + W2) : 0.0f;
+          q[3] = (tm.xo && tm.yo) ? __ldg(g + W2 + 1) : 0.0f;
+        }
+      }
+      const float v = (lane < 9 && tm.gate) ? blend4(q[0], q[1], q[2], q[3], tm.dx, tm.dy) : 0.0f;
+      float s = v;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = __shfl_sync(0xffffffffu, s, 0) / 9.0f;
+      const float g_m = warp_sum(gm_part) / m;
+      const float g_var = g_m * m * (1.0f - m);
+      gvk = lane < 9 ? g_var * 0.25f * (v - mean) : 0.0f;       // 2 (v - mean) / (9 - 1)
+      btap_scatter<kBW01, false>(acc + kOff1, tm, lane < 9, gvk);
+    }
+    // ---------------- zero-offset levels 2 and 3: scatter only (their offsets are detached zeros, corr.py:131-134)
+    BTap ta2, tb2, ta3, tb3;
+    int xb2, yb2, xb3, yb3;
+    auto uniform_bwd = [&](int l, float cx, float cy, BTap& ta, BTap& tb, int& xb, int& yb) {
+      const int H2 = prm.H2[l], W2 = prm.W2[l];
+      const float px = __fadd_rn(0.0f, cx), py = __fadd_rn(0.0f, cy);
+      const int fx = floor_to_int(px), fy = floor_to_int(py);
+      xb = box_origin_x(fx, 3, W2);
+      yb = box_origin_y(fy, 3, H2);
+      ta.dx = tb.dx = __fsub_rn(px, (float)fx);
+      ta.dy = tb.dy = __fsub_rn(py, (float)fy);
+      btap_setup<kBW23, kBH23>(ta, xb, yb, fx, fy, i0, j0, R, H2, W2);
+      btap_setup<kBW23, kBH23>(tb, xb, yb, fx, fy, i1, j1, R, H2, W2);
+      float* ac = acc + (l == 2 ? kOff2 : kOff3);
+      btap_scatter<kBW23, false>(ac, ta, true, sg[(l * TAPS + t0) * kOutPitch]);
+      btap_scatter<kBW23, false>(ac, tb, has1, sg[(l * TAPS + t1c) * kOutPitch]);
+    };
+    uniform_bwd(2, x2c, y2c, ta2, tb2, xb2, yb2);
+    uniform_bwd(3, x3c, y3c, ta3, tb3, xb3, yb3);
+    __syncwarp();
+
+    // ---------------- stream the four dense slices (zeros + box), then the rare out-of-box taps with global atomics
+    float* G2 = prm.gv[2] + pix * (size_t)(prm.H2[2] * prm.W2[2]);
+    float* G3 = prm.gv[3] + pix * (size_t)(prm.H2[3] * prm.W2[3]);
+    write_slice<kBW01, kBH01>(G0, acc + kOff0, xb0, yb0, prm.H2[0], prm.W2[0], lane);
+    write_slice<kBW01, kBH01>(G1, acc + kOff1, xb1, yb1, prm.H2[1], prm.W2[1], lane);
+    write_slice<kBW23, kBH23>(G2, acc + kOff2, xb2, yb2, prm.H2[2], prm.W2[2], lane);
+    write_slice<kBW23, kBH23>(G3, acc + kOff3, xb3, yb3, prm.H2[3], prm.W2[3], lane);
+    __syncwarp();                                               // slice stores ordered before the atomics below
+    const bool any_miss = (ta0.gate && !ta0.inbox) || (has1 && tb0.gate && !tb0.inbox) || (ta1.gate && !ta1.inbox) ||
+                          (has1 && tb1.gate && !tb1.inbox) || (lane < 9 && tm.gate && !tm.inbox) ||
+                          (ta2.gate && !ta2.inbox) || (has1 && tb2.gate && !tb2.inbox) || (ta3.gate && !ta3.inbox) ||
+                          (has1 && tb3.gate && !tb3.inbox);
+    if (__any_sync(0xffffffffu, any_miss)) {
+      __threadfence();
+      btap_scatter_global(G0, ta0, true, ga0, prm.W2[0]);
+      btap_scatter_global(G0, tb0, has1, gb0, prm.W2[0]);
+      btap_scatter_global(G1, ta1, true, ga1, prm.W2[1]);
+      btap_scatter_global(G1, tb1, has1, gb1, prm.W2[1]);
+      btap_scatter_global(G1, tm, lane < 9, gvk, prm.W2[1]);
+      btap_scatter_global(G2, ta2, true, sg[(2 * TAPS + t0) * kOutPitch], prm.W2[2]);
+      btap_scatter_global(G2, tb2, has1, sg[(2 * TAPS + t1c) * kOutPitch], prm.W2[2]);
+      btap_scatter_global(G3, ta3, true, sg[(3 * TAPS + t0) * kOutPitch], prm.W2[3]);
+      btap_scatter_global(G3, tb3, has1, sg[(3 * TAPS + t1c) * kOutPitch], prm.W2[3]);
+    }
+    __syncwarp();
+    if (k + 2 < kPixPerWarp) {
+      const float nx = __shfl_sync(0xffffffffu, cmine.x, k + 2), ny = __shfl_sync(0xffffffffu, cmine.y, k + 2);
+      if (lane == 0) issue(k + 2, nx, ny);
+    }
+  }
+}
+
+}  // namespace lgu
+
+extern "C" int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lvl1, const float* coords,
+                                              const float* off0, const float* off1_out, const float* mask,
+                                              const float* corr_grad, const float* off1_out_grad, float* gv0,
+                                              float* gv1, float* gv2, float* gv3, float* off0_grad, float* off1_grad,
+                                              int E, int H, int W, int num_levels, int radius, void* stream) {
+  using namespace lgu;
+  if (E == 0) return LGU_OK;
+  LGU_REQUIRE(lvl0 && lvl1 && coords && off0 && off1_out && mask && corr_grad && gv0 && gv1 && gv2 && gv3 &&
+                  off0_grad && off1_grad,
+              "lgu_corr_lookup_fused_backward: null pointer");
+  LGU_REQUIRE(E > 0 && H > 0 && W > 0, "lgu_corr_lookup_fused_backward: bad sizes E=%d H=%d W=%d", E, H, W);
+  if (num_levels != 4 || radius != 3 || (W % 32) != 0 || (H % 8) != 0) {
+    set_error("lgu_corr_lookup_fused_backward: only num_levels=4, radius=3, W%%32==0, H%%8==0 are implemented "
+              "(got levels=%d r=%d H=%d W=%d); use the per-level operators", num_levels, radius, H, W);
+    return LGU_ERR_UNSUPPORTED;
+  }
+  const int P = H * W;
+  const long long nslices = (long long)E * P;
+  LGU_REQUIRE(nslices < 2147483647LL, "lgu_corr_lookup_fused_backward: E*H*W = %lld too large", nslices);
+  float* gv[4] = {gv0, gv1, gv2, gv3};
+  for (int l = 0; l < 4; ++l)
+    LGU_REQUIRE((reinterpret_cast<uintptr_t>(gv[l]) & 15) == 0, "lgu_corr_lookup_fused_backward: gv%d not 16-byte aligned", l);
+  LGU_REQUIRE(((reinterpret_cast<uintptr_t>(lvl0) | reinterpret_cast<uintptr_t>(lvl1)) & 15) == 0,
+              "lgu_corr_lookup_fused_backward: pyramid levels must be 16-byte aligned");
+  FusedMaps maps;
+  FusedLookupBwdParams prm;
+  const float* lv[2] = {lvl0, lvl1};
+  for (int l = 0; l < 4; ++l) {
+    prm.H2[l] = H >> l;
+    prm.W2[l] = W >> l;
+    prm.gv[l] = gv[l];
+  }
+  for (int l = 0; l < 2; ++l) {
+    prm.lvl[l] = lv[l];
+    const int rc = make_slice_map(&maps.m[l], lv[l], nslices, H >> l, W >> l, fl::kBW01, fl::kBH01);
+    if (rc) return rc;
+  }
+  maps.m[2] = maps.m[0];
+  maps.m[3] = maps.m[0];
+  prm.coords = coords; prm.off0 = off0; prm.off1 = off1_out; prm.mask = mask; prm.g_out = corr_grad;
+  prm.g_off1_out = off1_out_grad; prm.g_off0 = off0_grad; prm.g_off1 = off1_grad;
+  prm.P = P;
+  prm.tiles_per_edge = P / fl::kTile;
+  const long long nblk = (long long)E * prm.tiles_per_edge;
+  LGU_REQUIRE(nblk < 2147483647LL, "lgu_corr_lookup_fused_backward: grid too large (%lld CTAs)", nblk);
+  cudaError_t e = cudaFuncSetAttribute(lookup_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       flb::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("lgu_corr_lookup_fused_backward: cannot opt in to %d B of shared memory: %s", flb::kSmemBytes,
+              cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  lookup_fused_bwd_kernel<<<(unsigned)nblk, fl::kThreads, flb::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
+  return check_launch("lgu_corr_lookup_fused_backward");
+}

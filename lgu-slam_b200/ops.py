@@ -243,8 +243,8 @@ def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_lev
 def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False):
     """CorrBlock.__call__'s data path (corr.py:88-109) in one TMA-staged kernel.
     pyramid: 4 tensors [E,H,W,H>>l,W>>l]; coords [E,H,W,2] (x,y; level-0 units); off0, off1 [E,H,W,98] or
-    [E,H,W,7,7,2] -- both mutated in place: centre taps zeroed (Q5), off1 multiplied by this call's uncertainty
-    mask (Q7).  Returns corr [E,196,H,W] (and the mask [E,H,W] if return_mask)."""
+    [E,H,W,7,7,2]; off1 is mutated in place (multiplied by this call's uncertainty mask, Q7); the centre taps are
+    read as 0 (Q5) but left untouched in memory.  Returns corr [E,196,H,W] (and the mask [E,H,W] if return_mask)."""
     if len(pyramid) != 4:
         raise RuntimeError("corr_lookup_fused needs a 4-level pyramid")
     E, H, W = pyramid[0].shape[:3]
@@ -270,3 +270,33 @@ def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False):
                                               _i(E), _i(H), _i(W), _i(4), _i(radius), _stream(coords))
     _lib.check(st, "corr_lookup_fused")
     return (corr, mask) if return_mask else corr
+
+
+def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad, off1_out_grad=None):
+    """Backward of corr_lookup_fused in one launch (what autograd runs for corr.py:88-109 in training).
+    pyramid: the 4 levels (only levels 0-1 are read); off1_out: off1 after the forward; mask [E,H,W] from the
+    forward; corr_grad [E,196,H,W]; off1_out_grad: upstream gradient on the post-mask offsets (later calls) or None.
+    Returns (gv0, gv1, gv2, gv3, off0_grad, off1_grad) -- dense level gradients, off1_grad w.r.t. the PRE-mask off1."""
+    E, H, W = pyramid[0].shape[:3]
+    for l, t in enumerate(pyramid):
+        _chk(t, f"pyramid[{l}]", 5)
+    _chk(coords, "coords", 4); _chk(mask, "mask", 3); _chk(corr_grad, "corr_grad", 4)
+    if tuple(corr_grad.shape) != (E, 196, H, W) or tuple(mask.shape) != (E, H, W) or tuple(coords.shape) != (E, H, W, 2):
+        raise RuntimeError("corr_lookup_fused_backward: inconsistent shapes")
+    for name, o in (("off0", off0), ("off1_out", off1_out), ("off1_out_grad", off1_out_grad)):
+        if o is None and name == "off1_out_grad":
+            continue
+        if not (isinstance(o, torch.Tensor) and o.is_cuda and o.is_contiguous() and o.dtype == torch.float32
+                and o.numel() == E * H * W * 98):
+            raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor with {E * H * W * 98} elements")
+    gv = [torch.empty_like(t) for t in pyramid]
+    g0 = torch.empty(E, H, W, 98, dtype=torch.float32, device=coords.device)
+    g1 = torch.empty_like(g0)
+    with torch.cuda.device(coords.device):
+        st = _lib.lib().lgu_corr_lookup_fused_backward(
+            _p(pyramid[0]), _p(pyramid[1]), _p(coords), _p(off0), _p(off1_out), _p(mask), _p(corr_grad),
+            _p(off1_out_grad) if off1_out_grad is not None else ctypes.c_void_p(0),
+            _p(gv[0]), _p(gv[1]), _p(gv[2]), _p(gv[3]), _p(g0), _p(g1), _i(E), _i(H), _i(W), _i(4), _i(3),
+            _stream(coords))
+    _lib.check(st, "corr_lookup_fused_backward")
+    return gv[0], gv[1], gv[2], gv[3], g0, g1

@@ -52,7 +52,11 @@ def test_corrblock_fused_inference_matches_per_op_path():
                 out_p, _, _ = blk_p(coords)
                 assert out_f.shape == (b, n, 196, 48, 64)
                 assert (out_f - out_p).abs().max().item() <= 1e-5, f"call {it}"
-                assert (blk_f.offset[1] - blk_p.offset[1].reshape(blk_f.offset[1].shape)).abs().max().item() <= 1e-5
+                # cumulative offset state, except the centre tap (tap 24): read as 0 by both paths, zeroed in memory
+                # only by the per-op path's in-place quirk Q5
+                d = (blk_f.offset[1] - blk_p.offset[1].reshape(blk_f.offset[1].shape)).view(n, 48, 64, 49, 2)
+                d[..., 24, :] = 0
+                assert d.abs().max().item() <= 1e-5
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
 

@@ -56,11 +56,16 @@ def test_fused_lookup_matches_oracle_composition(ops, oracle, E, seed, big, prob
     a, b = got[:, 49:98], want[:, 49:98]
     err = (torch.nan_to_num(a) - torch.nan_to_num(b)).abs().max().item()
     assert err <= ATOL, f"level 1: max abs err {err}"
-    # side effects
-    assert torch.equal(off0.cpu(), offs[0]), "off0: centre tap zeroed in place, nothing else touched"
-    o1 = off1.cpu()
-    assert torch.equal(torch.isnan(o1), torch.isnan(offs[1]))
-    assert (torch.nan_to_num(o1) - torch.nan_to_num(offs[1])).abs().max().item() <= 1e-5
+    # side effects: off0 untouched; off1 <- off1 * mask for every tap (the centre tap is only READ as zero: inside
+    # CorrBlock the reference zeroes a temporary copy, so the stored value survives there too)
+    assert torch.equal(off0.cpu(), c["offsets"][0])
+    o1 = off1.cpu().view(E, 48, 64, 49, 2)
+    w1 = offs[1].view(E, 48, 64, 49, 2)
+    keep = [t for t in range(49) if t != 24]
+    assert torch.equal(torch.isnan(o1[..., keep, :]), torch.isnan(w1[..., keep, :]))
+    assert (torch.nan_to_num(o1[..., keep, :]) - torch.nan_to_num(w1[..., keep, :])).abs().max().item() <= 1e-5
+    centre = c["offsets"][1].view(E, 48, 64, 49, 2)[..., 24, :] * mask.cpu()[..., None]
+    assert torch.allclose(torch.nan_to_num(o1[..., 24, :]), torch.nan_to_num(centre), atol=1e-6)
     assert mask.shape == (E, 48, 64)
 
 
@@ -109,3 +114,51 @@ def test_fused_lookup_unsupported_configuration_is_reported(ops):
     with pytest.raises(RuntimeError, match="W%32"):
         ops.corr_lookup_fused(pyr, torch.zeros(1, 8, 16, 2, device=dev), torch.zeros(1, 8, 16, 98, device=dev),
                               torch.zeros(1, 8, 16, 98, device=dev), 3)
+
+
+def _per_op_autograd(corr_mod, pyr, coords, off0, off1):
+    """The reference's autograd graph for CorrBlock.__call__ (corr.py:88-109) on the per-level operators."""
+    E = coords.shape[0]
+    c = coords.permute(0, 3, 1, 2).contiguous()
+    m = corr_mod.CorrSampler.apply(pyr[1], c / 2, 1)
+    mask = torch.sigmoid(torch.var(m.permute(0, 3, 4, 1, 2), dim=[3, 4])).view(E, 48, 64, 1)
+    off1_out = off1 * mask
+    z = torch.zeros_like(off0)
+    outs = []
+    for l, o in enumerate((off0, off1_out, z, z.clone())):
+        # like the reference inside CorrBlock, hand the sampler a COPY (`.contiguous()` of a permuted view)
+        outs.append(corr_mod.DefCorrSampler.apply(pyr[l], c / 2 ** l, o.clone().view(E, 48, 64, 7, 7, 2), 3)
+                    .view(E, 49, 48, 64))
+    return torch.cat(outs, dim=1), off1_out
+
+
+@pytest.mark.parametrize("big", [False, True])
+def test_fused_backward_matches_per_op_autograd(ops, big):
+    from importlib import import_module
+    corr_mod = import_module("lgu-slam_b200.corr")
+    E = 2
+    c = _case(E, 61, big_offsets=big)
+    dev = "cuda"
+    g = inputs.gen(62)
+    pyr_a = [torch.randn(E, 48, 64, 48 >> l, 64 >> l, generator=g).to(dev).requires_grad_() for l in range(4)]
+    pyr_b = [p.detach().clone().requires_grad_() for p in pyr_a]
+    coords = c["coords"].to(dev)
+    off0_a, off1_a = c["offsets"][0].to(dev).requires_grad_(), c["offsets"][1].to(dev).requires_grad_()
+    off0_b, off1_b = off0_a.detach().clone().requires_grad_(), off1_a.detach().clone().requires_grad_()
+    g_corr = torch.randn(E, 196, 48, 64, generator=g).to(dev)
+    g_off1 = (0.1 * torch.randn(E, 48, 64, 98, generator=g)).to(dev)
+
+    out_a, off1_out_a, _ = corr_mod.FusedCorrLookup.apply(*pyr_a, coords, off0_a, off1_a)
+    ((out_a * g_corr).sum() + (off1_out_a * g_off1).sum()).backward()
+    out_b, off1_out_b = _per_op_autograd(corr_mod, pyr_b, coords, off0_b, off1_b)
+    ((out_b * g_corr).sum() + (off1_out_b * g_off1).sum()).backward()
+
+    assert (out_a - out_b).abs().max().item() <= ATOL
+    for l in range(4):
+        err = (pyr_a[l].grad - pyr_b[l].grad).abs().max().item()
+        scale = pyr_b[l].grad.abs().max().item()
+        assert err <= 2e-5 * max(1.0, scale), f"level {l} volume grad: {err} (scale {scale})"
+    for name, a, b in (("off0", off0_a, off0_b), ("off1", off1_a, off1_b)):
+        err = (a.grad - b.grad).abs().max().item()
+        scale = b.grad.abs().max().item()
+        assert err <= 2e-5 * max(1.0, scale), f"{name} grad: {err} (scale {scale})"
