@@ -14,13 +14,17 @@
 // accumulator half, and the two halves of TMEM (512 columns) are double-buffered between the MMA issuer
 // and the epilogue.  A band of two halves (8 target rows) closes all four pyramid levels locally.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over units):
+// Warp roles (320 threads, 1 CTA / SM, persistent over units):
 //   warp 0   : TMA producer   (cp.async.bulk.tensor loads of A / B tiles, mbarrier expect_tx)
 //   warp 1   : MMA issuer     (tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accumulate in TMEM) + TMEM alloc
-//   warps 2-5: epilogue       (tcgen05.ld 32x32b.x32 -> registers; thread == source pixel == TMEM lane;
-//                              level 0/1 rows staged in 128B-swizzled shared memory and written with TMA
-//                              bulk stores, level 2/3 rows (64 B / 32 B) stored directly; the Gaussian
-//                              window (<= 81 elements per source pixel) is patched in shared memory)
+//   warps 2-9: epilogue       (tcgen05.ld 32x32b.x32 -> registers; thread == source pixel == TMEM lane; the two
+//                              warps of a TMEM lane quadrant split the 64 target columns in halves (xs = 0 / 1):
+//                              all four pyramid levels close inside a 32-column half.  Level-0 rows (128 B) and
+//                              level-1 rows (64 B) are staged in swizzled shared memory and written with TMA
+//                              bulk stores, level 2/3 rows (32 B / 16 B) stored directly; the Gaussian window
+//                              (<= 81 elements per source pixel) is patched in shared memory).
+//                              With 4 epilogue warps the kernel was bound by their instruction issue (ncu: one
+//                              warp per scheduler, 17 % issue-active, DRAM 39 %).
 // Precision: PREC 1 = one fp16 product (exact for fp16-valued feature maps: the inference path);
 //            PREC 2 = hi/lo fp16 split of both operands, 3 MMAs (hi*hi + hi*lo + lo*hi): ~2^-21 relative
 //            per product, for fp32-valued feature maps (the training path).
@@ -136,7 +140,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 // ---------------------------------------------------------------------------------------------
 // Kernel configuration
 // ---------------------------------------------------------------------------------------------
-constexpr int kBpThreads = 192;
+constexpr int kBpThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr bool kL1Direct = false;   // measured: direct 64-byte row stores are slower (727 vs 610 us at E=48)
 constexpr int kTileM = 128;      // source pixels per unit
 constexpr int kChunkN = 128;     // target pixels per MMA chunk (2 target rows of 64)
 constexpr int kC = 128;          // channels (K)
@@ -147,10 +153,10 @@ template <int PREC>
 struct BpCfg {
   static constexpr int kPlanes = PREC;                        // hi (+ lo)
   static constexpr int kStages = PREC == 1 ? 3 : 2;           // B-chunk pipeline depth
-  static constexpr int kStoreBufs = PREC == 1 ? 4 : 2;        // 4 KB staging buffers per epilogue warp
+  static constexpr int kStoreBufs = PREC == 1 ? 2 : 1;        // 4 KB staging buffers per epilogue warp (227 KB budget)
   static constexpr int kABytes = kPlanes * kPlaneBytes;
   static constexpr int kStageBytes = kPlanes * kPlaneBytes;
-  static constexpr int kStoreBytes = 4 * kStoreBufs * 4096;
+  static constexpr int kStoreBytes = kEpiWarps * kStoreBufs * 4096;
   static constexpr int kBarOffset = kABytes + kStages * kStageBytes + kStoreBytes;
   static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + 1 KB alignment slack
 };
@@ -161,6 +167,7 @@ struct BpParams {
   const float* means;   // [E,P,2] or null
   const float* covs;    // [E,P,2]
   const float* den;     // [E,P]
+  float* lvl1;          // [E,P,Q/4] or null (direct-store path)
   float* lvl2;          // [E,P,Q/16] or null
   float* lvl3;          // [E,P,Q/64] or null
   int E, P, H, gauss_radius, round_half, num_units, has_l1;
@@ -216,7 +223,7 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(t_full + b, 1);
-      mbar_init(t_empty + b, 4);                        // one arrival per epilogue warp
+      mbar_init(t_empty + b, kEpiWarps);                // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -299,18 +306,21 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
-    const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+    // =============================== epilogue (warps 2..9) ===============================
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may read (warp id % 4)
+    const int xs = (warp - 2) >> 2;                     // which 32-column half of the 64 target columns
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     uint8_t* my_store = sStore + (warp - 2) * Cfg::kStoreBufs * 4096;
     int sbuf = 0;
     const int gr = prm.gauss_radius;
     const unsigned rdg = 2u * (unsigned)gr + 1u;
     const int rsw = lane & 7;                           // 128B swizzle phase of this thread's staging row
+    const int rsw1 = (lane >> 1) & 3;                   // 64B swizzle phase (level-1 rows)
+    const int x0 = xs * 32;
 
     // stage one 32-float row segment per lane and hand the 32x32 tile to the TMA store engine
-    auto store_tile = [&](float (&v)[32], const CUtensorMap* map, int col, int row0, bool patch, int yy, int x0,
-                          float mx, float my, float c1, float c2, float den, unsigned bx) {
+    auto store_tile = [&](float (&v)[32], int col, int row0, bool patch, int yy, float mx, float my, float c1, float c2,
+                          float den, unsigned bx) {
       if (lane == 0) tma_wait_read<Cfg::kStoreBufs - 1>();
       __syncwarp();
       float4* rowp = reinterpret_cast<float4*>(my_store + sbuf * 4096 + lane * 128);
@@ -340,7 +350,22 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(map, my_store + sbuf * 4096, col, row0);
+        tma_store_2d(&map_l0, my_store + sbuf * 4096, col, row0);
+        tma_commit();
+      }
+      sbuf = (sbuf + 1 == Cfg::kStoreBufs) ? 0 : sbuf + 1;
+    };
+    // level 1: 16 floats (64 B) per lane, 64B-swizzled 32-row tile (2 KB of a staging buffer)
+    auto store_l1 = [&](const float (&v)[16], int col, int row0) {
+      if (lane == 0) tma_wait_read<Cfg::kStoreBufs - 1>();
+      __syncwarp();
+      float4* rowp = reinterpret_cast<float4*>(my_store + sbuf * 4096 + lane * 64);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rowp[c ^ rsw1] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_l1, my_store + sbuf * 4096, col, row0);
         tma_commit();
       }
       sbuf = (sbuf + 1 == Cfg::kStoreBufs) ? 0 : sbuf + 1;
@@ -361,71 +386,74 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
         bx = (unsigned)floor_to_int(mx) - (unsigned)gr;
         by = (unsigned)floor_to_int(my) - (unsigned)gr;
       }
-      float l2_prev[16];
+      float l2_prev[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) l2_prev[i] = 0.f;
+      for (int i = 0; i < 8; ++i) l2_prev[i] = 0.f;
 
       for (int h = 0; h < halves; ++h, ++half_it) {
         const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
         mbar_wait(t_full + buf, buf_use & 1);
         tc_fence_after();
-        const uint32_t tcol = tmem_base + lane_base + buf * 256;
-        float l1[2][32];
+        const uint32_t tcol = tmem_base + lane_base + buf * 256 + xs * 32;
+        float l1[2][16];
 #pragma unroll
         for (int rp = 0; rp < 2; ++rp) {
-#pragma unroll
-          for (int xs = 0; xs < 2; ++xs) {
-            float a[32], b[32];
-            tmem_ld32(tcol + (2 * rp) * 64 + xs * 32, a);
-            tmem_ld32(tcol + (2 * rp + 1) * 64 + xs * 32, b);
-            if (rp == 1 && xs == 1) {
-              // last TMEM read of this half: hand the accumulator back to the MMA issuer
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(t_empty + buf);
-            }
-            if (prm.round_half) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                a[i] = __half2float(__float2half_rn(a[i]));
-                b[i] = __half2float(__float2half_rn(b[i]));
-              }
-            }
-            const int ya = 4 * h + 2 * rp, yb = ya + 1, x0 = xs * 32;
-            const bool pa = gr > 0 && ((unsigned)ya - by) < rdg;
-            const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
-            store_tile(a, &map_l0, ya * 64 + x0, row0, pa, ya, x0, mx, my, c1, c2, den, bx);
-            store_tile(b, &map_l0, yb * 64 + x0, row0, pb, yb, x0, mx, my, c1, c2, den, bx);
-            // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              l1[rp][xs * 16 + i] =
-                  __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a[2 * i], a[2 * i + 1]), b[2 * i]), b[2 * i + 1]), 0.25f);
+          float a[32], b[32];
+          tmem_ld32(tcol + (2 * rp) * 64, a);
+          tmem_ld32(tcol + (2 * rp + 1) * 64, b);
+          if (rp == 1) {
+            // last TMEM read of this half: hand the accumulator back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + buf);
           }
-          if (prm.has_l1)
-            store_tile(l1[rp], &map_l1, (2 * h + rp) * 32, row0, false, 0, 0, 0.f, 0.f, 1.f, 1.f, 1.f, 0u);
-        }
-        if (prm.lvl2 != nullptr) {
-          float l2[16];
+          if (prm.round_half) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              a[i] = __half2float(__float2half_rn(a[i]));
+              b[i] = __half2float(__float2half_rn(b[i]));
+            }
+          }
+          const int ya = 4 * h + 2 * rp, yb = ya + 1;
+          const bool pa = gr > 0 && ((unsigned)ya - by) < rdg;
+          const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
+          store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx);
+          store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx);
+          // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
 #pragma unroll
           for (int i = 0; i < 16; ++i)
+            l1[rp][i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a[2 * i], a[2 * i + 1]), b[2 * i]), b[2 * i + 1]), 0.25f);
+          if (prm.has_l1) {
+            if (kL1Direct) {   // 64-byte rows cost the TMA store engine a full row slot each: use the idle LSU instead
+              float4* o1 = reinterpret_cast<float4*>(prm.lvl1 + pix * (size_t)(Q >> 2) + (2 * h + rp) * 32 + xs * 16);
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                __stcs(o1 + c, make_float4(l1[rp][4 * c], l1[rp][4 * c + 1], l1[rp][4 * c + 2], l1[rp][4 * c + 3]));
+            } else {
+              store_l1(l1[rp], (2 * h + rp) * 32 + xs * 16, row0);
+            }
+          }
+        }
+        if (prm.lvl2 != nullptr) {
+          float l2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
             l2[i] = __fmul_rn(
                 __fadd_rn(__fadd_rn(__fadd_rn(l1[0][2 * i], l1[0][2 * i + 1]), l1[1][2 * i]), l1[1][2 * i + 1]), 0.25f);
-          float4* o2 = reinterpret_cast<float4*>(prm.lvl2 + pix * (size_t)(Q >> 4) + h * 16);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) o2[c] = make_float4(l2[4 * c], l2[4 * c + 1], l2[4 * c + 2], l2[4 * c + 3]);
+          float4* o2 = reinterpret_cast<float4*>(prm.lvl2 + pix * (size_t)(Q >> 4) + h * 16 + xs * 8);
+          o2[0] = make_float4(l2[0], l2[1], l2[2], l2[3]);
+          o2[1] = make_float4(l2[4], l2[5], l2[6], l2[7]);
           if ((h & 1) == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) l2_prev[i] = l2[i];
+            for (int i = 0; i < 8; ++i) l2_prev[i] = l2[i];
           } else if (prm.lvl3 != nullptr) {
-            float l3[8];
+            float l3[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
               l3[i] = __fmul_rn(
                   __fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2 * i], l2_prev[2 * i + 1]), l2[2 * i]), l2[2 * i + 1]), 0.25f);
-            float4* o3 = reinterpret_cast<float4*>(prm.lvl3 + pix * (size_t)(Q >> 6) + (h >> 1) * 8);
-            o3[0] = make_float4(l3[0], l3[1], l3[2], l3[3]);
-            o3[1] = make_float4(l3[4], l3[5], l3[6], l3[7]);
+            *reinterpret_cast<float4*>(prm.lvl3 + pix * (size_t)(Q >> 6) + (h >> 1) * 8 + xs * 4) =
+                make_float4(l3[0], l3[1], l3[2], l3[3]);
           }
         }
       }
@@ -487,7 +515,8 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D row-major tensor [rows, cols] of `elem_bytes`-byte elements, box [box_rows, box_cols], 128B swizzle.
 static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows,
-                       uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+                       uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -498,7 +527,7 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes,
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
               (unsigned long long)rows, (unsigned long long)cols);
@@ -571,12 +600,12 @@ extern "C" int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, con
   rc = make_map_2d(&m0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, (uint64_t)E * P, P, 32, 32);
   if (rc) return rc;
   rc = make_map_2d(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl1 ? lvl1 : lvl0, (uint64_t)E * P, lvl1 ? P / 4 : P, 32,
-                   32);
+                   16, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
 
   BpParams prm;
   prm.ii = ii; prm.jj = jj; prm.means = means; prm.covs = covs; prm.den = den;
-  prm.lvl2 = lvl2; prm.lvl3 = lvl3;
+  prm.lvl1 = lvl1; prm.lvl2 = lvl2; prm.lvl3 = lvl3;
   prm.E = E; prm.P = P; prm.H = H; prm.gauss_radius = gauss_radius; prm.round_half = round_half;
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = lvl1 != nullptr;
