@@ -151,6 +151,17 @@ LGU_API int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const fl
                           const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                           int E, int H, int W, int num_levels, int radius, void* stream);
 
+/* The same fused lookup with the BACKEND path's semantics (AltCorrBlock.corr_fn, corr.py:174-215, whose samplers
+ * are lowMem_defSample.cu:27-134 and src/altcorr_kernel.cu:27-149): every bilinear corner is gated on its own
+ * (quirk Q4) and fractions are x - floor(x).  lvl_l here is the volume of level 0 source maps against the level-l
+ * POOLED target maps (lgu_build_volume).  shared_offsets = 1 reproduces the reference's offset-slab indexing
+ * `offset[b*n]` with N = 1 (quirk Q2): every edge reads the offsets of edge 0; apply_mask = 0 uses off1 as given
+ * (the caller has already multiplied it by the mask, corr.py:206) and writes nothing back. */
+LGU_API int lgu_altcorr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                             const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
+                             int E, int H, int W, int num_levels, int radius,
+                             int shared_offsets, int apply_mask, void* stream);
+
 /* Backward of lgu_corr_lookup_fused = what autograd runs for corr.py:88-109 in training (4 x
  * defCorr_index_backward, the offset[1]*mask / sigmoid / var chain, corr_index_backward), in one launch:
  *   gv0..gv3      dense gradients of the pyramid levels (each written exactly once; level 1 includes the mask path)
@@ -165,6 +176,18 @@ LGU_API int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lvl1,
                                    float* gv0, float* gv1, float* gv2, float* gv3,
                                    float* off0_grad, float* off1_grad,
                                    int E, int H, int W, int num_levels, int radius, void* stream);
+
+/* All-pairs volume between two DIFFERENT map sets, no Gaussian, no pooling:
+ *   volume[e, p, q] = sum_c fmaps1[ii[e], p, c] * fmaps2[jj[e], q, c]        (fp32 accumulate on tcgen05)
+ * fmaps1 [T1,P,C], fmaps2 [T2,Q,C]: channels-last fp16 planes, already scaled (the caller's /4, corr.py:163);
+ * lo planes for precision 2 as in lgu_build_pyramid.  volume [E,P,Q].  C = 128, P % 128 == 0, Q % 4 == 0.
+ * This is how the backend path (AltCorrBlock, corr.py:155-215) is served on B200: its pyramid pools the FEATURE
+ * maps (one volume per level against the pooled target map) and the reference avoids materialising them only for
+ * lack of memory (lowMem_defSample.cu); with 180 GB of HBM a chunk of edges is materialised per level on tensor
+ * cores and sampled with the fused lookup. */
+LGU_API int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi, const void* fmaps2_lo,
+                     const int32_t* ii, const int32_t* jj, float* volume,
+                     int T1, int T2, int E, int P, int Q, int C, int precision, void* stream);
 
 /* fmaps [T,C,P] fp32 or fp16 (NCHW as the encoders emit) -> channels-last fp16 planes
  * hi [T,P,C] (and lo [T,P,C] = fp16(x/4 - hi) when lo != NULL), pre-scaled by 1/4 (corr.py:148-149). */

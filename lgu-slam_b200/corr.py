@@ -287,10 +287,18 @@ class CorrBlock:
 # AltCorrBlock (backend, no volume)
 # ------------------------------------------------------------------------------------------------
 class AltCorrBlock:
-    """corr.py:155-249: on-the-fly correlation for global BA.  `strict_ref=True` keeps the reference's
-    offset-slab indexing (quirk Q2: with S == 1 every edge of a chunk reads edge 0's offsets)."""
+    """corr.py:155-249: correlation for global BA without a persistent volume.  `strict_ref=True` keeps the
+    reference's offset-slab indexing (quirk Q2: with S == 1 every edge of a chunk reads edge 0's offsets).
 
-    def __init__(self, ofsMap, ofs_residual, GA, fmaps, num_levels=4, radius=3, strict_ref=True):
+    materialize=True (default where supported: 4 levels, r = 3, C = 128, H*W % 128 == 0, W % 32 == 0): each call
+    builds the chunk's four volumes (level-0 source maps x level-l pooled target maps) on tcgen05 into scratch HBM
+    (50 MB / edge; the reference's on-the-fly sampler exists only because 12-24 GB GPUs could not hold them) and
+    samples them with the fused TMA-staged lookup in per-corner-gating mode.  materialize=False: the reference's
+    op sequence on the drop-in operators (altcorr_forward + 4 x lowMem_defSample)."""
+
+    MAX_EDGES_PER_PASS = 256          # scratch bound: 256 x 50 MB = 12.8 GB
+
+    def __init__(self, ofsMap, ofs_residual, GA, fmaps, num_levels=4, radius=3, strict_ref=True, materialize=None):
         self.num_levels = num_levels
         self.radius = radius
         self.GA = GA
@@ -304,17 +312,77 @@ class AltCorrBlock:
         for i in range(num_levels):
             self.pyramid.append(cur.permute(0, 2, 3, 1).contiguous().view(B, N, H >> i, W >> i, C))
             cur = F.avg_pool2d(cur, 2, stride=2)
+        can = (num_levels == 4 and radius == 3 and C == 128 and (H * W) % 128 == 0 and W % 32 == 0 and H % 8 == 0
+               and B == 1 and fmaps.is_cuda)
+        self.materialize = can if materialize is None else (materialize and can)
+        self._planes = None
+
+    def _level_planes(self):
+        """Channels-last fp16 operand planes per level: the pyramid itself when the buffer is fp16 (the backend's case,
+        depth_video.py:36 -- products are then exact), hi/lo split for fp32 buffers."""
+        if self._planes is None:
+            planes = []
+            for lvl in self.pyramid:
+                x = lvl.reshape(lvl.shape[1], -1, lvl.shape[-1])                  # [T, Q_l, C] (B == 1)
+                if x.dtype == torch.float16:
+                    planes.append((x.contiguous(), None))
+                else:
+                    hi = x.float().half()
+                    planes.append((hi.contiguous(), (x.float() - hi.float()).half().contiguous()))
+            self._planes = planes
+        return self._planes
+
+    def _corr_materialized(self, coords, ii, jj):
+        B, N, H, W, S, _ = coords.shape
+        assert B == 1 and S == 1, "the materialised path serves the reference's only call shape (B = S = 1)"
+        planes = self._level_planes()
+        c = coords.reshape(N, H, W, 2).float().contiguous()
+        ii32, jj32 = ii.to(torch.int32).contiguous(), jj.to(torch.int32).contiguous()
+        off0 = self.offset[0].reshape(N, H, W, -1).float().contiguous()
+        off1 = self.offset[1].reshape(N, H, W, -1).float().contiguous()
+        if self.strict_ref:
+            # Q2: every edge samples with edge 0's offsets; edge 0's level-1 offsets carry edge 0's mask (corr.py:201-206)
+            f1 = self.pyramid[0][0, ii[:1]].float().contiguous()
+            f2 = self.pyramid[1][0, jj[:1]].float().contiguous()
+            m0, = ops.altcorr_forward(f1, f2, (c[:1] / 2).view(1, 1, H, W, 2).contiguous(), MASK_RADIUS)
+            mask0 = torch.sigmoid(torch.var(m0.permute(0, 1, 3, 4, 2).reshape(1, H, W, 9), dim=3))
+            slab0 = (off0[:1].contiguous(), (off1[:1] * mask0.view(1, H, W, 1)).contiguous())
+        outs, masks, new_off1 = [], [], []
+        for s in range(0, N, self.MAX_EDGES_PER_PASS):
+            e = slice(s, min(N, s + self.MAX_EDGES_PER_PASS))
+            vols = [ops.build_volume(planes[0][0], planes[0][1], planes[l][0], planes[l][1], ii32[e], jj32[e])
+                    .view(-1, H, W, H >> l, W >> l) for l in range(self.num_levels)]
+            if self.strict_ref:
+                o, m = ops.altcorr_lookup_fused(vols, c[e], slab0[0], slab0[1], self.radius, shared_offsets=True,
+                                                apply_mask=False, return_mask=True)
+            else:
+                o1 = off1[e].clone()                                      # updated in place: offset[1] * mask
+                o, m = ops.altcorr_lookup_fused(vols, c[e], off0[e].contiguous(), o1, self.radius, shared_offsets=False,
+                                                apply_mask=True, return_mask=True)
+                new_off1.append(o1)
+            outs.append(o)
+            masks.append(m)
+            del vols
+        # the attribute the reference leaves behind: offset[1] * mask (corr.py:206)
+        if self.strict_ref:
+            self.offset[1] = self.offset[1] * torch.cat(masks, 0).view(N, H, W, 1)
+        else:
+            self.offset[1] = torch.cat(new_off1, 0) if len(new_off1) > 1 else new_off1[0]
+        out = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+        return out.view(B, N, -1, H, W, 1)
 
     def corr_fn(self, coords, ii, jj):
         B, N, H, W, S, _ = coords.shape
         rd = 2 * self.radius + 1
-        coords = coords.permute(0, 1, 4, 2, 3, 5)
         f1 = self.pyramid[0][:, ii]
         f1 = f1.reshape((B * N,) + f1.shape[2:])
         f2 = self.pyramid[0][:, jj]
         f2 = f2.reshape((B * N,) + f2.shape[2:])
         t = torch.cat(((f1 * 4.0).permute(0, 3, 1, 2), (f2 * 4.0).permute(0, 3, 1, 2)), dim=1).float()
         self.offset = _generate_offsets(self.ofsMap, self.ofs_residual, t)
+        if self.materialize and B == 1 and S == 1:
+            return self._corr_materialized(coords, ii, jj)
+        coords = coords.permute(0, 1, 4, 2, 3, 5)
         f1 = f1.float().contiguous()
 
         out = []

@@ -171,6 +171,8 @@ struct BpParams {
   float* lvl2;          // [E,P,Q/16] or null
   float* lvl3;          // [E,P,Q/64] or null
   int E, P, H, gauss_radius, round_half, num_units, has_l1;
+  int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
+  int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
 };
 
 // Gaussian residual of one element (gaussianAttn.cu:58-64 + gaussianMask_cuda.py:85-86), fp32, no contraction.
@@ -187,6 +189,7 @@ __device__ __forceinline__ float gauss_residual(float v, int x1, int y1, float m
 template <int PREC>
 __global__ void __launch_bounds__(kBpThreads, 1)
 build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                     const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                      const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
                      const BpParams prm) {
   using Cfg = BpCfg<PREC>;
@@ -207,12 +210,13 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = prm.P;
   const int tiles_m = P / kTileM;
-  const int halves = prm.H / 4;                         // 4 target rows per TMEM half
-  const int Q = P;                                      // target pixels (same grid)
+  const int halves = prm.halves;                        // 256 target columns (4 rows of 64) per TMEM half
+  const int Q = prm.Q;                                  // target pixels per map
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_hi);
-    if (PREC == 2) prefetch_tmap(&map_lo);
+    prefetch_tmap(&map_bhi);
+    if (PREC == 2) { prefetch_tmap(&map_lo); prefetch_tmap(&map_blo); }
     prefetch_tmap(&map_l0);
     if (prm.has_l1) prefetch_tmap(&map_l1);
     mbar_init(a_full, 1);
@@ -257,11 +261,11 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
           uint8_t* dst = sB + s * Cfg::kStageBytes;
           const int b_row = b_row0 + c * kChunkN;
           mbar_expect_tx(b_full + s, Cfg::kStageBytes);
-          tma_load_2d(dst, &map_hi, b_full + s, 0, b_row);
-          tma_load_2d(dst + kAtomBytes, &map_hi, b_full + s, 64, b_row);
+          tma_load_2d(dst, &map_bhi, b_full + s, 0, b_row);
+          tma_load_2d(dst + kAtomBytes, &map_bhi, b_full + s, 64, b_row);
           if (PREC == 2) {
-            tma_load_2d(dst + kPlaneBytes, &map_lo, b_full + s, 0, b_row);
-            tma_load_2d(dst + kPlaneBytes + kAtomBytes, &map_lo, b_full + s, 64, b_row);
+            tma_load_2d(dst + kPlaneBytes, &map_blo, b_full + s, 0, b_row);
+            tma_load_2d(dst + kPlaneBytes + kAtomBytes, &map_blo, b_full + s, 64, b_row);
           }
         }
       }
@@ -417,8 +421,8 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
           const int ya = 4 * h + 2 * rp, yb = ya + 1;
           const bool pa = gr > 0 && ((unsigned)ya - by) < rdg;
           const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
-          store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx);
-          store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx);
+          if (ya * 64 + x0 < Q) store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx);   // flat mode: Q may
+          if (yb * 64 + x0 < Q) store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx);   // end mid-half
           // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -537,8 +541,8 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes,
 }
 
 template <int PREC>
-static int launch_build(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& m0, const CUtensorMap& m1,
-                        const BpParams& prm, cudaStream_t st) {
+static int launch_build(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mbh, const CUtensorMap& mbl,
+                        const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st) {
   using Cfg = BpCfg<PREC>;
   auto kern = build_pyramid_kernel<PREC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -550,7 +554,7 @@ static int launch_build(const CUtensorMap& mh, const CUtensorMap& ml, const CUte
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = prm.num_units < sms ? prm.num_units : sms;
-  kern<<<grid, kBpThreads, Cfg::kSmemBytes, st>>>(mh, ml, m0, m1, prm);
+  kern<<<grid, kBpThreads, Cfg::kSmemBytes, st>>>(mh, ml, mbh, mbl, m0, m1, prm);
   return check_launch("lgu_build_pyramid");
 }
 
@@ -609,6 +613,48 @@ extern "C" int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, con
   prm.E = E; prm.P = P; prm.H = H; prm.gauss_radius = gauss_radius; prm.round_half = round_half;
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = lvl1 != nullptr;
-  if (precision == 1) return launch_build<1>(mh, ml, m0, m1, prm, (cudaStream_t)stream);
-  return launch_build<2>(mh, ml, m0, m1, prm, (cudaStream_t)stream);
+  prm.Q = P;
+  prm.halves = H / 4;
+  if (precision == 1) return launch_build<1>(mh, ml, mh, ml, m0, m1, prm, (cudaStream_t)stream);
+  return launch_build<2>(mh, ml, mh, ml, m0, m1, prm, (cudaStream_t)stream);
+}
+
+extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
+                                const void* fmaps2_lo, const int32_t* ii, const int32_t* jj, float* volume, int T1,
+                                int T2, int E, int P, int Q, int C, int precision, void* stream) {
+  using namespace lgu;
+  if (E == 0) return LGU_OK;
+  LGU_REQUIRE(fmaps1_hi && fmaps2_hi && ii && jj && volume, "lgu_build_volume: null pointer");
+  LGU_REQUIRE(precision == 1 || precision == 2, "lgu_build_volume: precision must be 1 or 2");
+  LGU_REQUIRE(precision == 1 || (fmaps1_lo && fmaps2_lo), "lgu_build_volume: precision 2 needs the lo planes");
+  LGU_REQUIRE(T1 > 0 && T2 > 0 && E > 0 && P > 0 && Q > 0, "lgu_build_volume: bad sizes");
+  if (!(C == 128 && (P % kTileM) == 0 && (Q % 4) == 0)) {
+    set_error("lgu_build_volume: needs C=128, P%%128==0, Q%%4==0 (got C=%d P=%d Q=%d)", C, P, Q);
+    return LGU_ERR_UNSUPPORTED;
+  }
+  LGU_REQUIRE((long long)E * P < 2147483647LL && (long long)T1 * P < 2147483647LL && (long long)T2 * Q < 2147483647LL,
+              "lgu_build_volume: too many rows");
+  CUtensorMap mh, ml, mbh, mbl, m0;
+  int rc = make_map_2d(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fmaps1_hi, (uint64_t)T1 * P, C, 128, 64);
+  if (rc) return rc;
+  rc = make_map_2d(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, precision == 2 ? fmaps1_lo : fmaps1_hi, (uint64_t)T1 * P, C,
+                   128, 64);
+  if (rc) return rc;
+  rc = make_map_2d(&mbh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fmaps2_hi, (uint64_t)T2 * Q, C, 128, 64);
+  if (rc) return rc;
+  rc = make_map_2d(&mbl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, precision == 2 ? fmaps2_lo : fmaps2_hi, (uint64_t)T2 * Q, C,
+                   128, 64);
+  if (rc) return rc;
+  rc = make_map_2d(&m0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, volume, (uint64_t)E * P, Q, 32, 32);
+  if (rc) return rc;
+  BpParams prm;
+  prm.ii = ii; prm.jj = jj; prm.means = nullptr; prm.covs = nullptr; prm.den = nullptr;
+  prm.lvl1 = nullptr; prm.lvl2 = nullptr; prm.lvl3 = nullptr;
+  prm.E = E; prm.P = P; prm.H = 0; prm.gauss_radius = 0; prm.round_half = 0;
+  prm.num_units = E * (P / kTileM);
+  prm.has_l1 = 0;
+  prm.Q = Q;
+  prm.halves = (Q + 255) / 256;
+  if (precision == 1) return launch_build<1>(mh, ml, mbh, mbl, m0, m0, prm, (cudaStream_t)stream);
+  return launch_build<2>(mh, ml, mbh, mbl, m0, m0, prm, (cudaStream_t)stream);
 }

@@ -64,12 +64,15 @@ struct Tap {
   bool gate, miss;
 };
 
-template <int BW, int BH>
+// PER_CORNER = false: the reference's volume lookups gate the whole tap on its top-left corner (quirk Q3);
+// PER_CORNER = true : lowMem_defSample / altcorr gate every corner on its own (quirk Q4) -- which is exactly what the
+//                     zero-filled TMA box gives, so the tap is always "on" and only the slow path needs the tests.
+template <int BW, int BH, bool PER_CORNER = false>
 __device__ __forceinline__ void tap_fetch(Tap& t, const float* __restrict__ box, int xb, int yb, int fx, int fy, int i,
                                           int j, int r, int H2, int W2) {
   t.x1 = tap_coord(fx, r, i);
   t.y1 = tap_coord(fy, r, j);
-  t.gate = ((unsigned)t.x1 < (unsigned)W2) && ((unsigned)t.y1 < (unsigned)H2);    // top-left gate (Q3)
+  t.gate = PER_CORNER ? true : (((unsigned)t.x1 < (unsigned)W2) && ((unsigned)t.y1 < (unsigned)H2));   // Q3 / Q4
   const unsigned rx = (unsigned)t.x1 - (unsigned)xb, ry = (unsigned)t.y1 - (unsigned)yb;
   const bool inbox = rx < (unsigned)(BW - 1) && ry < (unsigned)(BH - 1);
   t.miss = t.gate && !inbox;
@@ -77,14 +80,17 @@ __device__ __forceinline__ void tap_fetch(Tap& t, const float* __restrict__ box,
   t.q11 = b[0]; t.q21 = b[1]; t.q12 = b[BW]; t.q22 = b[BW + 1];
 }
 // Slow path for flagged lanes: same gating as the reference (x2 / y2 corners gated individually).
+template <bool PER_CORNER = false>
 __device__ __forceinline__ void tap_patch_from_global(Tap& t, const float* __restrict__ V, int H2, int W2) {
   if (t.miss) {
     const int x2 = wrap_inc(t.x1), y2 = wrap_inc(t.y1);
+    const bool x1i = (unsigned)t.x1 < (unsigned)W2, y1i = (unsigned)t.y1 < (unsigned)H2;
     const bool xo = (unsigned)x2 < (unsigned)W2, yo = (unsigned)y2 < (unsigned)H2;
-    const float* g = V + (size_t)t.y1 * W2 + t.x1;
-    t.q11 = __ldg(g);
-    t.q21 = xo ? __ldg(g + 1) : 0.0f;
-    t.q12 = yo ? __ldg(g + W2) : 0.0f;
+    // 64-bit element offset: with PER_CORNER the top-left corner itself may be out of bounds
+    const float* g = V + ((long long)t.y1 * W2 + t.x1);
+    t.q11 = (x1i && y1i) ? __ldg(g) : 0.0f;
+    t.q21 = (xo && y1i) ? __ldg(g + 1) : 0.0f;
+    t.q12 = (x1i && yo) ? __ldg(g + W2) : 0.0f;
     t.q22 = (xo && yo) ? __ldg(g + W2 + 1) : 0.0f;
   }
 }

@@ -35,8 +35,11 @@ struct FusedLookupParams {
   float* mask_out;       // [E,P] or null: the sigmoid(var) mask of this call
   int P, tiles_per_edge;
   int H2[4], W2[4];
+  long long off_edge_stride;   // float2 elements between the offset slabs of consecutive edges (0: every edge reads slab 0, Q2)
+  int apply_mask;              // 1: off1 <- off1 * sigmoid(var) of this call (CorrBlock); 0: offsets are used as given
 };
 
+template <bool PC>   // PC: per-corner gating (lowMem / altcorr semantics, Q4) instead of top-left gating (Q3)
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupParams prm) {
   using namespace fl;
@@ -99,9 +102,9 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 
   float2 a0, a1, b0, b1;                                        // level-0 / level-1 offsets of taps t0, t1
   auto load_offsets = [&](int k) {
-    const size_t pix = (size_t)n * P + min(pw + k, P - 1);
-    const float2* O0 = reinterpret_cast<const float2*>(prm.off0) + pix * TAPS;
-    const float2* O1 = reinterpret_cast<const float2*>(prm.off1) + pix * TAPS;
+    const size_t opix = (size_t)n * prm.off_edge_stride + (size_t)min(pw + k, P - 1) * TAPS;
+    const float2* O0 = reinterpret_cast<const float2*>(prm.off0) + opix;
+    const float2* O1 = reinterpret_cast<const float2*>(prm.off1) + opix;
     a0 = O0[t0]; a1 = O0[t1c]; b0 = O1[t0]; b1 = O1[t1c];
   };
   load_offsets(0);
@@ -114,18 +117,20 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     {
       const float px = __fadd_rn(oa.x, cx), py = __fadd_rn(oa.y, cy);        // defCorrSample_kernel.cu:56-61
       const int fx = floor_to_int(px), fy = floor_to_int(py);
-      ta.dx = __fsub_rn(px, (float)fx); ta.dy = __fsub_rn(py, (float)fy);
-      tap_fetch<kBW01, kBH01>(ta, bx, xb, yb, fx, fy, i0, j0, R, H2, W2);
+      ta.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);     // lowMem_defSample.cu:87-88 uses floor()
+      ta.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
+      tap_fetch<kBW01, kBH01, PC>(ta, bx, xb, yb, fx, fy, i0, j0, R, H2, W2);
     }
     {
       const float px = __fadd_rn(ob.x, cx), py = __fadd_rn(ob.y, cy);
       const int fx = floor_to_int(px), fy = floor_to_int(py);
-      tb.dx = __fsub_rn(px, (float)fx); tb.dy = __fsub_rn(py, (float)fy);
-      tap_fetch<kBW01, kBH01>(tb, bx, xb, yb, fx, fy, i1, j1, R, H2, W2);
+      tb.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);
+      tb.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
+      tap_fetch<kBW01, kBH01, PC>(tb, bx, xb, yb, fx, fy, i1, j1, R, H2, W2);
     }
     if (__any_sync(0xffffffffu, ta.miss || tb.miss)) {          // |offset| >= 4: rare
-      tap_patch_from_global(ta, V, H2, W2);
-      tap_patch_from_global(tb, V, H2, W2);
+      tap_patch_from_global<PC>(ta, V, H2, W2);
+      tap_patch_from_global<PC>(tb, V, H2, W2);
     }
     so[t0 * kOutPitch] = tap_value(ta);
     if (has1) so[t1 * kOutPitch] = tap_value(tb);
@@ -136,13 +141,13 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     const int fx = floor_to_int(px), fy = floor_to_int(py);
     const int xb = box_origin_x(fx, 3, W2), yb = box_origin_y(fy, 3, H2);
     Tap ta, tb;
-    ta.dx = tb.dx = __fsub_rn(px, (float)fx);
-    ta.dy = tb.dy = __fsub_rn(py, (float)fy);
-    tap_fetch<kBW23, kBH23>(ta, bx, xb, yb, fx, fy, i0, j0, R, H2, W2);
-    tap_fetch<kBW23, kBH23>(tb, bx, xb, yb, fx, fy, i1, j1, R, H2, W2);
+    ta.dx = tb.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);
+    ta.dy = tb.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
+    tap_fetch<kBW23, kBH23, PC>(ta, bx, xb, yb, fx, fy, i0, j0, R, H2, W2);
+    tap_fetch<kBW23, kBH23, PC>(tb, bx, xb, yb, fx, fy, i1, j1, R, H2, W2);
     if (__any_sync(0xffffffffu, ta.miss || tb.miss)) {          // only for clamped (far out-of-range) coords
-      tap_patch_from_global(ta, V, H2, W2);
-      tap_patch_from_global(tb, V, H2, W2);
+      tap_patch_from_global<PC>(ta, V, H2, W2);
+      tap_patch_from_global<PC>(tb, V, H2, W2);
     }
     so[t0 * kOutPitch] = tap_value(ta);
     if (has1) so[t1 * kOutPitch] = tap_value(tb);
@@ -174,8 +179,8 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
       Tap tm;
       tm.dx = __fsub_rn(x1c, floorf(x1c));
       tm.dy = __fsub_rn(y1c, floorf(y1c));
-      tap_fetch<kBW01, kBH01>(tm, box + kOff1, xb, yb, fx, fy, mi, mj, 1, H2, W2);
-      if (__any_sync(0xffffffffu, tm.miss)) tap_patch_from_global(tm, V1, H2, W2);
+      tap_fetch<kBW01, kBH01, PC>(tm, box + kOff1, xb, yb, fx, fy, mi, mj, 1, H2, W2);
+      if (__any_sync(0xffffffffu, tm.miss)) tap_patch_from_global<PC>(tm, V1, H2, W2);
       const float v = lane < 9 ? tap_value(tm) : 0.0f;
       // unbiased variance over the 9 taps (torch.var default, corr.py:96), then sigmoid (corr.py:97)
       float s = v;
@@ -190,8 +195,10 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
       m = 1.0f / (1.0f + expf(-var));
     }
     // offset[1] <- offset[1] * mask (Q7) for every tap; the lookup itself reads the centre tap as 0 (Q5)
-    o10 = make_float2(__fmul_rn(o10.x, m), __fmul_rn(o10.y, m));
-    o11 = make_float2(__fmul_rn(o11.x, m), __fmul_rn(o11.y, m));
+    if (prm.apply_mask) {
+      o10 = make_float2(__fmul_rn(o10.x, m), __fmul_rn(o10.y, m));
+      o11 = make_float2(__fmul_rn(o11.x, m), __fmul_rn(o11.y, m));
+    }
     const float2 o10_store = o10;
     if (lane == CENTER) o10 = make_float2(0.0f, 0.0f);
 
@@ -206,9 +213,11 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 
     // ---------------- in-place side effects on the caller's offsets
     if (live) {
-      float2* O1 = reinterpret_cast<float2*>(prm.off1) + pix * TAPS;
-      O1[t0] = o10_store;
-      if (has1) O1[t1] = o11;
+      if (prm.apply_mask) {
+        float2* O1 = reinterpret_cast<float2*>(prm.off1) + (size_t)n * prm.off_edge_stride + (size_t)min(p, P - 1) * TAPS;
+        O1[t0] = o10_store;
+        if (has1) O1[t1] = o11;
+      }
       if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[pix] = m;
     }
     __syncwarp();                                               // every lane is done with this slot
@@ -229,9 +238,29 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 
 }  // namespace lgu
 
+namespace lgu {
+static int launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                               const float* coords, const float* off0, float* off1, float* corr, float* mask_out, int E,
+                               int H, int W, int num_levels, int radius, int per_corner, int shared_offsets,
+                               int apply_mask, void* stream);
+}
 extern "C" int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                      const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                      int E, int H, int W, int num_levels, int radius, void* stream) {
+  return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, corr, mask_out, E, H, W, num_levels,
+                                  radius, 0, 0, 1, stream);
+}
+extern "C" int lgu_altcorr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                        const float* coords, const float* off0, float* off1, float* corr,
+                                        float* mask_out, int E, int H, int W, int num_levels, int radius,
+                                        int shared_offsets, int apply_mask, void* stream) {
+  return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, corr, mask_out, E, H, W, num_levels,
+                                  radius, 1, shared_offsets, apply_mask, stream);
+}
+static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                    const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
+                                    int E, int H, int W, int num_levels, int radius, int per_corner,
+                                    int shared_offsets, int apply_mask, void* stream) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && off0 && off1 && corr, "lgu_corr_lookup_fused: null pointer");
@@ -262,11 +291,15 @@ extern "C" int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const
   prm.tiles_per_edge = (P + fl::kTile - 1) / fl::kTile;
   const long long nblk = (long long)E * prm.tiles_per_edge;
   LGU_REQUIRE(nblk < 2147483647LL, "lgu_corr_lookup_fused: grid too large (%lld CTAs)", nblk);
-  cudaError_t e = cudaFuncSetAttribute(lookup_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::kSmemBytes);
+  prm.off_edge_stride = shared_offsets ? 0 : (long long)P * fl::TAPS;
+  prm.apply_mask = apply_mask;
+  LGU_REQUIRE(!(shared_offsets && apply_mask), "lgu_*_lookup_fused: apply_mask needs per-edge offsets");
+  auto kern = per_corner ? lookup_fused_kernel<true> : lookup_fused_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("lgu_corr_lookup_fused: cannot opt in to %d B of shared memory: %s", fl::kSmemBytes, cudaGetErrorString(e));
     return LGU_ERR_LAUNCH;
   }
-  lookup_fused_kernel<<<(unsigned)nblk, fl::kThreads, fl::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
+  kern<<<(unsigned)nblk, fl::kThreads, fl::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
   return check_launch("lgu_corr_lookup_fused");
 }

@@ -300,3 +300,59 @@ def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad,
             _stream(coords))
     _lib.check(st, "corr_lookup_fused_backward")
     return gv[0], gv[1], gv[2], gv[3], g0, g1
+
+
+def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj):
+    """volume[e,p,q] = sum_c f1[ii[e],p,c] * f2[jj[e],q,c] on tcgen05 (fp32 accumulate).  f1_* [T1,P,C],
+    f2_* [T2,Q,C] contiguous CUDA fp16 planes (lo planes None for single-product precision); ii, jj int32 [E].
+    Returns [E,P,Q] fp32.  The backend path's per-level volume (source level 0 x pooled target level l)."""
+    for t, name in ((f1_hi, "f1_hi"), (f2_hi, "f2_hi")):
+        if not (t.is_cuda and t.dtype == torch.float16 and t.dim() == 3 and t.is_contiguous()):
+            raise RuntimeError(f"{name} must be a contiguous CUDA fp16 tensor [T,P,C]")
+    split = f1_lo is not None
+    if split and (f2_lo is None or f1_lo.shape != f1_hi.shape or f2_lo.shape != f2_hi.shape):
+        raise RuntimeError("precision 2 needs lo planes for both map sets")
+    T1, P, C = f1_hi.shape
+    T2, Q, C2 = f2_hi.shape
+    if C2 != C:
+        raise RuntimeError("channel mismatch")
+    for t, name in ((ii, "ii"), (jj, "jj")):
+        if not (t.is_cuda and t.dtype == torch.int32 and t.dim() == 1 and t.is_contiguous()):
+            raise RuntimeError(f"{name} must be a contiguous CUDA int32 vector")
+    E = ii.numel()
+    vol = torch.empty(E, P, Q, dtype=torch.float32, device=f1_hi.device)
+    null = ctypes.c_void_p(0)
+    with torch.cuda.device(f1_hi.device):
+        st = _lib.lib().lgu_build_volume(_p(f1_hi), _p(f1_lo) if split else null, _p(f2_hi), _p(f2_lo) if split else null,
+                                         _p(ii), _p(jj), _p(vol), _i(T1), _i(T2), _i(E), _i(P), _i(Q), _i(C),
+                                         _i(2 if split else 1), _stream(f1_hi))
+    _lib.check(st, "build_volume")
+    return vol
+
+
+def altcorr_lookup_fused(volumes, coords, off0, off1, radius=3, shared_offsets=False, apply_mask=True,
+                         return_mask=False):
+    """corr_lookup_fused with the backend samplers' semantics (per-corner gating, quirk Q4; lowMem_defSample.cu /
+    altcorr_kernel.cu).  volumes: 4 tensors [E,H,W,H>>l,W>>l] from build_volume.  shared_offsets: every edge reads
+    offset slab 0 (quirk Q2; off0/off1 then hold >= 1 slab); apply_mask=False: off1 is used as given."""
+    E, H, W = volumes[0].shape[:3]
+    for l, t in enumerate(volumes):
+        _chk(t, f"volumes[{l}]", 5)
+        if tuple(t.shape) != (E, H, W, H >> l, W >> l):
+            raise RuntimeError(f"volumes[{l}] shape {tuple(t.shape)} != {(E, H, W, H >> l, W >> l)}")
+    _chk(coords, "coords", 4)
+    need = H * W * 98 * (1 if shared_offsets else E)
+    for name, o in (("off0", off0), ("off1", off1)):
+        if not (isinstance(o, torch.Tensor) and o.is_cuda and o.is_contiguous() and o.dtype == torch.float32
+                and o.numel() >= need):
+            raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor with >= {need} elements")
+    corr = torch.empty(E, 196, H, W, dtype=torch.float32, device=coords.device)
+    mask = torch.empty(E, H, W, dtype=torch.float32, device=coords.device) if return_mask else None
+    with torch.cuda.device(coords.device):
+        st = _lib.lib().lgu_altcorr_lookup_fused(_p(volumes[0]), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]),
+                                                 _p(coords), _p(off0), _p(off1), _p(corr),
+                                                 _p(mask) if return_mask else ctypes.c_void_p(0), _i(E), _i(H), _i(W),
+                                                 _i(4), _i(radius), _i(1 if shared_offsets else 0),
+                                                 _i(1 if apply_mask else 0), _stream(coords))
+    _lib.check(st, "altcorr_lookup_fused")
+    return (corr, mask) if return_mask else corr

@@ -111,7 +111,7 @@ def test_altcorrblock_interface_and_shapes(oracle):
     jj = torch.tensor([1, 2, 3, 4], device=dev)
     coords = inputs.make_coords(4, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, 4, 48, 64, 2).to(dev)
     with torch.no_grad():
-        blk = corr.AltCorrBlock(ofsMap, ofs_residual, GA, fmaps)
+        blk = corr.AltCorrBlock(ofsMap, ofs_residual, GA, fmaps, materialize=False)
         out = blk(coords, ii, jj)
         assert out.shape == (1, 4, 196, 48, 64) and torch.isfinite(out).all()
         # zero-offset levels (2, 3) equal the oracle's lowMem sampler on the same pooled maps
@@ -127,3 +127,53 @@ def test_altcorrblock_interface_and_shapes(oracle):
             want, = oracle.lowMem_defSample(f1, f2, c, torch.zeros(4, 48, 64, 7, 7, 2), 3)
             got = out[0, :, 49 * l:49 * (l + 1)].cpu()
             assert (got - want.view(4, 49, 48, 64)).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("strict_ref", [True, False])
+@pytest.mark.parametrize("half", [True, False])
+def test_altcorrblock_materialized_matches_lowmem_operators(strict_ref, half):
+    """The B200 backend path (per-level volumes on tcgen05 + fused per-corner-gated lookup) against the reference's
+    op sequence on the drop-in operators (altcorr_forward + 4 x lowMem_defSample, themselves parity-tested against
+    the oracle and the compiled reference).  Tolerance: 1e-4 abs on values of magnitude ~10 (dot-then-interpolate vs
+    interpolate-then-dot in fp32; the fp16 buffer's products are exact in the tensor core)."""
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 4)
+    g = inputs.gen(11)
+    T, E = 6, 7
+    fmaps = torch.randn(1, T, 128, 48, 64, generator=g)
+    fmaps = (fmaps.half() if half else fmaps).to(dev)
+    ii = torch.tensor([0, 1, 2, 3, 4, 5, 2], device=dev)
+    jj = torch.tensor([1, 2, 3, 4, 5, 4, 0], device=dev)
+    coords = inputs.make_coords(E, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, E, 48, 64, 2).to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            a = corr.AltCorrBlock(ofsMap, ofs_residual, GA, fmaps, strict_ref=strict_ref, materialize=True)
+            b = corr.AltCorrBlock(ofsMap, ofs_residual, GA, fmaps, strict_ref=strict_ref, materialize=False)
+            assert a.materialize and not b.materialize
+            out_a = a(coords, ii, jj)
+            out_b = b(coords, ii, jj)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert out_a.shape == out_b.shape == (1, E, 196, 48, 64)
+    assert torch.equal(out_a == 0, out_b == 0) or ((out_a == 0) ^ (out_b == 0)).float().mean().item() < 1e-4
+    err = (out_a - out_b).abs().max().item()
+    assert err <= 1e-4 * max(1.0, out_b.abs().max().item() / 10), f"max abs err {err} (max |v| {out_b.abs().max().item()})"
+    d = (a.offset[1] - b.offset[1]).reshape(E, 48, 64, 49, 2)
+    d[..., 24, :] = 0          # the centre tap: zeroed in memory only by the drop-in operator's in-place quirk (Q5)
+    assert d.abs().max().item() <= 1e-5
+
+
+def test_build_volume_matches_matmul(ops):
+    dev = "cuda"
+    g = inputs.gen(12)
+    f1 = (torch.randn(3, 3072, 128, generator=g) / 4).half().to(dev)
+    for Q in (3072, 768, 192, 48):
+        f2 = (torch.randn(4, Q, 128, generator=g) / 4).half().to(dev)
+        ii = torch.tensor([0, 2, 1, 1], dtype=torch.int32, device=dev)
+        jj = torch.tensor([3, 0, 1, 2], dtype=torch.int32, device=dev)
+        got = ops.build_volume(f1, None, f2, None, ii, jj)
+        want = torch.matmul(f1[ii.long()].double(), f2[jj.long()].double().transpose(1, 2))
+        assert got.shape == (4, 3072, Q)
+        assert (got.double() - want).abs().max().item() <= 1e-5, f"Q={Q}"

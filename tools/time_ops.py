@@ -72,5 +72,43 @@ def main():
         cl_ = (co / 2).contiguous()
         rep("altcorr_forward r1 l1", timeit(lambda: ops.altcorr_forward(f1, f2s[1], cl_, 1), iters=5), B * (4 * P * 128 + 4 * 768 * 128 + P * (8 + 36)))
 
+def backend():
+    """Backend chunk (AltCorrBlock.__call__): materialised tcgen05 path vs the lowMem operator sequence."""
+    import torch.nn as nn
+    from importlib import import_module
+    corr = import_module("lgu-slam_b200.corr")
+    dev = "cuda"
+    torch.manual_seed(0)
+    ofsMap = nn.Conv2d(256, 98, 3, padding=1).to(dev); ofs_res = nn.Conv2d(256, 98, 3, padding=1).to(dev)
+    GA = corr.GaussianMask(48, 64).to(dev)
+    T, E = 64, 48
+    g = inputs.gen(3)
+    fmaps = torch.randn(1, T, 128, 48, 64, generator=g).half().to(dev)
+    ii, jj = inputs.edge_list(T, E, g)
+    ii, jj = ii.long().to(dev), jj.long().to(dev)
+    coords = inputs.make_coords(E, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, E, 48, 64, 2).to(dev)
+    with torch.no_grad():
+        for mat in (True, False):
+            for strict in (True, False):
+                blk = corr.AltCorrBlock(ofsMap, ofs_res, GA, fmaps, strict_ref=strict, materialize=mat)
+                us = timeit(lambda: blk(coords, ii, jj), iters=5, warm=2)
+                print(f"AltCorrBlock.__call__ E={E} materialize={mat} strict_ref={strict}: median {us[0]:9.1f} us "
+                      f"-> {E / us[0] * 1e6:9.0f} edges/s (incl. offset convs)")
+        blk = corr.AltCorrBlock(ofsMap, ofs_res, GA, fmaps, strict_ref=False, materialize=True)
+        planes = blk._level_planes()
+        ii32, jj32 = ii.int(), jj.int()
+        for l in range(4):
+            us = timeit(lambda: ops.build_volume(planes[0][0], None, planes[l][0], None, ii32, jj32))
+            Q = (48 >> l) * (64 >> l)
+            rep(f"build_volume l{l}", us, E * (3072 * Q * 4 + 3072 * 256 + Q * 256))
+
+
+def rep(name, us, bytes_):
+    print(f"{name:28s} median {us[0]:8.1f} us  min {us[1]:8.1f} us   alg {bytes_/1e6:8.1f} MB  -> {bytes_ / us[0] / 1e3:7.1f} GB/s ({bytes_ / us[0] / 1e3 / 6552 * 100:4.1f}% of 6552)")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "backend":
+        backend()
+        sys.exit(0)
     main()
