@@ -157,7 +157,11 @@ struct BpCfg {
   static constexpr int kABytes = kPlanes * kPlaneBytes;
   static constexpr int kStageBytes = kPlanes * kPlaneBytes;
   static constexpr int kStoreBytes = kEpiWarps * kStoreBufs * 4096;
-  static constexpr int kBarOffset = kABytes + kStages * kStageBytes + kStoreBytes;
+  // level-1 rows: the two warps of a TMEM lane quadrant fill the halves of ONE 32-row x 128-byte tile (the TMA
+  // store engine is bound by row slots -- measured: a 64-byte-row tile costs as much as a 128-byte-row tile)
+  static constexpr bool kPairL1 = PREC == 1;
+  static constexpr int kL1Bytes = kPairL1 ? 4 * 2 * 4096 : 0;
+  static constexpr int kBarOffset = kABytes + kStages * kStageBytes + kStoreBytes + kL1Bytes;
   static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + 1 KB alignment slack
 };
 
@@ -198,6 +202,7 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
   uint8_t* sA = smem;                                   // [plane][atom][128 rows][128 B]
   uint8_t* sB = smem + Cfg::kABytes;                    // [stage][plane][atom][128 rows][128 B]
   uint8_t* sStore = sB + Cfg::kStages * Cfg::kStageBytes;   // [warp][buf][32 rows][128 B]
+  uint8_t* sL1 = sStore + Cfg::kStoreBytes;             // [quad][2][32 rows][128 B] (PREC 1 only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
@@ -315,7 +320,9 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     const int xs = (warp - 2) >> 2;                     // which 32-column half of the 64 target columns
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     uint8_t* my_store = sStore + (warp - 2) * Cfg::kStoreBufs * 4096;
-    int sbuf = 0;
+    uint8_t* pair_l1 = sL1 + quad * 2 * 4096;
+    int sbuf = 0, l1buf = 0;
+    const bool l1_issuer = Cfg::kPairL1 && xs == 0 && prm.has_l1;   // this warp's bulk groups also carry the L1 tiles
     const int gr = prm.gauss_radius;
     const unsigned rdg = 2u * (unsigned)gr + 1u;
     const int rsw = lane & 7;                           // 128B swizzle phase of this thread's staging row
@@ -325,7 +332,12 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     // stage one 32-float row segment per lane and hand the 32x32 tile to the TMA store engine
     auto store_tile = [&](float (&v)[32], int col, int row0, bool patch, int yy, float mx, float my, float c1, float c2,
                           float den, unsigned bx) {
-      if (lane == 0) tma_wait_read<Cfg::kStoreBufs - 1>();
+      if (lane == 0) {
+        // the tile staged in this buffer two level-0 stores ago must have been read; the issuer warp has one
+        // level-1 group between them, so it may leave one more group pending
+        if (l1_issuer) tma_wait_read<Cfg::kStoreBufs>();
+        else tma_wait_read<Cfg::kStoreBufs - 1>();
+      }
       __syncwarp();
       float4* rowp = reinterpret_cast<float4*>(my_store + sbuf * 4096 + lane * 128);
 #pragma unroll
@@ -433,6 +445,21 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 __stcs(o1 + c, make_float4(l1[rp][4 * c], l1[rp][4 * c + 1], l1[rp][4 * c + 2], l1[rp][4 * c + 3]));
+            } else if (Cfg::kPairL1) {
+              // named barrier of the quadrant's two warps (ids 1..4).  A: the issuer's waits before its two level-0
+              // stores of this row pair guarantee that the tile stored from this buffer two rows ago has been read.
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+              float4* rowp = reinterpret_cast<float4*>(pair_l1 + l1buf * 4096 + lane * 128);
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                rowp[(xs * 4 + c) ^ rsw] = make_float4(l1[rp][4 * c], l1[rp][4 * c + 1], l1[rp][4 * c + 2], l1[rp][4 * c + 3]);
+              fence_proxy_async();
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");      // B: both halves are in the tile
+              if (xs == 0 && lane == 0) {
+                tma_store_2d(&map_l1, pair_l1 + l1buf * 4096, (2 * h + rp) * 32, row0);
+                tma_commit();
+              }
+              l1buf ^= 1;
             } else {
               store_l1(l1[rp], (2 * h + rp) * 32 + xs * 16, row0);
             }
@@ -603,8 +630,9 @@ extern "C" int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, con
   if (rc) return rc;
   rc = make_map_2d(&m0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, (uint64_t)E * P, P, 32, 32);
   if (rc) return rc;
+  // level-1 store tiles: 32 rows x 128 B shared by a warp pair (precision 1), 32 rows x 64 B per warp (precision 2)
   rc = make_map_2d(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl1 ? lvl1 : lvl0, (uint64_t)E * P, lvl1 ? P / 4 : P, 32,
-                   16, CU_TENSOR_MAP_SWIZZLE_64B);
+                   precision == 1 ? 32 : 16, precision == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
 
   BpParams prm;

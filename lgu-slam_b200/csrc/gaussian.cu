@@ -87,25 +87,52 @@ gaussian_bwd_kernel(const float* __restrict__ means, const float* __restrict__ c
     const float* V = volume + (size_t)pix * Q;
     const float* G = out_grad + (size_t)pix * Q;
     float gm0 = 0.0f, gm1 = 0.0f, gc0 = 0.0f, gc1 = 0.0f;
-    // lanes sweep the window row-major in memory (y outer, x inner) so a warp instruction
-    // touches ~3.5 consecutive 36-byte row segments.
-    for (int t = lane; t < taps; t += 32) {
-      const int j = t / rd, i = t - j * rd;          // j: y tap, i: x tap
+    // lanes sweep the window row-major in memory (y outer, x inner) so a warp instruction touches ~3.5 consecutive
+    // 36-byte row segments.  All passes' loads are issued before any is consumed (the kernel was stalling once per
+    // pass on the volume / gradient gathers); radius <= 4 -> at most 3 passes, larger windows take the tail loop.
+    constexpr int kHoist = 3;
+    float v3s[kHoist], gs[kHoist];
+    int xs_[kHoist], ys_[kHoist];
+    bool ok[kHoist];
+#pragma unroll
+    for (int ps = 0; ps < kHoist; ++ps) {
+      const int t = ps * 32 + lane;
+      const int tt = t < taps ? t : 0;
+      const int j = tt / rd, i = tt - j * rd;          // j: y tap, i: x tap
+      xs_[ps] = tap_coord(cx, r, i);
+      ys_[ps] = tap_coord(cy, r, j);
+      ok[ps] = t < taps && in_bounds(ys_[ps], xs_[ps], H2, W2);
+      const int q = ok[ps] ? ys_[ps] * W2 + xs_[ps] : 0;
+      v3s[ps] = __ldg(V + q);
+      gs[ps] = __ldg(G + q);
+    }
+    // per-pixel reciprocals (the reference divides per tap; multiplying by the correctly rounded reciprocal differs
+    // by <= 1 ulp per factor, far inside the 1e-5 gradient tolerance, and removes 4 fp32 + 2 fp64 divisions per tap)
+    const float rcx = __fdiv_rn(1.0f, c.x), rcy = __fdiv_rn(1.0f, c.y);
+    const double rccx = 1.0 / (double)__fmul_rn(c.x, c.x), rccy = 1.0 / (double)__fmul_rn(c.y, c.y);
+    auto accumulate = [&](int x1, int y1, float vraw, float g) {
+      const float ddx = __fsub_rn((float)x1, m.x), ddy = __fsub_rn((float)y1, m.y);
+      const float t1 = __fmul_rn(ddx, rcx), t2 = __fmul_rn(ddy, rcy);
+      const float s = __fmaf_rn(ddy, t2, __fmul_rn(t1, ddx));
+      const float e = expf(__fmul_rn(s, -0.5f));
+      const float v3 = __fmul_rn(vraw, 3.0f);
+      gm0 = __fmaf_rn(__fmul_rn(v3, __fmul_rn(__fmul_rn(ddx, e), rcx)), g, gm0);   // gaussianAttn.cu:117
+      gm1 = __fmaf_rn(__fmul_rn(v3, __fmul_rn(__fmul_rn(ddy, e), rcy)), g, gm1);   // :118
+      const double eh = (double)e * 0.5;                                           // :120,122 (fp64)
+      const float dE1 = (float)(((eh * (double)ddx) * (double)ddx) * rccx);
+      const float dE2 = (float)(((eh * (double)ddy) * (double)ddy) * rccy);
+      gc0 = __fmaf_rn(__fmul_rn(dE1, v3), g, gc0);                                 // :125
+      gc1 = __fmaf_rn(__fmul_rn(dE2, v3), g, gc1);                                 // :126
+    };
+#pragma unroll
+    for (int ps = 0; ps < kHoist; ++ps)
+      if (ok[ps]) accumulate(xs_[ps], ys_[ps], v3s[ps], gs[ps]);
+    for (int t = kHoist * 32 + lane; t < taps; t += 32) {
+      const int j = t / rd, i = t - j * rd;
       const int x1 = tap_coord(cx, r, i), y1 = tap_coord(cy, r, j);
       if (in_bounds(y1, x1, H2, W2)) {
-        const float ddx = __fsub_rn((float)x1, m.x), ddy = __fsub_rn((float)y1, m.y);
-        const float t1 = __fdiv_rn(ddx, c.x), t2 = __fdiv_rn(ddy, c.y);
-        const float s = __fmaf_rn(ddy, t2, __fmul_rn(t1, ddx));
-        const float e = expf(__fmul_rn(s, -0.5f));
         const int q = y1 * W2 + x1;
-        const float v3 = __fmul_rn(__ldg(V + q), 3.0f), g = __ldg(G + q);
-        gm0 = __fmaf_rn(__fmul_rn(v3, __fdiv_rn(__fmul_rn(ddx, e), c.x)), g, gm0);   // gaussianAttn.cu:117
-        gm1 = __fmaf_rn(__fmul_rn(v3, __fdiv_rn(__fmul_rn(ddy, e), c.y)), g, gm1);   // :118
-        const double eh = (double)e * 0.5;                                           // :120,122 (fp64)
-        const float dE1 = (float)(((eh * (double)ddx) * (double)ddx) / (double)__fmul_rn(c.x, c.x));
-        const float dE2 = (float)(((eh * (double)ddy) * (double)ddy) / (double)__fmul_rn(c.y, c.y));
-        gc0 = __fmaf_rn(__fmul_rn(dE1, v3), g, gc0);                                 // :125
-        gc1 = __fmaf_rn(__fmul_rn(dE2, v3), g, gc1);                                 // :126
+        accumulate(x1, y1, __ldg(V + q), __ldg(G + q));
       }
     }
     gm0 = warp_sum(gm0); gm1 = warp_sum(gm1); gc0 = warp_sum(gc0); gc1 = warp_sum(gc1);

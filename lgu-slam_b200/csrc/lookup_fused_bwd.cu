@@ -118,21 +118,45 @@ __device__ __forceinline__ float2 offset_grad(float q11, float q21, float q12, f
 }
 
 // Stream one level's dense gradient slice: zeros outside the accumulator box, the accumulator (then re-zeroed) inside.
+// Fast path (W2/4 divides 32, i.e. W2 in {8,16,32,64,128}): a lane owns one float4 column of the slice and walks
+// rows with a fixed stride, so the column test and the accumulator column are loop invariants -- no divisions.
+// (The first version divided by W2/4 per float4: ncu showed 2700 instructions per pixel, 40 % of them here.)
 template <int BW, int BH>
 __device__ __forceinline__ void write_slice(float* __restrict__ G, float* acc, int xb, int yb, int H2, int W2, int lane) {
-  const int W4 = W2 >> 2, n4 = H2 * W4;
+  const int W4 = W2 >> 2;
   float4* G4 = reinterpret_cast<float4*>(G);
   const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  for (int q4 = lane; q4 < n4; q4 += 32) {
-    const int y = q4 / W4, x = (q4 - y * W4) << 2;
-    const unsigned ry = (unsigned)(y - yb), rx = (unsigned)(x - xb);
-    float4 v = z;
-    if (ry < (unsigned)BH && rx < (unsigned)BW) {              // xb % 4 == 0: the float4 lies entirely inside
-      float4* a = reinterpret_cast<float4*>(acc + ry * BW + rx);
-      v = *a;
-      *a = z;
+  if (W4 <= 32 && (32 % W4) == 0) {
+    const int rpi = 32 / W4;                                   // rows per warp iteration
+    const int ly = lane / W4, lx = lane - ly * W4;             // W4 is a power of two here: shifts
+    const unsigned rx = (unsigned)((lx << 2) - xb);
+    const bool col_in = rx < (unsigned)BW;                     // xb % 4 == 0: the float4 lies entirely inside
+    float* acol = acc + rx;
+    float4* g = G4 + ly * W4 + lx;
+    const int gstep = rpi * W4;                                // == 32
+    for (int y = ly; y < H2; y += rpi, g += gstep) {
+      const unsigned ry = (unsigned)(y - yb);
+      float4 v = z;
+      if (col_in && ry < (unsigned)BH) {
+        float4* a = reinterpret_cast<float4*>(acol + ry * BW);
+        v = *a;
+        *a = z;
+      }
+      __stcs(g, v);
     }
-    __stcs(G4 + q4, v);
+  } else {
+    const int n4 = H2 * W4;
+    for (int q4 = lane; q4 < n4; q4 += 32) {
+      const int y = q4 / W4, x = (q4 - y * W4) << 2;
+      const unsigned ry = (unsigned)(y - yb), rx = (unsigned)(x - xb);
+      float4 v = z;
+      if (ry < (unsigned)BH && rx < (unsigned)BW) {
+        float4* a = reinterpret_cast<float4*>(acc + ry * BW + rx);
+        v = *a;
+        *a = z;
+      }
+      __stcs(G4 + q4, v);
+    }
   }
 }
 

@@ -55,6 +55,15 @@ def main():
                 pyr = [torch.randn(E, H, W, H >> l, W >> l, device=dev, generator=g) for l in range(4)]
                 fz = (pyr, fc["coords"].to(dev), fc["offsets"][0].to(dev), fc["offsets"][1].to(dev))
             ops.corr_lookup_fused(fz[0], fz[1], fz[2], fz[3].clone(), 3)
+        elif a.op == "fusedbwd":
+            if "fzb" not in globals():
+                global fzb
+                fc = inputs.frontend_case(E=E, T=20, seed=5, half_fmaps=True)
+                pyr = [torch.randn(E, H, W, H >> l, W >> l, device=dev, generator=g) for l in range(4)]
+                o1 = fc["offsets"][1].to(dev)
+                corr_, mask_ = ops.corr_lookup_fused(pyr, fc["coords"].to(dev), fc["offsets"][0].to(dev), o1, 3, return_mask=True)
+                fzb = (pyr, fc["coords"].to(dev), fc["offsets"][0].to(dev), o1, mask_, torch.randn(E, 196, H, W, device=dev, generator=g))
+            ops.corr_lookup_fused_backward(fzb[0], fzb[1], fzb[2], fzb[3], fzb[4], fzb[5])
         elif a.op == "fwd1":
             ops.corr_index_forward(vol, coords, 1)
         else:

@@ -36,9 +36,13 @@ def main():
     def rep(name, us, bytes_):
         print(f"{name:28s} median {us[0]:8.1f} us  min {us[1]:8.1f} us   alg {bytes_/1e6:8.1f} MB  -> {GB(bytes_, us[0]):7.1f} GB/s ({GB(bytes_, us[0])/6552*100:4.1f}% of 6552)")
     w = set(a.which)
-    def on(k): return not w or k in w
+    def on(k): return (not w and k != 'buildx') or k in w
     if on("build"):
         rep("build_pyramid", timeit(lambda: ops.build_pyramid(hi, None, ii, jj, H, W, means=means, covs=covs, den=den)), E * 51.757e6)
+    if on("buildx"):
+        for lv in (1, 2, 3, 4):
+            for gr in (0, 4):
+                rep(f"build levels={lv} gauss={gr}", timeit(lambda: ops.build_pyramid(hi, None, ii, jj, H, W, means=means, covs=covs, den=den, num_levels=lv, gauss_radius=gr)), E * (2 * P * 128 * 2 + 4 * P * sum(P >> (2 * l) for l in range(lv))))
     if on("fused"):
         o1 = off1.clone()
         rep("corr_lookup_fused", timeit(lambda: ops.corr_lookup_fused(pyr, coords, off0, o1, 3)), E * P * 3656)
