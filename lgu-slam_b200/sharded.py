@@ -127,9 +127,58 @@ class ShardedBackendCorr:
             outs.append(self.compute(coords[:, v], ii[v], jj[v]))
         return torch.cat(outs, dim=1) if outs else None
 
+    def lookup_streamed_to(self, coords, ii, jj, dst=0):
+        """gather="dst" with the transfer hidden behind the compute: every chunk's outputs leave for rank `dst` as
+        soon as the chunk is done (point-to-point isend over NVLink / NVSwitch, asynchronous to the next chunk's
+        kernels); `dst` posts all receives up front, computes its own chunks into place and scatters the received
+        chunks into the original edge order.  Returns [1,E_visited,CH,H,W] on `dst`, None elsewhere."""
+        assert self.plan is not None, "call set_edges(ii, jj) first"
+        plan, dev = self.plan, coords.device
+        mine = plan.rank_chunks[self.rank]
+        outs = {}
+        first = None
+        if mine:                                                   # the first chunk also tells the output shape
+            v = plan.chunk_edges[mine[0]].to(dev)
+            first = self.compute(coords[:, v], ii[v], jj[v])
+            outs[mine[0]] = first
+        shape = self._out_shape(first, coords)
+        if self.rank != dst:
+            reqs = []
+            for k, c in enumerate(mine):
+                if k > 0:
+                    v = plan.chunk_edges[c].to(dev)
+                    outs[c] = self.compute(coords[:, v], ii[v], jj[v])
+                outs[c] = outs[c][0].contiguous()
+                reqs.append(dist.isend(outs[c], dst=dst, group=self.group))
+            for r in reqs:
+                r.wait()
+            return None
+        full = torch.empty((1, plan.num_edges) + shape, dtype=torch.float32, device=dev)
+        visited = torch.cat(plan.chunk_edges) if plan.chunk_edges else torch.zeros(0, dtype=torch.int64)
+        # position of every visited edge in the compact output (edges the reference loop never visits have none)
+        remap = torch.full((int(visited.max()) + 1 if visited.numel() else 0,), -1, dtype=torch.int64)
+        remap[torch.sort(visited).values] = torch.arange(visited.numel())
+        recv = []
+        for r in range(self.world):
+            if r == dst:
+                continue
+            for c in plan.rank_chunks[r]:                          # same order as the sender's isend sequence
+                buf = torch.empty((plan.chunk_edges[c].numel(),) + shape, dtype=torch.float32, device=dev)
+                recv.append((c, buf, dist.irecv(buf, src=r, group=self.group)))
+        for k, c in enumerate(mine):
+            v = plan.chunk_edges[c]
+            if k > 0:
+                vd = v.to(dev)
+                outs[c] = self.compute(coords[:, vd], ii[vd], jj[vd])
+            full[:, remap[v].to(dev)] = outs[c]
+        for c, buf, req in recv:
+            req.wait()
+            full[:, remap[plan.chunk_edges[c]].to(dev)] = buf[None]
+        return full
+
     def __call__(self, coords, ii, jj, gather="all", dst=0):
         """gather=None: (local outputs, their edge positions).  gather="all": full [1,E,CH,H,W] in the original edge
-        order on every rank.  gather="dst": the same on rank `dst`, None elsewhere."""
+        order on every rank.  gather="dst": the same on rank `dst`, None elsewhere (see also lookup_streamed_to)."""
         local = self.local_lookup(coords, ii, jj)
         mine = self.plan.rank_edges[self.rank]
         if gather is None:

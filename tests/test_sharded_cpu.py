@@ -115,7 +115,7 @@ def _worker(rank, world, port, gather, q):
         assert torch.equal(full, fmaps)
         eng = sh.ShardedBackendCorr(_oracle_compute(_levels(full)))
         plan = eng.set_edges(ii, jj)
-        out = eng(coords, ii, jj, gather=gather)
+        out = eng.lookup_streamed_to(coords, ii, jj, dst=0) if gather == "stream" else eng(coords, ii, jj, gather=gather)
         if gather is None:
             local, pos = out
             q.put((rank, "local", local, pos))
@@ -128,7 +128,7 @@ def _worker(rank, world, port, gather, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("gather", ["all", "dst", None])
+@pytest.mark.parametrize("gather", ["all", "dst", "stream", None])
 def test_world_size_2_gloo_equals_single_process(gather):
     fmaps, ii, jj, coords = _case()
     sh = _sharded()
@@ -155,7 +155,7 @@ def test_world_size_2_gloo_equals_single_process(gather):
     if gather == "all":
         for _, kind, out, _ in got:
             assert kind == "full" and torch.equal(out, full)
-    elif gather == "dst":
+    elif gather in ("dst", "stream"):
         assert got[0][1] == "full" and torch.equal(got[0][2], full) and got[1][1] == "none"
     else:
         seen = torch.zeros(ii.numel(), dtype=torch.bool)
