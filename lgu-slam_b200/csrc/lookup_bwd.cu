@@ -379,6 +379,11 @@ static int launch_lookup_bwd(const float* volume, const float* coords, float* of
 
 }  // namespace lgu
 
+namespace lgu {
+int launch_level_tma(bool bwd, const float* volume, const float* coords, float* offset, float* corr,
+                     const float* corr_grad, float* volume_grad, float* offset_grad, int E, int H1, int W1, int H2,
+                     int W2, cudaStream_t st);   // lookup_level_tma.cu
+}
 extern "C" int lgu_corr_index_backward(const float* coords, const float* corr_grad, float* volume_grad, int E, int H1,
                                        int W1, int H2, int W2, int radius, void* stream) {
   if (E == 0) return LGU_OK;   // empty edge set: nothing to do (pointers may be null)
@@ -399,6 +404,11 @@ extern "C" int lgu_defcorr_index_backward(const float* volume, const float* coor
   LGU_REQUIRE(E >= 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && radius >= 0,
               "lgu_defcorr_index_backward: bad sizes E=%d H1=%d W1=%d H2=%d W2=%d r=%d", E, H1, W1, H2, W2, radius);
   LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_defcorr_index_backward: H2*W2 too large");
+  if (radius == 3) {   // TMA-staged footprints + box accumulator (lookup_level_tma.cu)
+    const int rc = lgu::launch_level_tma(true, volume, coords, offset, nullptr, corr_grad, volume_grad, offset_grad, E,
+                                         H1, W1, H2, W2, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   return lgu::launch_lookup_bwd<true>(volume, coords, offset, corr_grad, volume_grad, offset_grad, E, H1, W1, H2, W2,
                                       radius, (cudaStream_t)stream);
 }

@@ -36,7 +36,8 @@ constexpr int kInSlotBytes = kInSlotFloats * 4;                  // 2560 B
 constexpr int kAccFloats = kSlotFloats;                          // 832 floats: acc0 | acc1 | acc2 | acc3
 constexpr int kWarpFloats = kSlots * kInSlotFloats + kAccFloats; // 2112 floats = 8448 B
 constexpr int kSmemWarp = kWarps * kWarpFloats * 4;              // 67,584 B
-constexpr int kSmemG = CH * kOutPitch * 4;                       // 25,872 B
+constexpr int kGWarpFloats = CH * kPixPerWarp;                   // per-warp upstream-gradient rows: 196 x 4 pixels
+constexpr int kSmemG = kWarps * kGWarpFloats * 4;                // 25,088 B
 constexpr int kSmemBytes = kSmemWarp + kSmemG + kWarps * kSlots * 8;
 }  // namespace flb
 
@@ -168,7 +169,7 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
   float* wmem = reinterpret_cast<float*>(smem) + warp * kWarpFloats;
   float* inbox = wmem;                                           // [slot][lvl0 | lvl1]
   float* acc = wmem + kSlots * kInSlotFloats;                    // acc0 | acc1 | acc2 | acc3 (offsets kOff0..3)
-  float* s_g = reinterpret_cast<float*>(smem + kSmemWarp);       // [CH][kOutPitch]
+  float* s_g = reinterpret_cast<float*>(smem + kSmemWarp) + warp * kGWarpFloats;   // this warp's [CH][4 pixels]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemWarp + kSmemG) + warp * kSlots;
 
   const int P = prm.P;
@@ -210,13 +211,18 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
     }
   }
 
-  // upstream gradient tile: 196 rows of 32 pixels (128 B), transposed through shared memory; clear the accumulators
+  // upstream gradients of this warp's 4 pixels: 196 rows of 16 bytes, fetched with cp.async straight into the warp's
+  // own shared-memory strip (no CTA-wide tile, no __syncthreads: a CTA no longer starts with an exposed DRAM round
+  // trip, the rows land while the first TMA boxes are in flight); clear the accumulators
   {
-    const float* g = prm.g_out + (size_t)n * CH * P + p0 + lane;
-    for (int ch = warp; ch < CH; ch += kWarps) s_g[ch * kOutPitch + lane] = __ldg(g + (size_t)ch * P);
+    const float* g = prm.g_out + (size_t)n * CH * P + pw;
+    for (int ch = lane; ch < CH; ch += 32) {
+      const uint32_t dst = fl_smem_u32(s_g + ch * kPixPerWarp);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + (size_t)ch * P) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     for (int q = lane; q < kAccFloats; q += 32) acc[q] = 0.0f;
   }
-  __syncthreads();
 
   const int t0 = lane, t1 = lane + 32;
   const int i0 = t0 / RD, j0 = t0 - i0 * RD;
@@ -241,12 +247,13 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
     mk = __ldg(prm.mask + pix);
   };
   load_offsets(0);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
 
 #pragma unroll 1
   for (int k = 0; k < kPixPerWarp; ++k) {
     const int slot = k & 1;
     const size_t pix = (size_t)n * P + min(pw + k, P - 1);
-    const int pl = warp * kPixPerWarp + k;
     const float x0 = __shfl_sync(0xffffffffu, cmine.x, k), y0 = __shfl_sync(0xffffffffu, cmine.y, k);
     float2 o00 = a0, o01 = a1, o10 = b0, o11 = b1;
     const float2 o10_raw = b0;                                  // the stored centre tap still multiplies g_m (see header)
@@ -258,7 +265,7 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
     fl_mbar_wait(bars + slot, (k >> 1) & 1);
     const float* box0 = inbox + slot * kInSlotFloats;
     const float* box1 = box0 + kBW01 * kBH01;
-    const float* sg = s_g + pl;
+    const float* sg = s_g + k;
 
     const float x1c = __fmul_rn(x0, 0.5f), y1c = __fmul_rn(y0, 0.5f);
     const float x2c = __fmul_rn(x1c, 0.5f), y2c = __fmul_rn(y1c, 0.5f);
@@ -287,8 +294,8 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
         tb.dx = __fsub_rn(px, (float)fx); tb.dy = __fsub_rn(py, (float)fy);
         btap_setup<kBW01, kBH01>(tb, xb, yb, fx, fy, i1, j1, R, H2, W2);
       }
-      ga = sg[(l * TAPS + t0) * kOutPitch];
-      gb = sg[(l * TAPS + t1c) * kOutPitch];
+      ga = sg[(l * TAPS + t0) * kPixPerWarp];
+      gb = sg[(l * TAPS + t1c) * kPixPerWarp];
       // corner values (zero-filled out of bounds by the TMA unit) for the offset gradient
       float qa[4], qb[4];
       {
@@ -382,8 +389,8 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       btap_setup<kBW23, kBH23>(ta, xb, yb, fx, fy, i0, j0, R, H2, W2);
       btap_setup<kBW23, kBH23>(tb, xb, yb, fx, fy, i1, j1, R, H2, W2);
       float* ac = acc + (l == 2 ? kOff2 : kOff3);
-      btap_scatter<kBW23, false>(ac, ta, true, sg[(l * TAPS + t0) * kOutPitch]);
-      btap_scatter<kBW23, false>(ac, tb, has1, sg[(l * TAPS + t1c) * kOutPitch]);
+      btap_scatter<kBW23, false>(ac, ta, true, sg[(l * TAPS + t0) * kPixPerWarp]);
+      btap_scatter<kBW23, false>(ac, tb, has1, sg[(l * TAPS + t1c) * kPixPerWarp]);
     };
     uniform_bwd(2, x2c, y2c, ta2, tb2, xb2, yb2);
     uniform_bwd(3, x3c, y3c, ta3, tb3, xb3, yb3);
@@ -408,10 +415,10 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       btap_scatter_global(G1, ta1, true, ga1, prm.W2[1]);
       btap_scatter_global(G1, tb1, has1, gb1, prm.W2[1]);
       btap_scatter_global(G1, tm, lane < 9, gvk, prm.W2[1]);
-      btap_scatter_global(G2, ta2, true, sg[(2 * TAPS + t0) * kOutPitch], prm.W2[2]);
-      btap_scatter_global(G2, tb2, has1, sg[(2 * TAPS + t1c) * kOutPitch], prm.W2[2]);
-      btap_scatter_global(G3, ta3, true, sg[(3 * TAPS + t0) * kOutPitch], prm.W2[3]);
-      btap_scatter_global(G3, tb3, has1, sg[(3 * TAPS + t1c) * kOutPitch], prm.W2[3]);
+      btap_scatter_global(G2, ta2, true, sg[(2 * TAPS + t0) * kPixPerWarp], prm.W2[2]);
+      btap_scatter_global(G2, tb2, has1, sg[(2 * TAPS + t1c) * kPixPerWarp], prm.W2[2]);
+      btap_scatter_global(G3, ta3, true, sg[(3 * TAPS + t0) * kPixPerWarp], prm.W2[3]);
+      btap_scatter_global(G3, tb3, has1, sg[(3 * TAPS + t1c) * kPixPerWarp], prm.W2[3]);
     }
     __syncwarp();
     if (k + 2 < kPixPerWarp) {
