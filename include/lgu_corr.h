@@ -177,6 +177,23 @@ LGU_API int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lvl1,
                                    float* off0_grad, float* off1_grad,
                                    int E, int H, int W, int num_levels, int radius, void* stream);
 
+/* Edge-slot pool variants (replace the whole-pyramid copies of CorrBlock.cat / CorrBlock.__getitem__,
+ * corr.py:111-115,137-141, which the frontend pays on every keyframe: factor_graph.py:123,158).  The pyramid levels
+ * and the offsets live in storage of `num_slots` edge slots ([num_slots,H,W,H>>l,W>>l], [num_slots,H,W,7,7,2]);
+ * out_slots[e] / slots[e] (int32, device) name the slot of the e-th edge of this call.  Adding edges = building into
+ * free slots; removing edges = dropping their slot numbers; nothing is copied.  Everything else as in
+ * lgu_build_pyramid / lgu_corr_lookup_fused (means, covs, den, coords, corr, mask_out are in call order). */
+LGU_API int lgu_build_pyramid_slots(const void* fmaps_hi, const void* fmaps_lo, const int32_t* ii, const int32_t* jj,
+                            const float* means, const float* covs, const float* den,
+                            float* lvl0, float* lvl1, float* lvl2, float* lvl3,
+                            const int32_t* out_slots, int num_slots,
+                            int T, int E, int H, int W, int C, int gauss_radius, int precision,
+                            int round_half, void* stream);
+LGU_API int lgu_corr_lookup_fused_slots(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
+                                const int32_t* slots, int num_slots,
+                                int E, int H, int W, int num_levels, int radius, void* stream);
+
 /* All-pairs volume between two DIFFERENT map sets, no Gaussian, no pooling:
  *   volume[e, p, q] = sum_c fmaps1[ii[e], p, c] * fmaps2[jj[e], q, c]        (fp32 accumulate on tcgen05)
  * fmaps1 [T1,P,C], fmaps2 [T2,Q,C]: channels-last fp16 planes, already scaled (the caller's /4, corr.py:163);

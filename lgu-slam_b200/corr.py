@@ -284,6 +284,109 @@ class CorrBlock:
 
 
 # ------------------------------------------------------------------------------------------------
+# Edge-slot pool: CorrBlock.cat / __getitem__ without copying the pyramid
+# ------------------------------------------------------------------------------------------------
+class CorrPool:
+    """Storage for up to `capacity` edges: the four pyramid levels [capacity,h,w,h>>l,w>>l] and the two offset tensors
+    [capacity,h,w,98], allocated once.  The frontend's factor graph adds and drops edges on every keyframe
+    (factor_graph.py:90-167); with the reference's CorrBlock each of those is a torch.cat / boolean-index COPY of the
+    whole pyramid (corr.py:111-115,137-141; <= 2.4 GB at 48 edges).  Here an edge is a slot number."""
+
+    def __init__(self, capacity, h, w, device, num_levels=4, radius=3):
+        self.capacity, self.h, self.w, self.num_levels, self.radius = capacity, h, w, num_levels, radius
+        self.levels = [torch.empty(capacity, h, w, h >> l, w >> l, dtype=torch.float32, device=device)
+                       for l in range(num_levels)]
+        nch = 2 * (2 * radius + 1) ** 2
+        self.off0 = torch.zeros(capacity, h, w, nch, dtype=torch.float32, device=device)
+        self.off1 = torch.zeros(capacity, h, w, nch, dtype=torch.float32, device=device)
+        self.free = list(range(capacity - 1, -1, -1))
+
+    def alloc(self, n):
+        if n > len(self.free):
+            raise RuntimeError(f"CorrPool: {n} slots requested, {len(self.free)} free of {self.capacity}")
+        return [self.free.pop() for _ in range(n)]
+
+    def release(self, slots):
+        self.free.extend(reversed(list(slots)))
+
+
+class PooledCorrBlock:
+    """CorrBlock (corr.py:53-152) for inference on a CorrPool: same constructor arguments (+ pool), same
+    `__call__(coords) -> (corr, mean_n, theta)`, `cat`, `__getitem__`; edges live in pool slots, so `cat` and
+    `__getitem__` only edit the slot list.  Build = one tcgen05 launch into the slots, lookup = one TMA-staged launch."""
+
+    def __init__(self, pool, ofsMap, ofs_residual, GA, fmap1, fmap2, num_levels=4, radius=3, autocast_rounding=False):
+        assert num_levels == pool.num_levels == 4 and radius == pool.radius == 3
+        self.pool, self.num_levels, self.radius = pool, num_levels, radius
+        self.GA, self.ofsMap, self.ofs_residual = GA, ofsMap, ofs_residual
+        b, n, c, h, w = fmap1.shape
+        E = b * n
+        assert (h, w) == (pool.h, pool.w) and w == 64 and h % 8 == 0 and c == 128
+        self.batch = b
+        with torch.no_grad():
+            f1, f2 = fmap1.reshape(E, c, h, w), fmap2.reshape(E, c, h, w)
+            t = torch.cat((f1, f2), dim=1)
+            offs = _generate_offsets(ofsMap, ofs_residual, t.float())
+            mean, cov, det = GA.params(t.permute(0, 2, 3, 1).float())
+            self.slots = pool.alloc(E)
+            sl = torch.tensor(self.slots, dtype=torch.int32, device=fmap1.device)
+            idx = sl.long()
+            pool.off0[idx] = offs[0]
+            pool.off1[idx] = offs[1]
+            frames = torch.cat((f1, f2), dim=0).contiguous()
+            hi, lo = ops.pack_fmaps(frames, split=frames.dtype == torch.float32)
+            ar = torch.arange(2 * E, dtype=torch.int32, device=frames.device)
+            den = (6.28 * torch.sqrt(det)).view(E, h, w).float().contiguous()
+            ops.build_pyramid(hi, lo, ar[:E].contiguous(), ar[E:].contiguous(), h, w, means=mean.float().contiguous(),
+                              covs=cov.contiguous(), den=den, num_levels=num_levels, gauss_radius=GAUSS_RADIUS,
+                              round_half=autocast_rounding, out=pool.levels, out_slots=sl)
+        self.mean_n = mean.view(E, h, w, 2)
+        self.theta = 2 * det.view(E, h, w)
+        self._sl = sl
+
+    def _slot_tensor(self, device):
+        if self._sl is None or self._sl.numel() != len(self.slots):
+            self._sl = torch.tensor(self.slots, dtype=torch.int32, device=device)
+        return self._sl
+
+    def __len__(self):
+        return len(self.slots)
+
+    @torch.no_grad()
+    def __call__(self, coords):
+        batch, num, ht, wd, _ = coords.shape
+        E = batch * num
+        assert E == len(self.slots), f"coords carry {E} edges, the block holds {len(self.slots)}"
+        c = coords.reshape(E, ht, wd, 2).float().contiguous()
+        out = ops.corr_lookup_fused(self.pool.levels, c, self.pool.off0, self.pool.off1, self.radius,
+                                    slots=self._slot_tensor(c.device))
+        return out.view(batch, num, -1, ht, wd), self.mean_n.view(batch, num, ht, wd, 2), self.theta.view(batch, num, ht, wd)
+
+    def cat(self, other):
+        assert other.pool is self.pool, "cat needs blocks of the same CorrPool"
+        self.slots = self.slots + other.slots
+        other.slots = []
+        self.mean_n = torch.cat([self.mean_n, other.mean_n], 0)
+        self.theta = torch.cat([self.theta, other.theta], 0)
+        self._sl = None
+        return self
+
+    def __getitem__(self, index):
+        n = len(self.slots)
+        keep = torch.arange(n)[index.cpu() if isinstance(index, torch.Tensor) else index].tolist()
+        kept = set(keep)
+        self.pool.release([s for i, s in enumerate(self.slots) if i not in kept])
+        self.slots = [self.slots[i] for i in keep]
+        self.mean_n, self.theta = self.mean_n[index], self.theta[index]
+        self._sl = None
+        return self
+
+    def release(self):
+        self.pool.release(self.slots)
+        self.slots = []
+
+
+# ------------------------------------------------------------------------------------------------
 # AltCorrBlock (backend, no volume)
 # ------------------------------------------------------------------------------------------------
 class AltCorrBlock:

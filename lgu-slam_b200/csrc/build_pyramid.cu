@@ -175,6 +175,7 @@ struct BpParams {
   float* lvl2;          // [E,P,Q/16] or null
   float* lvl3;          // [E,P,Q/64] or null
   int E, P, H, gauss_radius, round_half, num_units, has_l1;
+  const int32_t* out_slots;   // [E] or null: edge e is written to pyramid slot out_slots[e] (edge-slot pool)
   int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
   int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
 };
@@ -390,15 +391,17 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     uint32_t half_it = 0;
     for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x) {
       const int e = u / tiles_m, mt = u - e * tiles_m;
-      const int row0 = e * P + mt * kTileM + quad * 32;   // first output row (edge-pixel index) of this warp
+      const int es = prm.out_slots != nullptr ? __ldg(prm.out_slots + e) : e;   // storage slot of this edge
+      const int row0 = es * P + mt * kTileM + quad * 32;  // first output row (slot-pixel index) of this warp
       const size_t pix = (size_t)row0 + lane;
       float mx = 0.f, my = 0.f, c1 = 1.f, c2 = 1.f, den = 1.f;
       unsigned bx = 0, by = 0;
       if (gr > 0) {
-        const float2 m = __ldg(reinterpret_cast<const float2*>(prm.means) + pix);
-        const float2 c = __ldg(reinterpret_cast<const float2*>(prm.covs) + pix);
+        const size_t ipix = (size_t)e * P + mt * kTileM + quad * 32 + lane;      // Gaussian parameters: input order
+        const float2 m = __ldg(reinterpret_cast<const float2*>(prm.means) + ipix);
+        const float2 c = __ldg(reinterpret_cast<const float2*>(prm.covs) + ipix);
         mx = m.x; my = m.y; c1 = c.x; c2 = c.y;
-        den = __ldg(prm.den + pix);
+        den = __ldg(prm.den + ipix);
         bx = (unsigned)floor_to_int(mx) - (unsigned)gr;
         by = (unsigned)floor_to_int(my) - (unsigned)gr;
       }
@@ -602,10 +605,33 @@ extern "C" int lgu_pack_fmaps(const void* fmaps, int src_is_half, void* hi, void
   return lgu::check_launch("lgu_pack_fmaps");
 }
 
+static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const int32_t* ii, const int32_t* jj,
+                              const float* means, const float* covs, const float* den, float* lvl0, float* lvl1,
+                              float* lvl2, float* lvl3, const int32_t* out_slots, int num_slots, int T, int E, int H,
+                              int W, int C, int gauss_radius, int precision, int round_half, void* stream);
 extern "C" int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, const int32_t* ii, const int32_t* jj,
                                  const float* means, const float* covs, const float* den, float* lvl0, float* lvl1,
                                  float* lvl2, float* lvl3, int T, int E, int H, int W, int C, int gauss_radius,
                                  int precision, int round_half, void* stream) {
+  return build_pyramid_impl(fmaps_hi, fmaps_lo, ii, jj, means, covs, den, lvl0, lvl1, lvl2, lvl3, nullptr, E, T, E, H, W,
+                            C, gauss_radius, precision, round_half, stream);
+}
+extern "C" int lgu_build_pyramid_slots(const void* fmaps_hi, const void* fmaps_lo, const int32_t* ii, const int32_t* jj,
+                                       const float* means, const float* covs, const float* den, float* lvl0,
+                                       float* lvl1, float* lvl2, float* lvl3, const int32_t* out_slots, int num_slots,
+                                       int T, int E, int H, int W, int C, int gauss_radius, int precision,
+                                       int round_half, void* stream) {
+  if (E > 0 && out_slots == nullptr) {
+    lgu::set_error("lgu_build_pyramid_slots: null slot list");
+    return LGU_ERR_BAD_ARG;
+  }
+  return build_pyramid_impl(fmaps_hi, fmaps_lo, ii, jj, means, covs, den, lvl0, lvl1, lvl2, lvl3, out_slots, num_slots, T,
+                            E, H, W, C, gauss_radius, precision, round_half, stream);
+}
+static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const int32_t* ii, const int32_t* jj,
+                              const float* means, const float* covs, const float* den, float* lvl0, float* lvl1,
+                              float* lvl2, float* lvl3, const int32_t* out_slots, int num_slots, int T, int E, int H,
+                              int W, int C, int gauss_radius, int precision, int round_half, void* stream) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(fmaps_hi && ii && jj && lvl0, "lgu_build_pyramid: null pointer");
@@ -620,7 +646,9 @@ extern "C" int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, con
   LGU_REQUIRE(lvl2 == nullptr || lvl1 != nullptr, "lgu_build_pyramid: lvl2 requires lvl1");
   LGU_REQUIRE(lvl3 == nullptr || lvl2 != nullptr, "lgu_build_pyramid: lvl3 requires lvl2");
   const int P = H * W;
-  LGU_REQUIRE((long long)E * P < 2147483647LL && (long long)T * P < 2147483647LL, "lgu_build_pyramid: too many rows");
+  LGU_REQUIRE(num_slots >= 1, "lgu_build_pyramid: bad pool size %d", num_slots);
+  LGU_REQUIRE((long long)num_slots * P < 2147483647LL && (long long)T * P < 2147483647LL, "lgu_build_pyramid: too many rows");
+  const long long S = num_slots;                                 // rows of the output storage = slots * P
 
   CUtensorMap mh, ml, m0, m1;
   int rc = make_map_2d(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fmaps_hi, (uint64_t)T * P, C, 128, 64);
@@ -628,10 +656,10 @@ extern "C" int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, con
   rc = make_map_2d(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, precision == 2 ? fmaps_lo : fmaps_hi, (uint64_t)T * P, C,
                    128, 64);
   if (rc) return rc;
-  rc = make_map_2d(&m0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, (uint64_t)E * P, P, 32, 32);
+  rc = make_map_2d(&m0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl0, (uint64_t)S * P, P, 32, 32);
   if (rc) return rc;
   // level-1 store tiles: 32 rows x 128 B shared by a warp pair (precision 1), 32 rows x 64 B per warp (precision 2)
-  rc = make_map_2d(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl1 ? lvl1 : lvl0, (uint64_t)E * P, lvl1 ? P / 4 : P, 32,
+  rc = make_map_2d(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl1 ? lvl1 : lvl0, (uint64_t)S * P, lvl1 ? P / 4 : P, 32,
                    precision == 1 ? 32 : 16, precision == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
 
@@ -641,6 +669,7 @@ extern "C" int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, con
   prm.E = E; prm.P = P; prm.H = H; prm.gauss_radius = gauss_radius; prm.round_half = round_half;
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = lvl1 != nullptr;
+  prm.out_slots = out_slots;
   prm.Q = P;
   prm.halves = H / 4;
   if (precision == 1) return launch_build<1>(mh, ml, mh, ml, m0, m1, prm, (cudaStream_t)stream);
@@ -681,6 +710,7 @@ extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, co
   prm.E = E; prm.P = P; prm.H = 0; prm.gauss_radius = 0; prm.round_half = 0;
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = 0;
+  prm.out_slots = nullptr;
   prm.Q = Q;
   prm.halves = (Q + 255) / 256;
   if (precision == 1) return launch_build<1>(mh, ml, mbh, mbl, m0, m0, prm, (cudaStream_t)stream);

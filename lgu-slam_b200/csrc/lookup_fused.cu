@@ -37,6 +37,7 @@ struct FusedLookupParams {
   int H2[4], W2[4];
   long long off_edge_stride;   // float2 elements between the offset slabs of consecutive edges (0: every edge reads slab 0, Q2)
   int apply_mask;              // 1: off1 <- off1 * sigmoid(var) of this call (CorrBlock); 0: offsets are used as given
+  const int32_t* slots;        // [E] or null: edge n lives in pyramid / offset slot slots[n] (edge-slot pool)
 };
 
 template <bool PC>   // PC: per-corner gating (lowMem / altcorr semantics, Q4) instead of top-left gating (Q3)
@@ -53,6 +54,7 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
   const int n = blockIdx.x / prm.tiles_per_edge;
   const int p0 = (blockIdx.x - n * prm.tiles_per_edge) * kTile;
   const int pw = p0 + warp * kPixPerWarp;                       // first pixel of this warp
+  const int ns = prm.slots != nullptr ? __ldg(prm.slots + n) : n;   // storage slot of this edge (pyramid, offsets)
 
   if (lane == 0) {
     fl_mbar_init(bars + 0, 1);
@@ -68,7 +70,7 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 
   auto issue = [&](int k, float cx, float cy) {                 // lane 0 only
     const int slot = k & 1;
-    const int pix = n * P + min(pw + k, P - 1);
+    const int pix = ns * P + min(pw + k, P - 1);
     float* dst = boxes + slot * kSlotFloats;
     fl_mbar_expect_tx(bars + slot, kSlotBytes);
     float sx = cx, sy = cy;
@@ -102,7 +104,7 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 
   float2 a0, a1, b0, b1;                                        // level-0 / level-1 offsets of taps t0, t1
   auto load_offsets = [&](int k) {
-    const size_t opix = (size_t)n * prm.off_edge_stride + (size_t)min(pw + k, P - 1) * TAPS;
+    const size_t opix = (size_t)ns * prm.off_edge_stride + (size_t)min(pw + k, P - 1) * TAPS;
     const float2* O0 = reinterpret_cast<const float2*>(prm.off0) + opix;
     const float2* O1 = reinterpret_cast<const float2*>(prm.off1) + opix;
     a0 = O0[t0]; a1 = O0[t1c]; b0 = O1[t0]; b1 = O1[t1c];
@@ -158,7 +160,7 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     const int slot = k & 1;
     const int p = pw + k;
     const bool live = p < P;                                    // warp-uniform
-    const size_t pix = (size_t)n * P + min(p, P - 1);
+    const size_t pix = (size_t)ns * P + min(p, P - 1);          // slice index in the pyramid storage
     const float x0 = __shfl_sync(0xffffffffu, cmine.x, k), y0 = __shfl_sync(0xffffffffu, cmine.y, k);
     float2 o00 = a0, o01 = a1, o10 = b0, o11 = b1;              // this pixel's offsets (loaded one iteration ahead)
     if (lane == CENTER) o00 = make_float2(0.0f, 0.0f);          // Q5: the centre tap reads as 0
@@ -214,11 +216,11 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     // ---------------- in-place side effects on the caller's offsets
     if (live) {
       if (prm.apply_mask) {
-        float2* O1 = reinterpret_cast<float2*>(prm.off1) + (size_t)n * prm.off_edge_stride + (size_t)min(p, P - 1) * TAPS;
+        float2* O1 = reinterpret_cast<float2*>(prm.off1) + (size_t)ns * prm.off_edge_stride + (size_t)min(p, P - 1) * TAPS;
         O1[t0] = o10_store;
         if (has1) O1[t1] = o11;
       }
-      if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[pix] = m;
+      if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[(size_t)n * P + p] = m;
     }
     __syncwarp();                                               // every lane is done with this slot
     if (k + 2 < kPixPerWarp) {
@@ -242,25 +244,35 @@ namespace lgu {
 static int launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                const float* coords, const float* off0, float* off1, float* corr, float* mask_out, int E,
                                int H, int W, int num_levels, int radius, int per_corner, int shared_offsets,
-                               int apply_mask, void* stream);
+                               int apply_mask, const int32_t* slots, int num_slots, void* stream);
 }
 extern "C" int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                      const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                      int E, int H, int W, int num_levels, int radius, void* stream) {
   return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, corr, mask_out, E, H, W, num_levels,
-                                  radius, 0, 0, 1, stream);
+                                  radius, 0, 0, 1, nullptr, E, stream);
+}
+extern "C" int lgu_corr_lookup_fused_slots(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                           const float* coords, const float* off0, float* off1, float* corr,
+                                           float* mask_out, const int32_t* slots, int num_slots, int E, int H, int W,
+                                           int num_levels, int radius, void* stream) {
+  LGU_REQUIRE(E == 0 || slots != nullptr, "lgu_corr_lookup_fused_slots: null slot list");
+  LGU_REQUIRE(num_slots > 0, "lgu_corr_lookup_fused_slots: bad pool size %d", num_slots);
+  return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, corr, mask_out, E, H, W, num_levels,
+                                  radius, 0, 0, 1, slots, num_slots, stream);
 }
 extern "C" int lgu_altcorr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                         const float* coords, const float* off0, float* off1, float* corr,
                                         float* mask_out, int E, int H, int W, int num_levels, int radius,
                                         int shared_offsets, int apply_mask, void* stream) {
   return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, corr, mask_out, E, H, W, num_levels,
-                                  radius, 1, shared_offsets, apply_mask, stream);
+                                  radius, 1, shared_offsets, apply_mask, nullptr, E, stream);
 }
 static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                     const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                     int E, int H, int W, int num_levels, int radius, int per_corner,
-                                    int shared_offsets, int apply_mask, void* stream) {
+                                    int shared_offsets, int apply_mask, const int32_t* slots, int num_slots,
+                                    void* stream) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && off0 && off1 && corr, "lgu_corr_lookup_fused: null pointer");
@@ -271,8 +283,8 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
     return LGU_ERR_UNSUPPORTED;
   }
   const int P = H * W;
-  const long long nslices = (long long)E * P;
-  LGU_REQUIRE(nslices < 2147483647LL, "lgu_corr_lookup_fused: E*H*W = %lld exceeds the TMA coordinate range", nslices);
+  const long long nslices = (long long)num_slots * P;        // slices held by the storage (== E without a pool)
+  LGU_REQUIRE(nslices < 2147483647LL, "lgu_corr_lookup_fused: slots*H*W = %lld exceeds the TMA coordinate range", nslices);
   const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
   for (int l = 0; l < 4; ++l)
     LGU_REQUIRE((reinterpret_cast<uintptr_t>(lv[l]) & 15) == 0, "lgu_corr_lookup_fused: level %d is not 16-byte aligned", l);
@@ -293,6 +305,7 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
   LGU_REQUIRE(nblk < 2147483647LL, "lgu_corr_lookup_fused: grid too large (%lld CTAs)", nblk);
   prm.off_edge_stride = shared_offsets ? 0 : (long long)P * fl::TAPS;
   prm.apply_mask = apply_mask;
+  prm.slots = slots;
   LGU_REQUIRE(!(shared_offsets && apply_mask), "lgu_*_lookup_fused: apply_mask needs per-edge offsets");
   auto kern = per_corner ? lookup_fused_kernel<true> : lookup_fused_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::kSmemBytes);

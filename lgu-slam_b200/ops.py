@@ -200,11 +200,13 @@ def pack_fmaps(fmaps, split=False):
 
 
 def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_levels=4, gauss_radius=4,
-                  precision=None, round_half=False):
+                  precision=None, round_half=False, out=None, out_slots=None):
     """CorrBlock.__init__'s data path (corr.py:61-86) in one tcgen05/TMA kernel: all-pairs volume of edge
     (ii[e] -> jj[e]) + Gaussian residual (gaussianMask_cuda.py:84-86) + num_levels-level average pyramid.
     hi/lo from pack_fmaps; ii, jj int32 [E]; means, covs [E,H,W,2]; den [E,H,W] = 6.28*sqrt(cov_x*cov_y).
-    Returns [lvl0 [E,H,W,H,W], lvl1 [E,H,W,H/2,W/2], ...]."""
+    Returns [lvl0 [E,H,W,H,W], lvl1 [E,H,W,H/2,W/2], ...].
+    Edge-slot pool: out = the pool's level storages [S,H,W,H>>l,W>>l] and out_slots = int32 [E] slot of each edge;
+    the levels are then written in place (nothing is allocated) and `out` is returned."""
     if hi.dtype != torch.float16 or not hi.is_cuda or hi.dim() != 3 or not hi.is_contiguous():
         raise RuntimeError("hi must be a contiguous CUDA fp16 tensor [T,H*W,C] (see pack_fmaps)")
     T, P, C = hi.shape
@@ -227,8 +229,27 @@ def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_lev
             raise RuntimeError("means/covs must be [E,H,W,2] and den [E,H,W]")
     if not 1 <= num_levels <= 4:
         raise RuntimeError("num_levels must be in 1..4")
-    lv = [torch.empty(E, H, W, H >> l, W >> l, dtype=torch.float32, device=hi.device) for l in range(num_levels)]
     null = ctypes.c_void_p(0)
+    if out is not None:
+        if out_slots is None or not (out_slots.is_cuda and out_slots.dtype == torch.int32 and out_slots.numel() == E
+                                     and out_slots.is_contiguous()):
+            raise RuntimeError("out_slots must be a contiguous CUDA int32 vector with one slot per edge")
+        S = out[0].shape[0]
+        for l, t in enumerate(out[:num_levels]):
+            _chk(t, f"out[{l}]", 5)
+            if tuple(t.shape) != (S, H, W, H >> l, W >> l):
+                raise RuntimeError(f"out[{l}] shape {tuple(t.shape)} != {(S, H, W, H >> l, W >> l)}")
+        lv = list(out[:num_levels])
+        ptr = [_p(t) for t in lv] + [null] * (4 - num_levels)
+        with torch.cuda.device(hi.device):
+            st = _lib.lib().lgu_build_pyramid_slots(
+                _p(hi), _p(lo) if precision == 2 else null, _p(ii), _p(jj), _p(means) if use_gauss else null,
+                _p(covs) if use_gauss else null, _p(den) if use_gauss else null, ptr[0], ptr[1], ptr[2], ptr[3],
+                _p(out_slots), _i(S), _i(T), _i(E), _i(H), _i(W), _i(C), _i(gauss_radius if use_gauss else 0),
+                _i(precision), _i(1 if round_half else 0), _stream(hi))
+        _lib.check(st, "build_pyramid (slots)")
+        return lv
+    lv = [torch.empty(E, H, W, H >> l, W >> l, dtype=torch.float32, device=hi.device) for l in range(num_levels)]
     ptr = [_p(t) for t in lv] + [null] * (4 - num_levels)
     with torch.cuda.device(hi.device):
         st = _lib.lib().lgu_build_pyramid(_p(hi), _p(lo) if precision == 2 else null, _p(ii), _p(jj),
@@ -240,34 +261,44 @@ def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_lev
     return lv
 
 
-def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False):
+def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False, slots=None):
     """CorrBlock.__call__'s data path (corr.py:88-109) in one TMA-staged kernel.
     pyramid: 4 tensors [E,H,W,H>>l,W>>l]; coords [E,H,W,2] (x,y; level-0 units); off0, off1 [E,H,W,98] or
     [E,H,W,7,7,2]; off1 is mutated in place (multiplied by this call's uncertainty mask, Q7); the centre taps are
     read as 0 (Q5) but left untouched in memory.  Returns corr [E,196,H,W] (and the mask [E,H,W] if return_mask)."""
     if len(pyramid) != 4:
         raise RuntimeError("corr_lookup_fused needs a 4-level pyramid")
-    E, H, W = pyramid[0].shape[:3]
+    S, H, W = pyramid[0].shape[:3]                    # S = storage slots (== edges without a pool)
     for l, t in enumerate(pyramid):
         _chk(t, f"pyramid[{l}]", 5)
-        if tuple(t.shape) != (E, H, W, H >> l, W >> l):
-            raise RuntimeError(f"pyramid[{l}] shape {tuple(t.shape)} != {(E, H, W, H >> l, W >> l)}")
+        if tuple(t.shape) != (S, H, W, H >> l, W >> l):
+            raise RuntimeError(f"pyramid[{l}] shape {tuple(t.shape)} != {(S, H, W, H >> l, W >> l)}")
     _chk(coords, "coords", 4)
+    E = coords.shape[0] if slots is not None else S
+    if slots is not None and not (slots.is_cuda and slots.dtype == torch.int32 and slots.is_contiguous()
+                                  and slots.numel() == E):
+        raise RuntimeError("slots must be a contiguous CUDA int32 vector with one slot per edge of coords")
     if tuple(coords.shape) != (E, H, W, 2):
         raise RuntimeError(f"coords shape {tuple(coords.shape)} != {(E, H, W, 2)}")
     rd = 2 * int(radius) + 1
     for name, o in (("off0", off0), ("off1", off1)):
         if not (isinstance(o, torch.Tensor) and o.is_cuda and o.is_contiguous() and o.dtype == torch.float32):
             raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor")
-        if o.numel() != E * H * W * rd * rd * 2:
-            raise RuntimeError(f"{name} has {o.numel()} elements, expected {E * H * W * rd * rd * 2}")
+        if o.numel() != S * H * W * rd * rd * 2:
+            raise RuntimeError(f"{name} has {o.numel()} elements, expected {S * H * W * rd * rd * 2}")
     corr = torch.empty(E, 4 * rd * rd, H, W, dtype=torch.float32, device=coords.device)
     mask = torch.empty(E, H, W, dtype=torch.float32, device=coords.device) if return_mask else None
     with torch.cuda.device(coords.device):
-        st = _lib.lib().lgu_corr_lookup_fused(_p(pyramid[0]), _p(pyramid[1]), _p(pyramid[2]), _p(pyramid[3]),
-                                              _p(coords), _p(off0), _p(off1), _p(corr),
-                                              _p(mask) if return_mask else ctypes.c_void_p(0),
-                                              _i(E), _i(H), _i(W), _i(4), _i(radius), _stream(coords))
+        if slots is not None:
+            st = _lib.lib().lgu_corr_lookup_fused_slots(_p(pyramid[0]), _p(pyramid[1]), _p(pyramid[2]), _p(pyramid[3]),
+                                                        _p(coords), _p(off0), _p(off1), _p(corr),
+                                                        _p(mask) if return_mask else ctypes.c_void_p(0), _p(slots),
+                                                        _i(S), _i(E), _i(H), _i(W), _i(4), _i(radius), _stream(coords))
+        else:
+            st = _lib.lib().lgu_corr_lookup_fused(_p(pyramid[0]), _p(pyramid[1]), _p(pyramid[2]), _p(pyramid[3]),
+                                                  _p(coords), _p(off0), _p(off1), _p(corr),
+                                                  _p(mask) if return_mask else ctypes.c_void_p(0),
+                                                  _i(E), _i(H), _i(W), _i(4), _i(radius), _stream(coords))
     _lib.check(st, "corr_lookup_fused")
     return (corr, mask) if return_mask else corr
 

@@ -177,3 +177,43 @@ def test_build_volume_matches_matmul(ops):
         want = torch.matmul(f1[ii.long()].double(), f2[jj.long()].double().transpose(1, 2))
         assert got.shape == (4, 3072, Q)
         assert (got.double() - want).abs().max().item() <= 1e-5, f"Q={Q}"
+
+
+def test_pooled_corrblock_matches_corrblock_through_add_and_remove():
+    """Edge-slot pool: build into slots, cat, drop edges, add more (reusing freed slots), look up --
+    identical to the copying CorrBlock at every stage."""
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 5)
+    g = inputs.gen(13)
+    mk = lambda n: (torch.randn(1, n, 128, 48, 64, generator=g).half().to(dev),
+                    torch.randn(1, n, 128, 48, 64, generator=g).half().to(dev))
+    mc = lambda n: inputs.make_coords(n, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, n, 48, 64, 2).to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            pool = corr.CorrPool(6, 48, 64, dev)
+            fa, fb, fc = mk(3), mk(2), mk(2)
+            ref = corr.CorrBlock(ofsMap, ofs_residual, GA, *fa)
+            blk = corr.PooledCorrBlock(pool, ofsMap, ofs_residual, GA, *fa)
+            ref = ref.cat(corr.CorrBlock(ofsMap, ofs_residual, GA, *fb))
+            blk = blk.cat(corr.PooledCorrBlock(pool, ofsMap, ofs_residual, GA, *fb))
+            assert len(blk) == 5 and len(pool.free) == 1
+            c5 = mc(5)
+            o_ref, _, _ = ref(c5)
+            o_blk, mean_n, theta = blk(c5)
+            assert torch.equal(o_ref, o_blk) and mean_n.shape == (1, 5, 48, 64, 2) and theta.shape == (1, 5, 48, 64)
+            keep = torch.tensor([True, False, True, True, False], device=dev)
+            ref, blk = ref[keep], blk[keep]
+            assert len(blk) == 3 and len(pool.free) == 3
+            ref = ref.cat(corr.CorrBlock(ofsMap, ofs_residual, GA, *fc))
+            blk = blk.cat(corr.PooledCorrBlock(pool, ofsMap, ofs_residual, GA, *fc))      # reuses the freed slots
+            c5b = mc(5)
+            for _ in range(2):                                   # second call: cumulative offset[1] mask per slot (Q7)
+                o_ref, _, _ = ref(c5b)
+                o_blk, _, _ = blk(c5b)
+                assert torch.equal(o_ref, o_blk)
+            with pytest.raises(RuntimeError, match="slots requested"):
+                corr.PooledCorrBlock(pool, ofsMap, ofs_residual, GA, *mk(2))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
