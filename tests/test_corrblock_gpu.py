@@ -217,3 +217,51 @@ def test_pooled_corrblock_matches_corrblock_through_add_and_remove():
                 corr.PooledCorrBlock(pool, ofsMap, ofs_residual, GA, *mk(2))
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_training_clip_fused_lookup_equals_per_op_autograd():
+    """BASELINE configs[2] in miniature (train.py step shape: a clip's edges, several lookup iterations, one backward,
+    droid_net.py:187-222): the same CorrBlock with the fused differentiable lookup and with the reference's per-operator
+    autograd graph gives the same outputs and the same gradients on feature maps, offset heads and Gaussian head."""
+    dev = "cuda"
+    g = inputs.gen(14)
+    b, n, steps = 2, 5, 3
+    fm1 = torch.randn(b, n, 128, 48, 64, generator=g).to(dev)
+    fm2 = torch.randn(b, n, 128, 48, 64, generator=g).to(dev)
+    coords = [inputs.make_coords(b * n, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(b, n, 48, 64, 2).to(dev)
+              for _ in range(steps)]
+    wts = [torch.randn(b, n, 196, 48, 64, generator=g).to(dev) for _ in range(steps)]
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    res = []
+    try:
+        for fused_lookup in (True, False):
+            corr, ofsMap, ofs_residual, GA = _modules(dev, 6)
+            f1, f2 = fm1.clone().requires_grad_(), fm2.clone().requires_grad_()
+            blk = corr.CorrBlock(ofsMap, ofs_residual, GA, f1, f2, fused_lookup=fused_lookup)
+            loss = 0.0
+            outs = []
+            for c, w in zip(coords, wts):
+                out, mean_n, theta = blk(c)
+                outs.append(out.detach())
+                loss = loss + (out * w).mean() + 1e-3 * (mean_n.square().mean() + theta.mean())
+            loss.backward()
+            res.append((outs, [t.grad.clone() for t in (f1, f2, ofsMap.weight, ofs_residual.weight, GA.map.weight,
+                                                         GA.covMap.weight, GA.meanMap.weight)]))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    (outs_a, grads_a), (outs_b, grads_b) = res
+    for k, (a, bb) in enumerate(zip(outs_a, outs_b)):
+        assert (a - bb).abs().max().item() <= 2e-5, f"lookup {k}"
+    names = ("fmap1", "fmap2", "ofsMap.weight", "ofs_residual.weight", "GA.map.weight", "GA.covMap.weight",
+             "GA.meanMap.weight")
+    # the two graphs sum the same fp32 terms in different orders (shared-memory reductions in the fused backward); the
+    # feature-map gradients then pass through a 3072-term matmul with heavy cancellation -> compare against the RMS
+    report = []
+    for name, a, bb in zip(names, grads_a, grads_b):
+        rms = bb.square().mean().sqrt().item()
+        err = (a - bb).abs().max().item()
+        report.append(f"{name}: max err {err:.3e}, rms {rms:.3e}")
+        assert err <= 2e-2 * rms + 1e-12, "; ".join(report)
+    print("\n".join(report))
