@@ -528,6 +528,40 @@ __global__ void __launch_bounds__(256) pack_fmaps_kernel(const SRC* __restrict__
   }
 }
 
+// Vector version for C % 64 == 0, P % 64 == 0 and 16-byte aligned tensors: 64 channels x 64 pixels per block, 16-byte
+// loads along the pixel axis and 16-byte stores along the channel axis (the scalar kernel above moved 2 bytes per
+// thread and took 31 us for 20 frames, 38 % of the roofline).
+template <typename SRC>
+__global__ void __launch_bounds__(256) pack_fmaps_vec_kernel(const SRC* __restrict__ src, __half* __restrict__ hi,
+                                                             __half* __restrict__ lo, int C, int P) {
+  __shared__ float tile[64][65];
+  constexpr int PER = 16 / (int)sizeof(SRC);             // source elements per 16-byte load (8 halves / 4 floats)
+  constexpr int SEGS = 64 / PER;                         // 16-byte segments per 64-pixel row
+  const int t = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  for (int q = threadIdx.x; q < 64 * SEGS; q += 256) {
+    const int c = q / SEGS, seg = q - c * SEGS;
+    const uint4 raw = *reinterpret_cast<const uint4*>(src + ((size_t)t * C + c0 + c) * P + p0 + seg * PER);
+    const SRC* e = reinterpret_cast<const SRC*>(&raw);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) tile[c][seg * PER + k] = (float)e[k];
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < 64 * 8; q += 256) {
+    const int p = q >> 3, seg = q & 7;
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float x = tile[seg * 8 + k][p] * 0.25f;
+      h[k] = __float2half_rn(x);
+      l[k] = __float2half_rn(x - __half2float(h[k]));
+    }
+    const size_t o = ((size_t)t * P + p0 + p) * C + c0 + seg * 8;
+    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+    if (lo != nullptr) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -595,6 +629,18 @@ extern "C" int lgu_pack_fmaps(const void* fmaps, int src_is_half, void* hi, void
   if (T == 0) return LGU_OK;
   LGU_REQUIRE(fmaps && hi, "lgu_pack_fmaps: null pointer");
   LGU_REQUIRE(T > 0 && C > 0 && P > 0 && T <= 65535, "lgu_pack_fmaps: bad sizes T=%d C=%d P=%d", T, C, P);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(fmaps) | reinterpret_cast<uintptr_t>(hi) |
+                         reinterpret_cast<uintptr_t>(lo)) & 15) == 0;
+  if ((C % 64) == 0 && (P % 64) == 0 && aligned) {
+    const dim3 vgrid(P / 64, C / 64, T);
+    if (src_is_half)
+      lgu::pack_fmaps_vec_kernel<__half><<<vgrid, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const __half*>(fmaps), reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), C, P);
+    else
+      lgu::pack_fmaps_vec_kernel<float><<<vgrid, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float*>(fmaps), reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), C, P);
+    return lgu::check_launch("lgu_pack_fmaps");
+  }
   const dim3 grid((P + 31) / 32, (C + 31) / 32, T);
   if (src_is_half)
     lgu::pack_fmaps_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(
