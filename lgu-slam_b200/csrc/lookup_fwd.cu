@@ -163,6 +163,40 @@ lookup_fwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
   }
 }
 
+// Plain lookup with r = 1 (the uncertainty-mask lookup, corr.py:94): only 9 taps, so warp-per-pixel leaves 23 lanes
+// idle.  One THREAD per pixel instead: its 4 x 4 footprint is loaded once (16 bounds-checked loads, zero outside),
+// the 9 taps are blended from registers, and consecutive threads store consecutive pixels of each tap plane
+// (coalesced).  Index logic as corrSample_kernel.cu:52-77 (top-left gating, Q3).
+__global__ void __launch_bounds__(128)
+lookup_fwd_r1_kernel(const float* __restrict__ volume, const float* __restrict__ coords, float* __restrict__ corr,
+                     int P, int H2, int W2, long long npix) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int n = (int)(pix / P), p = (int)(pix - (long long)n * P);
+  const float x0 = __ldg(coords + (size_t)n * 2 * P + p), y0 = __ldg(coords + (size_t)n * 2 * P + P + p);
+  const float dx = __fsub_rn(x0, floorf(x0)), dy = __fsub_rn(y0, floorf(y0));
+  const int fx = floor_to_int(x0), fy = floor_to_int(y0);
+  const float* V = volume + (size_t)pix * H2 * W2;
+  int xs[4], ys[4];
+  xs[0] = tap_coord(fx, 1, 0); ys[0] = tap_coord(fy, 1, 0);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) { xs[k] = wrap_inc(xs[k - 1]); ys[k] = wrap_inc(ys[k - 1]); }
+  float q[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      q[a][b] = in_bounds(ys[a], xs[b], H2, W2) ? __ldg(V + (size_t)ys[a] * W2 + xs[b]) : 0.0f;
+  float* out = corr + (size_t)n * 9 * P + p;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)          // x tap
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {      // y tap
+      const bool gate = in_bounds(ys[j], xs[i], H2, W2);      // out-of-bounds x2 / y2 corners already read as 0
+      out[(size_t)(i * 3 + j) * P] = gate ? blend4(q[j][i], q[j][i + 1], q[j + 1][i], q[j + 1][i + 1], dx, dy) : 0.0f;
+    }
+}
+
 // Any radius (slow path, rarely used): same mapping, direct strided stores.
 template <bool DEFORM>
 __global__ void __launch_bounds__(kLkThreads)
@@ -198,7 +232,14 @@ static int launch_lookup_fwd(const float* volume, const float* coords, float* of
   LGU_REQUIRE(nblk < 2147483647LL, "lookup forward: E*ceil(H1*W1/32) = %lld exceeds the grid limit", nblk);
   const dim3 grid((unsigned)nblk), block(kLkThreads);
   switch (r) {
-    case 1: lookup_fwd_kernel<1, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
+    case 1:
+      if (!DEFORM) {
+        const long long npix = (long long)E * P;
+        lookup_fwd_r1_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(volume, coords, corr, P, H2, W2, npix);
+        break;
+      }
+      lookup_fwd_kernel<1, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
+      break;
     case 2: lookup_fwd_kernel<2, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
     case 3: {
       const char* ex = getenv("LGU_EXP");
