@@ -223,6 +223,62 @@ class Workload:
         return h2d, d2h
 
 
+# ------------------------------------------------------------------------------------------------ reference CUDA, for information
+def time_ref_cuda(wl, iters=3):
+    """The same step on the reference's OWN kernels recompiled unmodified for sm_100 (oracle/_ref, built in the dev
+    container from /root/reference/offersample_LGS) + the torch glue the reference uses (corr.py:61-109).  Reported
+    under "ref_cuda" beside our numbers; never part of the product path or of `value`."""
+    import torch
+    from oracle import build_ref
+    ref = build_ref.load_ref("defCorrSample_ref")
+    if ref is None:
+        return None
+    d, E = wl.d, wl.E
+    f = d["fmaps"].float()
+
+    def step():
+        f1 = f[d["ii"].long()].reshape(E, C, P) / 4
+        f2 = f[d["jj"].long()].reshape(E, C, P) / 4
+        v = torch.matmul(f1.transpose(1, 2), f2).view(E, H, W, H, W)
+        v1, = ref.gaussianMask(d["means"], d["covs"], v, GR)
+        cur = (v1 / d["den"].view(E, H, W, 1, 1) + v).reshape(E * P, 1, H, W)
+        pyr = []
+        for i in range(LEVELS):
+            pyr.append(cur.view(E, H, W, H >> i, W >> i))
+            cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+        c = d["coords"].permute(0, 3, 1, 2).contiguous()
+        cl = [(c / 2 ** l).contiguous() for l in range(LEVELS)]
+        m, = ref.corr_index_forward(pyr[1], cl[1], 1)
+        mask = torch.sigmoid(torch.var(m.permute(0, 3, 4, 1, 2), dim=[3, 4])).view(E, H, W, 1)
+        offs = [d["off0"].clone(), d["off1"] * mask, wl.zero_off, wl.zero_off2]
+        offs = [o.view(E, H, W, 2 * R + 1, 2 * R + 1, 2) for o in offs]
+        outs = [ref.defCorr_index_forward(pyr[l], cl[l], offs[l], R)[0].view(E, TAPS, H, W) for l in range(LEVELS)]
+        corr = torch.cat(outs, dim=1)
+        gl = d["corr_grad"].view(E, LEVELS, 2 * R + 1, 2 * R + 1, H, W)
+        grads = [ref.defCorr_index_backward(pyr[l], cl[l], offs[l], gl[:, l].contiguous(), R) for l in range(LEVELS)]
+        gmask, = ref.corr_index_backward(pyr[1], cl[1], wl.g_mask, 1)
+        gm, gc = ref.gaussianMask_backward(d["means"], d["covs"], wl.v_raw, wl.g_vol, GR)
+        return corr, grads, gmask, gm, gc
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": E / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms,
+            "what": "reference offersample_LGS kernels recompiled unmodified for sm_100 + the reference's torch glue "
+                    "(fp32 matmul, no TF32), same tensors, same GPU, 1 rank"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_step(orc, host, E_cpu):
     """The same step on the CPU oracle for the first E_cpu edges (bounded sample)."""
@@ -409,11 +465,19 @@ def main():
         except Exception as ex:            # the oracle is test infrastructure; never let it break the product number
             cpu = {"value": None, "unit": "edges/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
+    ref_cuda = None
+    if not a.no_ref_cuda:
+        try:
+            ref_cuda = time_ref_cuda(wl)
+        except Exception as ex:            # informational only
+            ref_cuda = {"value": None, "what": f"failed: {ex}"}
+
     line = {"metric": metric, "value": value, "unit": "edges/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config, "clocks": sampler.result(),
             "e2e": {"value": e2e_val, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": wl.launches_per_step * a.steps, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": wl.launches_per_step * a.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "ref_cuda": ref_cuda}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
