@@ -109,6 +109,65 @@ class FusedCorrLookup(torch.autograd.Function):
         return gv0, gv1, gv2, gv3, None, g0.view_as(off0), g1.view_as(off1_out)
 
 
+class FusedBuild(torch.autograd.Function):
+    """CorrBlock.__init__'s data path (corr.py:61-86 + gaussianMask_cuda.py:84-86) as ONE differentiable op.
+    forward  : pack + one tcgen05/TMA launch -> the 4 pyramid levels (fp32 maps: hi/lo split, three MMAs).
+    backward : exactly what autograd computes for the reference graph
+                 g0     = g_lvl0 + up2(g_lvl1)/4 + up4(g_lvl2)/16 + up8(g_lvl3)/64            (3 x avg_pool2d)
+                 g_V    = g0                                (GaussianMaskCuda returns NO gradient for corr,
+                                                             gaussianMask_cuda.py:23 -- only the `+ corr` branch)
+                 g_mean, g_cov = gaussianMask_backward(mean, cov, V, g0 / den)               (gaussianAttn.cu:72-131)
+                 g_den  = -sum_q g0 * corr1 / den^2,  corr1 = (lvl0 - V) * den  ->  g_det via den = 6.28 sqrt(det)
+                 g_f1   = g_V f2 / 16,   g_f2 = g_V^T f1 / 16                                 (torch.bmm, fp32)
+               The raw volume V is not stored: inside the 9x9 window lvl0 = V (1 + 3 e / den), so V = lvl0 / (1 + w/den)
+               with w = gaussianMask(mean, cov, 1) -- one dense pass instead of a saved 37.75 MB/edge tensor."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, mean, cov, det, autocast_rounding):
+        E, c, h, w = f1.shape
+        frames = torch.cat((f1, f2), dim=0).contiguous()
+        hi, lo = ops.pack_fmaps(frames, split=frames.dtype == torch.float32)
+        idx = torch.arange(2 * E, dtype=torch.int32, device=frames.device)
+        den = (6.28 * torch.sqrt(det)).view(E, h, w).float().contiguous()
+        mean_c, cov_c = mean.float().contiguous(), cov.float().contiguous()
+        pyr = ops.build_pyramid(hi, lo, idx[:E].contiguous(), idx[E:].contiguous(), h, w, means=mean_c, covs=cov_c, den=den,
+                                num_levels=4, gauss_radius=GAUSS_RADIUS, round_half=bool(autocast_rounding))
+        ctx.save_for_backward(f1, f2, mean_c, cov_c, det, den, pyr[0])
+        return tuple(pyr)
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, g3):
+        f1, f2, mean, cov, det, den, lvl0 = ctx.saved_tensors
+        E, c, h, w = f1.shape
+        P = h * w
+
+        def up(g, k):                                    # avg_pool2d^T: nearest upsampling of the target axes
+            return g.repeat_interleave(k, dim=3).repeat_interleave(k, dim=4)
+
+        g = torch.zeros_like(lvl0) if g0 is None else g0.clone()
+        for gl, k in ((g1, 2), (g2, 4), (g3, 8)):
+            if gl is not None:
+                g += up(gl, k) / float(k * k)
+        ones = torch.ones(1, device=g.device).expand_as(lvl0)
+        wgt, = ops.gaussianMask(mean, cov, ones.contiguous(), GAUSS_RADIUS)           # 3 e inside the window, 0 outside
+        dn = den.view(E, h, w, 1, 1)
+        V = lvl0 / (1.0 + wgt / dn)
+        g_mean, g_cov = ops.gaussianMask_backward(mean, cov, V.contiguous(), (g / dn).contiguous(), GAUSS_RADIUS)
+        g_den = -(g * (lvl0 - V)).sum(dim=(3, 4)) / den                               # corr1 / den^2 = (lvl0 - V) / den
+        g_det = (g_den * (0.5 * 6.28) / torch.sqrt(det).view(E, h, w)).view_as(det)
+        gm = g.view(E, P, P)
+        a1 = f1.reshape(E, c, P).float()
+        a2 = f2.reshape(E, c, P).float()
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            g_f1 = torch.bmm(a2, gm.transpose(1, 2)) / 16.0                          # [E,c,P1]
+            g_f2 = torch.bmm(a1, gm) / 16.0                                          # [E,c,P2]
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return (g_f1.view_as(f1).to(f1.dtype), g_f2.view_as(f2).to(f2.dtype), g_mean, g_cov, g_det, None)
+
+
 def per_Corr_Normalization(x, normalIndex, eps=1e-5):
     """corr.py:44-51 / gaussianMask_cuda.py:26-33: standardise over `normalIndex` (biased variance + eps)."""
     mean = torch.mean(x, dim=normalIndex, keepdim=True)
@@ -178,8 +237,9 @@ def _generate_offsets(ofsMap, ofs_residual, t):
 # ------------------------------------------------------------------------------------------------
 class CorrBlock:
     """corr.py:53-152.  Attributes kept: corr_pyramid (list of [E,h,w,h>>l,w>>l]), offset (list of [E,h,w,98]),
-    mean_n, theta, num_levels, radius.  `fused=None` picks the fused build whenever no gradient can flow into it
-    (inference: torch.no_grad, as FactorGraph / MotionFilter run) and the per-op autograd path otherwise."""
+    mean_n, theta, num_levels, radius.  `fused=None` picks the fused build (one tcgen05 launch, differentiable through
+    FusedBuild) whenever the shape is supported (w = 64, h % 8 = 0, C = 128, 4 levels); `fused=False` is the
+    reference's per-operator graph (matmul -> GaussianMaskCuda -> / den + corr -> 3 x avg_pool2d)."""
 
     def __init__(self, ofsMap, ofs_residual, GA, fmap1, fmap2, num_levels=4, radius=3, fused=None,
                  autocast_rounding=None, fused_lookup=True):
@@ -194,7 +254,7 @@ class CorrBlock:
         needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad or any(
             p.requires_grad for p in GA.parameters()))
         if fused is None:
-            fused = not needs_grad and w == 64 and h % 8 == 0 and c == 128
+            fused = w == 64 and h % 8 == 0 and c == 128 and num_levels == 4
         # under autocast the reference's matmul emits fp16 (factor_graph.py:90, corr.py:64); reproduce on request
         if autocast_rounding is None:
             autocast_rounding = False
@@ -204,16 +264,10 @@ class CorrBlock:
         self.t = t.permute(0, 2, 3, 1).contiguous()
 
         if fused:
+            # one tcgen05/TMA launch; differentiable (FusedBuild) when gradients are needed
             mean, cov, det = GA.params(self.t.float())
-            frames = torch.cat((fmap1.reshape(E, c, h, w), fmap2.reshape(E, c, h, w)), dim=0).contiguous()
-            split = frames.dtype == torch.float32
-            hi, lo = ops.pack_fmaps(frames, split=split)
-            idx = torch.arange(2 * E, dtype=torch.int32, device=frames.device)
-            den = (6.28 * torch.sqrt(det)).view(E, h, w).float().contiguous()
-            self.corr_pyramid = ops.build_pyramid(hi, lo, idx[:E].contiguous(), idx[E:].contiguous(), h, w,
-                                                  means=mean.float().contiguous(), covs=cov.contiguous(), den=den,
-                                                  num_levels=num_levels, gauss_radius=GAUSS_RADIUS,
-                                                  round_half=autocast_rounding)
+            self.corr_pyramid = list(FusedBuild.apply(fmap1.reshape(E, c, h, w), fmap2.reshape(E, c, h, w), mean, cov,
+                                                      det, autocast_rounding))
         else:
             corr = CorrBlock.corr(fmap1, fmap2).view(E, h, w, h, w).float()
             corr, mean, det = GA(self.t.float(), corr)

@@ -221,8 +221,9 @@ def test_pooled_corrblock_matches_corrblock_through_add_and_remove():
 
 def test_training_clip_fused_lookup_equals_per_op_autograd():
     """BASELINE configs[2] in miniature (train.py step shape: a clip's edges, several lookup iterations, one backward,
-    droid_net.py:187-222): the same CorrBlock with the fused differentiable lookup and with the reference's per-operator
-    autograd graph gives the same outputs and the same gradients on feature maps, offset heads and Gaussian head."""
+    droid_net.py:187-222): the same CorrBlock with the fused differentiable build + lookup (2 + 2 launches per
+    iteration pair) and with the reference's per-operator autograd graph gives the same outputs and the same gradients
+    on feature maps, offset heads and Gaussian head."""
     dev = "cuda"
     g = inputs.gen(14)
     b, n, steps = 2, 5, 3
@@ -239,7 +240,9 @@ def test_training_clip_fused_lookup_equals_per_op_autograd():
         for fused_lookup in (True, False):
             corr, ofsMap, ofs_residual, GA = _modules(dev, 6)
             f1, f2 = fm1.clone().requires_grad_(), fm2.clone().requires_grad_()
-            blk = corr.CorrBlock(ofsMap, ofs_residual, GA, f1, f2, fused_lookup=fused_lookup)
+            # fused: differentiable tcgen05 build (FusedBuild) + differentiable fused lookup; else the reference's graph
+            blk = corr.CorrBlock(ofsMap, ofs_residual, GA, f1, f2, fused=fused_lookup, fused_lookup=fused_lookup)
+            assert ("FusedBuild" in type(blk.corr_pyramid[0].grad_fn).__name__) == fused_lookup
             loss = 0.0
             outs = []
             for c, w in zip(coords, wts):
