@@ -455,7 +455,11 @@ class AltCorrBlock:
 
     MAX_EDGES_PER_PASS = 256          # scratch bound: 256 x 50 MB = 12.8 GB
 
-    def __init__(self, ofsMap, ofs_residual, GA, fmaps, num_levels=4, radius=3, strict_ref=True, materialize=None):
+    def __init__(self, ofsMap, ofs_residual, GA, fmaps, num_levels=4, radius=3, strict_ref=True, materialize=None,
+                 sampler_ops=None):
+        # sampler_ops: object with altcorr_forward / lowMem_defSample (default: this package's operators); benchmarks
+        # pass the reference's compiled extension here to time its kernels inside the same Python glue
+        self.sampler_ops = sampler_ops if sampler_ops is not None else ops
         self.num_levels = num_levels
         self.radius = radius
         self.GA = GA
@@ -548,11 +552,14 @@ class AltCorrBlock:
             f2_i = f2_i.reshape((B * N,) + f2_i.shape[2:]).float().contiguous()
             coords_i = (coords / 2 ** i).reshape(B * N, S, H, W, 2).contiguous()
             if i == 1:
-                m, = ops.altcorr_forward(f1, f2_i, coords_i, MASK_RADIUS)
+                m, = self.sampler_ops.altcorr_forward(f1, f2_i, coords_i, MASK_RADIUS)
                 m = m.permute(0, 1, 3, 4, 2).contiguous().view(N, H, W, 3, 3)       # corr.py:203 (assumes B == S == 1)
                 self.offset[1] = self.offset[1] * torch.sigmoid(torch.var(m, dim=[3, 4])).view(B * N, H, W, 1)
             o = self.offset[i].contiguous().view(B * N, H, W, rd, rd, 2).float()
-            corr, = ops.lowMem_defSample(f1, f2_i, coords_i, o, self.radius, strict_ref=self.strict_ref)
+            if self.sampler_ops is ops:
+                corr, = ops.lowMem_defSample(f1, f2_i, coords_i, o, self.radius, strict_ref=self.strict_ref)
+            else:
+                corr, = self.sampler_ops.lowMem_defSample(f1, f2_i, coords_i, o, self.radius)
             out.append(corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2))
         return torch.cat(out, dim=2)
 
