@@ -133,3 +133,15 @@ def test_build_unsupported_shape_is_reported(ops):
     ii = torch.zeros(1, dtype=torch.int32, device="cuda")
     with pytest.raises(RuntimeError, match="W=64"):
         ops.build_pyramid(hi, None, ii, ii, 32, 32, gauss_radius=0)
+
+
+@pytest.mark.parametrize("H", [32, 8, 64])
+def test_build_other_grid_heights(ops, oracle, H):
+    """W = 64 is fixed by the tile shape, the height is free (H % 8 == 0): 32 / 8 / 64 rows against the oracle."""
+    c = inputs.frontend_case(E=2, T=3, H=H, W=64, seed=40 + H, half_fmaps=True)
+    got = _run(ops, oracle, c, precision=1, gauss=True)
+    want = _oracle_pyramid(oracle, c, True)
+    for l, (g_, w_) in enumerate(zip(got, want)):
+        assert g_.shape == w_.shape
+        err = (g_.cpu() - w_).abs().max().item()
+        assert err <= ATOL, f"H={H} level {l}: max abs err {err}"
