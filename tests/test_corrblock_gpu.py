@@ -268,3 +268,23 @@ def test_training_clip_fused_lookup_equals_per_op_autograd():
         report.append(f"{name}: max err {err:.3e}, rms {rms:.3e}")
         assert err <= 2e-2 * rms + 1e-12, "; ".join(report)
     print("\n".join(report))
+
+
+def test_pool_build_writes_only_its_slots():
+    """Canary test (compute-sanitizer is closed on this pool): the slot-indirected build writes exactly the slots it was
+    given -- every other slot of the pool keeps its NaN sentinel bit pattern, and the written slots hold no sentinel."""
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 7)
+    g = inputs.gen(15)
+    pool = corr.CorrPool(5, 48, 64, dev)
+    for t in pool.levels:
+        t.fill_(float("nan"))
+    pool.free = [4, 2, 0, 3, 1]                       # alloc() pops from the end: the block gets slots 1 and 3
+    f1 = torch.randn(1, 2, 128, 48, 64, generator=g).half().to(dev)
+    f2 = torch.randn(1, 2, 128, 48, 64, generator=g).half().to(dev)
+    with torch.no_grad():
+        blk = corr.PooledCorrBlock(pool, ofsMap, ofs_residual, GA, f1, f2)
+    assert sorted(blk.slots) == [1, 3]
+    for l, t in enumerate(pool.levels):
+        assert torch.isnan(t[[0, 2, 4]]).all(), f"level {l}: a slot outside the block was written"
+        assert torch.isfinite(t[[1, 3]]).all(), f"level {l}: a slot of the block was not fully written"
