@@ -177,6 +177,31 @@ LGU_API int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lvl1,
                                    float* off0_grad, float* off1_grad,
                                    int E, int H, int W, int num_levels, int radius, void* stream);
 
+/* Same backward for a training clip, where ONE pyramid is looked up num_steps times (droid_net.py:187-222,
+ * train.py:203): gv0..gv3 are PERSISTENT accumulators (zeroed once by the caller) and this launch ADDS its
+ * gradient into them -- only the <= 20x16 / 12x8 footprint of every pixel is touched (16-byte L2 reductions),
+ * no dense zero-fill per call and no dense autograd sum afterwards (the reference's graph moves
+ * 4 x 50 MB/edge per lookup for that: zeros_like in defCorrSample_kernel.cu:206 + AccumulateGrad).
+ * Every other argument as above. */
+LGU_API int lgu_corr_lookup_fused_backward_accumulate(const float* lvl0, const float* lvl1, const float* coords,
+                                   const float* off0, const float* off1_out, const float* mask,
+                                   const float* corr_grad, const float* off1_out_grad,
+                                   float* gv0, float* gv1, float* gv2, float* gv3,
+                                   float* off0_grad, float* off1_grad,
+                                   int E, int H, int W, int num_levels, int radius, void* stream);
+
+/* Gaussian-head part of the backward of lgu_build_pyramid (what autograd runs for gaussianMask_cuda.py:84-86
+ * followed by 3 x avg_pool2d, corr.py:83-86), straight from the four LEVEL gradients, without a dense pass:
+ *   g(q)      = g0[q] + g1[q/2]/4 + g2[q/4]/16 + g3[q/8]/64          (avg_pool2d^T, evaluated at the window taps only)
+ *   V(q)      = lvl0[q] / (1 + 3 e(q) / den)                         (the raw volume, recovered inside the window)
+ *   means_grad, covs_grad = gaussianMask_backward(means, covs, V, g / den)    (gaussianAttn.cu:72-131)
+ *   den_grad  = - sum_window g (lvl0 - V) / den                      (the 1/den of gaussianMask_cuda.py:85-86)
+ * means, covs [E,H,W,2]; den, den_grad [E,H,W]; lvl0, g0 [E,H,W,H,W]; g_l [E,H,W,H>>l,W>>l] (any g_l may be NULL). */
+LGU_API int lgu_build_backward_gauss(const float* means, const float* covs, const float* den, const float* lvl0,
+                                   const float* g0, const float* g1, const float* g2, const float* g3,
+                                   float* means_grad, float* covs_grad, float* den_grad,
+                                   int E, int H, int W, int radius, void* stream);
+
 /* Edge-slot pool variants (replace the whole-pyramid copies of CorrBlock.cat / CorrBlock.__getitem__,
  * corr.py:111-115,137-141, which the frontend pays on every keyframe: factor_graph.py:123,158).  The pyramid levels
  * and the offsets live in storage of `num_slots` edge slots ([num_slots,H,W,H>>l,W>>l], [num_slots,H,W,7,7,2]);

@@ -86,17 +86,47 @@ class GaussianMaskCuda(torch.autograd.Function):
         return gm, gc, None, None
 
 
+class LevelGradAccumulator:
+    """Persistent gradient buffers of one pyramid for a training clip (droid_net.py:187-222 looks the same CorrBlock up
+    `num_steps` times).  The reference's graph allocates, zero-fills and writes a dense 50 MB/edge gradient per lookup
+    (defCorrSample_kernel.cu:206) and AccumulateGrad then sums them; here every lookup's backward ADDS its footprints
+    into these four buffers (lgu_corr_lookup_fused_backward_accumulate) and FusedBuild.backward consumes them once.
+    `levels` are the FusedBuild outputs the buffers belong to (identity-checked by the lookup)."""
+
+    def __init__(self):
+        self.levels = None
+        self.grads = None
+
+    def owns(self, pyramid):
+        return self.levels is not None and all(a is b for a, b in zip(self.levels, pyramid))
+
+    def buffers(self):
+        if self.grads is None:
+            self.grads = [torch.zeros_like(t) for t in self.levels]
+        return self.grads
+
+    def take(self):
+        g, self.grads = self.grads, None
+        return g
+
+
 class FusedCorrLookup(torch.autograd.Function):
     """CorrBlock.__call__'s whole data path (corr.py:88-109) as ONE differentiable op: forward = one TMA-staged
     launch, backward = one launch (lgu_corr_lookup_fused_backward).  Inputs: the 4 pyramid levels, coords [E,H,W,2],
     off0, off1 [E,H,W,98].  Outputs: corr [E,196,H,W] and the post-mask offsets offset[1]*mask (which the block
-    keeps for its next call, quirk Q7).  Gradients: pyramid levels, off0, off1; none for coords (corr.py:42)."""
+    keeps for its next call, quirk Q7).  Gradients: pyramid levels, off0, off1; none for coords (corr.py:42).
+    With an accumulator (`acc`, the pyramid's LevelGradAccumulator) the level gradients are added into its persistent
+    buffers instead of being returned; `token` (an output of the same FusedBuild) carries a defined zero gradient back
+    so that FusedBuild.backward runs after every lookup of the clip and picks the buffers up."""
 
     @staticmethod
-    def forward(ctx, lvl0, lvl1, lvl2, lvl3, coords, off0, off1):
+    def forward(ctx, lvl0, lvl1, lvl2, lvl3, coords, off0, off1, *extra):
+        token, acc = (tuple(extra) + (None, None))[:2]
+        ctx.n_extra = len(extra)
         off1_out = off1.detach().clone()                    # the kernel updates offset[1] in place
         corr, mask = ops.corr_lookup_fused([lvl0, lvl1, lvl2, lvl3], coords, off0, off1_out, 3, return_mask=True)
         ctx.save_for_backward(lvl0, lvl1, lvl2, lvl3, coords, off0, off1_out, mask)
+        ctx.acc = acc if (acc is not None and token is not None and acc.owns((lvl0, lvl1, lvl2, lvl3))) else None
         ctx.mark_non_differentiable(mask)
         return corr, off1_out, mask
 
@@ -104,26 +134,34 @@ class FusedCorrLookup(torch.autograd.Function):
     def backward(ctx, g_corr, g_off1_out, _g_mask):
         lvl0, lvl1, lvl2, lvl3, coords, off0, off1_out, mask = ctx.saved_tensors
         up = g_off1_out.contiguous() if g_off1_out is not None else None
+        if ctx.acc is not None:
+            _, _, _, _, g0, g1 = ops.corr_lookup_fused_backward([lvl0, lvl1, lvl2, lvl3], coords, off0, off1_out, mask,
+                                                                g_corr.contiguous(), up,
+                                                                accumulate_into=ctx.acc.buffers())
+            return (None, None, None, None, None, g0.view_as(off0), g1.view_as(off1_out), g0.new_zeros(1), None)
         gv0, gv1, gv2, gv3, g0, g1 = ops.corr_lookup_fused_backward([lvl0, lvl1, lvl2, lvl3], coords, off0, off1_out,
                                                                     mask, g_corr.contiguous(), up)
-        return gv0, gv1, gv2, gv3, None, g0.view_as(off0), g1.view_as(off1_out)
+        return (gv0, gv1, gv2, gv3, None, g0.view_as(off0), g1.view_as(off1_out)) + (None,) * ctx.n_extra
 
 
 class FusedBuild(torch.autograd.Function):
     """CorrBlock.__init__'s data path (corr.py:61-86 + gaussianMask_cuda.py:84-86) as ONE differentiable op.
-    forward  : pack + one tcgen05/TMA launch -> the 4 pyramid levels (fp32 maps: hi/lo split, three MMAs).
-    backward : exactly what autograd computes for the reference graph
-                 g0     = g_lvl0 + up2(g_lvl1)/4 + up4(g_lvl2)/16 + up8(g_lvl3)/64            (3 x avg_pool2d)
-                 g_V    = g0                                (GaussianMaskCuda returns NO gradient for corr,
+    forward  : pack + one tcgen05/TMA launch -> the 4 pyramid levels (fp32 maps: hi/lo split, three MMAs) and a
+               1-element ordering token (see FusedCorrLookup).
+    backward : exactly what autograd computes for the reference graph, evaluated LEVEL-WISE (no dense merge pass):
+                 g      = g_lvl0 + up2(g_lvl1)/4 + up4(g_lvl2)/16 + up8(g_lvl3)/64              (3 x avg_pool2d)
+                 g_V    = g                                 (GaussianMaskCuda returns NO gradient for corr,
                                                              gaussianMask_cuda.py:23 -- only the `+ corr` branch)
-                 g_mean, g_cov = gaussianMask_backward(mean, cov, V, g0 / den)               (gaussianAttn.cu:72-131)
-                 g_den  = -sum_q g0 * corr1 / den^2,  corr1 = (lvl0 - V) * den  ->  g_det via den = 6.28 sqrt(det)
-                 g_f1   = g_V f2 / 16,   g_f2 = g_V^T f1 / 16                                 (torch.bmm, fp32)
-               The raw volume V is not stored: inside the 9x9 window lvl0 = V (1 + 3 e / den), so V = lvl0 / (1 + w/den)
-               with w = gaussianMask(mean, cov, 1) -- one dense pass instead of a saved 37.75 MB/edge tensor."""
+                 g_mean, g_cov = gaussianMask_backward(mean, cov, V, g / den)                  (gaussianAttn.cu:72-131)
+                 g_den  = -sum_q g * corr1 / den^2,  corr1 = (lvl0 - V) * den  ->  g_det via den = 6.28 sqrt(det)
+                   -- one launch over the 9x9 windows (lgu_build_backward_gauss); the raw volume V is not stored:
+                   inside the window lvl0 = V (1 + 3 e / den)
+                 g_f1   = g_V f2 / 16        = sum_l g_lvl_l  avgpool_l(f2) / 16               (pooling commutes with
+                 g_f2   = g_V^T f1 / 16      = sum_l up_l(g_lvl_l^T f1) / (16 * 4^l)            the contraction)
+               The level gradients are the accumulator's buffers (training clip) plus whatever autograd delivers."""
 
     @staticmethod
-    def forward(ctx, f1, f2, mean, cov, det, autocast_rounding):
+    def forward(ctx, f1, f2, mean, cov, det, autocast_rounding, acc=None):
         E, c, h, w = f1.shape
         frames = torch.cat((f1, f2), dim=0).contiguous()
         hi, lo = ops.pack_fmaps(frames, split=frames.dtype == torch.float32)
@@ -133,39 +171,50 @@ class FusedBuild(torch.autograd.Function):
         pyr = ops.build_pyramid(hi, lo, idx[:E].contiguous(), idx[E:].contiguous(), h, w, means=mean_c, covs=cov_c, den=den,
                                 num_levels=4, gauss_radius=GAUSS_RADIUS, round_half=bool(autocast_rounding))
         ctx.save_for_backward(f1, f2, mean_c, cov_c, det, den, pyr[0])
-        return tuple(pyr)
+        ctx.acc = acc
+        ctx.set_materialize_grads(False)
+        token = pyr[0].new_zeros(1)
+        return tuple(pyr) + (token,)
 
     @staticmethod
-    def backward(ctx, g0, g1, g2, g3):
+    def backward(ctx, g0, g1, g2, g3, _g_token=None):
         f1, f2, mean, cov, det, den, lvl0 = ctx.saved_tensors
         E, c, h, w = f1.shape
         P = h * w
-
-        def up(g, k):                                    # avg_pool2d^T: nearest upsampling of the target axes
-            return g.repeat_interleave(k, dim=3).repeat_interleave(k, dim=4)
-
-        g = torch.zeros_like(lvl0) if g0 is None else g0.clone()
-        for gl, k in ((g1, 2), (g2, 4), (g3, 8)):
-            if gl is not None:
-                g += up(gl, k) / float(k * k)
-        ones = torch.ones(1, device=g.device).expand_as(lvl0)
-        wgt, = ops.gaussianMask(mean, cov, ones.contiguous(), GAUSS_RADIUS)           # 3 e inside the window, 0 outside
-        dn = den.view(E, h, w, 1, 1)
-        V = lvl0 / (1.0 + wgt / dn)
-        g_mean, g_cov = ops.gaussianMask_backward(mean, cov, V.contiguous(), (g / dn).contiguous(), GAUSS_RADIUS)
-        g_den = -(g * (lvl0 - V)).sum(dim=(3, 4)) / den                               # corr1 / den^2 = (lvl0 - V) / den
+        grads = [g0, g1, g2, g3]
+        held = ctx.acc.take() if ctx.acc is not None else None
+        if held is not None:
+            grads = [a if g is None else a.add_(g) for a, g in zip(held, grads)]
+        grads = [None if g is None else g.float().contiguous() for g in grads]
+        if all(g is None for g in grads):
+            return (None,) * 7
+        g_mean, g_cov, g_den = ops.build_backward_gauss(mean, cov, den, lvl0, grads, GAUSS_RADIUS)
         g_det = (g_den * (0.5 * 6.28) / torch.sqrt(det).view(E, h, w)).view_as(det)
-        gm = g.view(E, P, P)
         a1 = f1.reshape(E, c, P).float()
-        a2 = f2.reshape(E, c, P).float()
+        g_f1 = torch.zeros(E, P, c, dtype=torch.float32, device=f1.device)
+        g_f2 = torch.zeros(E, c, h, w, dtype=torch.float32, device=f1.device)
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
-            g_f1 = torch.bmm(a2, gm.transpose(1, 2)) / 16.0                          # [E,c,P1]
-            g_f2 = torch.bmm(a1, gm) / 16.0                                          # [E,c,P2]
+            f2l = f2.float()
+            for l, g in enumerate(grads):
+                if l > 0:
+                    f2l = F.avg_pool2d(f2l, 2, stride=2)
+                if g is None:
+                    continue
+                Q = (h >> l) * (w >> l)
+                gm = g.view(E, P, Q)
+                g_f1.baddbmm_(gm, f2l.reshape(E, c, Q).transpose(1, 2))               # [E,P1,c]
+                t = torch.bmm(a1, gm).view(E, c, h >> l, w >> l)                      # [E,c,Q_l]
+                if l > 0:
+                    k = 1 << l
+                    t = (t / float(k * k)).repeat_interleave(k, dim=2).repeat_interleave(k, dim=3)
+                g_f2 += t
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
-        return (g_f1.view_as(f1).to(f1.dtype), g_f2.view_as(f2).to(f2.dtype), g_mean, g_cov, g_det, None)
+        g_f1 = (g_f1 / 16.0).transpose(1, 2).reshape(f1.shape)
+        g_f2 = g_f2 / 16.0
+        return (g_f1.to(f1.dtype), g_f2.view_as(f2).to(f2.dtype), g_mean, g_cov, g_det, None, None)
 
 
 def per_Corr_Normalization(x, normalIndex, eps=1e-5):
@@ -242,8 +291,9 @@ class CorrBlock:
     reference's per-operator graph (matmul -> GaussianMaskCuda -> / den + corr -> 3 x avg_pool2d)."""
 
     def __init__(self, ofsMap, ofs_residual, GA, fmap1, fmap2, num_levels=4, radius=3, fused=None,
-                 autocast_rounding=None, fused_lookup=True):
+                 autocast_rounding=None, fused_lookup=True, accumulate_grads=True):
         self.fused_lookup = fused_lookup
+        self._gacc = self._token = None
         self.num_levels = num_levels
         self.radius = radius
         self.GA = GA
@@ -266,8 +316,12 @@ class CorrBlock:
         if fused:
             # one tcgen05/TMA launch; differentiable (FusedBuild) when gradients are needed
             mean, cov, det = GA.params(self.t.float())
-            self.corr_pyramid = list(FusedBuild.apply(fmap1.reshape(E, c, h, w), fmap2.reshape(E, c, h, w), mean, cov,
-                                                      det, autocast_rounding))
+            self._gacc = LevelGradAccumulator() if (needs_grad and accumulate_grads) else None
+            *pyr, self._token = FusedBuild.apply(fmap1.reshape(E, c, h, w), fmap2.reshape(E, c, h, w), mean, cov, det,
+                                                 autocast_rounding, self._gacc)
+            self.corr_pyramid = list(pyr)
+            if self._gacc is not None:
+                self._gacc.levels = tuple(pyr)
         else:
             corr = CorrBlock.corr(fmap1, fmap2).view(E, h, w, h, w).float()
             corr, mean, det = GA(self.t.float(), corr)
@@ -298,8 +352,9 @@ class CorrBlock:
             pyr = [t if t.is_contiguous() else t.contiguous() for t in self.corr_pyramid]
             c = coords.detach().reshape(E, ht, wd, 2).float().contiguous()
             if self._needs_grad(coords):                     # training: differentiable fused op (1 + 1 launches)
+                # (with the fused build, level gradients accumulate in self._gacc's persistent buffers)
                 out, self.offset[1], _ = FusedCorrLookup.apply(pyr[0], pyr[1], pyr[2], pyr[3], c, self.offset[0],
-                                                               self.offset[1])
+                                                               self.offset[1], self._token, self._gacc)
             else:                                            # inference: offset[1] updated in place
                 out = ops.corr_lookup_fused(pyr, c, self.offset[0], self.offset[1], self.radius)
             return out.view(batch, num, -1, ht, wd), self.mean_n, self.theta

@@ -143,6 +143,67 @@ gaussian_bwd_kernel(const float* __restrict__ means, const float* __restrict__ c
   }
 }
 
+// Gaussian-head gradients of the fused build, from the four level gradients (see lgu_build_backward_gauss in
+// include/lgu_corr.h).  Same tap arithmetic as gaussian_bwd_kernel; the merged upstream gradient and the raw volume
+// are formed per tap from lvl0 and the level gradients (5 gathers per tap instead of two dense passes per edge).
+__global__ void __launch_bounds__(kGaWarps * 32)
+build_bwd_gauss_kernel(const float* __restrict__ means, const float* __restrict__ covs, const float* __restrict__ den,
+                       const float* __restrict__ lvl0, const float* __restrict__ g0, const float* __restrict__ g1,
+                       const float* __restrict__ g2, const float* __restrict__ g3, float* __restrict__ means_grad,
+                       float* __restrict__ covs_grad, float* __restrict__ den_grad, long long npix, int H2, int W2,
+                       int r) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int Q = H2 * W2;
+  const int rd = 2 * r + 1, taps = rd * rd;
+  for (long long pix = wid; pix < npix; pix += nwarps) {
+    const float2 m = __ldg(reinterpret_cast<const float2*>(means) + pix);
+    const float2 c = __ldg(reinterpret_cast<const float2*>(covs) + pix);
+    const float dn = __ldg(den + pix);
+    const int cx = floor_to_int(m.x), cy = floor_to_int(m.y);
+    const float* L0 = lvl0 + (size_t)pix * Q;
+    const float* G0 = g0 != nullptr ? g0 + (size_t)pix * Q : nullptr;
+    const float* G1 = g1 != nullptr ? g1 + (size_t)pix * (Q >> 2) : nullptr;
+    const float* G2 = g2 != nullptr ? g2 + (size_t)pix * (Q >> 4) : nullptr;
+    const float* G3 = g3 != nullptr ? g3 + (size_t)pix * (Q >> 6) : nullptr;
+    const float rcx = __fdiv_rn(1.0f, c.x), rcy = __fdiv_rn(1.0f, c.y);
+    const double rccx = 1.0 / (double)__fmul_rn(c.x, c.x), rccy = 1.0 / (double)__fmul_rn(c.y, c.y);
+    float gm0 = 0.0f, gm1 = 0.0f, gc0 = 0.0f, gc1 = 0.0f, gd = 0.0f;
+    for (int t = lane; t < taps; t += 32) {
+      const int j = t / rd, i = t - j * rd;
+      const int x1 = tap_coord(cx, r, i), y1 = tap_coord(cy, r, j);
+      if (!in_bounds(y1, x1, H2, W2)) continue;
+      const float l0 = __ldg(L0 + y1 * W2 + x1);
+      float g = G0 != nullptr ? __ldg(G0 + y1 * W2 + x1) : 0.0f;                 // avg_pool2d^T, level by level
+      if (G1 != nullptr) g = __fadd_rn(g, __fmul_rn(__ldg(G1 + (y1 >> 1) * (W2 >> 1) + (x1 >> 1)), 0.25f));
+      if (G2 != nullptr) g = __fadd_rn(g, __fmul_rn(__ldg(G2 + (y1 >> 2) * (W2 >> 2) + (x1 >> 2)), 0.0625f));
+      if (G3 != nullptr) g = __fadd_rn(g, __fmul_rn(__ldg(G3 + (y1 >> 3) * (W2 >> 3) + (x1 >> 3)), 0.015625f));
+      const float ddx = __fsub_rn((float)x1, m.x), ddy = __fsub_rn((float)y1, m.y);
+      const float t1 = __fmul_rn(ddx, rcx), t2 = __fmul_rn(ddy, rcy);
+      const float s = __fmaf_rn(ddy, t2, __fmul_rn(t1, ddx));
+      const float e = expf(__fmul_rn(s, -0.5f));
+      const float vraw = __fdiv_rn(l0, __fadd_rn(1.0f, __fdiv_rn(__fmul_rn(3.0f, e), dn)));   // lvl0 = V (1 + 3 e / den)
+      const float gq = __fdiv_rn(g, dn);
+      const float v3 = __fmul_rn(vraw, 3.0f);
+      gm0 = __fmaf_rn(__fmul_rn(v3, __fmul_rn(__fmul_rn(ddx, e), rcx)), gq, gm0);
+      gm1 = __fmaf_rn(__fmul_rn(v3, __fmul_rn(__fmul_rn(ddy, e), rcy)), gq, gm1);
+      const double eh = (double)e * 0.5;
+      const float dE1 = (float)(((eh * (double)ddx) * (double)ddx) * rccx);
+      const float dE2 = (float)(((eh * (double)ddy) * (double)ddy) * rccy);
+      gc0 = __fmaf_rn(__fmul_rn(dE1, v3), gq, gc0);
+      gc1 = __fmaf_rn(__fmul_rn(dE2, v3), gq, gc1);
+      gd = __fmaf_rn(g, __fsub_rn(l0, vraw), gd);
+    }
+    gm0 = warp_sum(gm0); gm1 = warp_sum(gm1); gc0 = warp_sum(gc0); gc1 = warp_sum(gc1); gd = warp_sum(gd);
+    if (lane == 0) {
+      reinterpret_cast<float2*>(means_grad)[pix] = make_float2(gm0, gm1);
+      reinterpret_cast<float2*>(covs_grad)[pix] = make_float2(gc0, gc1);
+      den_grad[pix] = -__fdiv_rn(gd, dn);
+    }
+  }
+}
+
 static inline unsigned grid_for_warps(long long nwarps_needed, int warps_per_cta, int ctas_per_sm) {
   long long want = (nwarps_needed + warps_per_cta - 1) / warps_per_cta;
   long long cap = (long long)kNumSMs * ctas_per_sm;
@@ -179,4 +240,21 @@ extern "C" int lgu_gaussian_mask_backward(const float* means, const float* covs,
   lgu::gaussian_bwd_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
       means, covs, volume, volume1_grad, means_grad, covs_grad, npix, H2, W2, radius);
   return lgu::check_launch("lgu_gaussian_mask_backward");
+}
+
+extern "C" int lgu_build_backward_gauss(const float* means, const float* covs, const float* den, const float* lvl0,
+                                        const float* g0, const float* g1, const float* g2, const float* g3,
+                                        float* means_grad, float* covs_grad, float* den_grad, int E, int H, int W,
+                                        int radius, void* stream) {
+  if (E == 0) return LGU_OK;
+  LGU_REQUIRE(means && covs && den && lvl0 && means_grad && covs_grad && den_grad,
+              "lgu_build_backward_gauss: null pointer");
+  LGU_REQUIRE(E >= 0 && H > 0 && W > 0 && radius >= 0 && (H % 8) == 0 && (W % 8) == 0,
+              "lgu_build_backward_gauss: bad sizes E=%d H=%d W=%d r=%d (H, W must be multiples of 8)", E, H, W, radius);
+  LGU_REQUIRE((long long)H * W < (1LL << 30), "lgu_build_backward_gauss: H*W too large");
+  const long long npix = (long long)E * H * W;
+  const unsigned grid = lgu::grid_for_warps(npix, lgu::kGaWarps, 8);
+  lgu::build_bwd_gauss_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
+      means, covs, den, lvl0, g0, g1, g2, g3, means_grad, covs_grad, den_grad, npix, H, W, radius);
+  return lgu::check_launch("lgu_build_backward_gauss");
 }

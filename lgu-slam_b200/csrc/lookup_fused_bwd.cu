@@ -161,6 +161,31 @@ __device__ __forceinline__ void write_slice(float* __restrict__ G, float* acc, i
   }
 }
 
+// Accumulate mode (training, several lookups per pyramid): the gradient buffers persist across launches, so only the
+// accumulator box is touched -- one 16-byte reduction (RED.ADD.F32x4, resolved in L2, nothing returns to the SM) per
+// non-zero box cell that lies inside the slice; the accumulator is re-zeroed on the fly.  The slice is private to this
+// warp within a launch, launches on one stream are ordered, so the result is the sequential sum of the calls.
+template <int BW, int BH>
+__device__ __forceinline__ void add_box(float* __restrict__ G, float* acc, int xb, int yb, int H2, int W2, int lane) {
+  constexpr int C4 = BW / 4, N4 = C4 * BH;
+  const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+  for (int c0 = 0; c0 < N4; c0 += 32) {
+    const int c = c0 + lane;
+    if (c < N4) {
+      const int ry = c / C4, rx = (c - ry * C4) << 2;
+      float4* a = reinterpret_cast<float4*>(acc + ry * BW + rx);
+      const float4 v = *a;
+      *a = z;
+      const int y = yb + ry, x = xb + rx;                        // xb % 4 == 0 and W2 % 4 == 0: all four lanes in or out
+      const bool nz = (v.x != 0.0f) || (v.y != 0.0f) || (v.z != 0.0f) || (v.w != 0.0f);
+      if (nz && (unsigned)y < (unsigned)H2 && (unsigned)x < (unsigned)W2)
+        atomicAdd(reinterpret_cast<float4*>(G + (size_t)y * W2 + x), v);
+    }
+  }
+}
+
+template <bool ACC>
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupBwdParams prm) {
   using namespace flb;
@@ -399,17 +424,24 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
     // ---------------- stream the four dense slices (zeros + box), then the rare out-of-box taps with global atomics
     float* G2 = prm.gv[2] + pix * (size_t)(prm.H2[2] * prm.W2[2]);
     float* G3 = prm.gv[3] + pix * (size_t)(prm.H2[3] * prm.W2[3]);
-    write_slice<kBW01, kBH01>(G0, acc + kOff0, xb0, yb0, prm.H2[0], prm.W2[0], lane);
-    write_slice<kBW01, kBH01>(G1, acc + kOff1, xb1, yb1, prm.H2[1], prm.W2[1], lane);
-    write_slice<kBW23, kBH23>(G2, acc + kOff2, xb2, yb2, prm.H2[2], prm.W2[2], lane);
-    write_slice<kBW23, kBH23>(G3, acc + kOff3, xb3, yb3, prm.H2[3], prm.W2[3], lane);
+    if (ACC) {
+      add_box<kBW01, kBH01>(G0, acc + kOff0, xb0, yb0, prm.H2[0], prm.W2[0], lane);
+      add_box<kBW01, kBH01>(G1, acc + kOff1, xb1, yb1, prm.H2[1], prm.W2[1], lane);
+      add_box<kBW23, kBH23>(G2, acc + kOff2, xb2, yb2, prm.H2[2], prm.W2[2], lane);
+      add_box<kBW23, kBH23>(G3, acc + kOff3, xb3, yb3, prm.H2[3], prm.W2[3], lane);
+    } else {
+      write_slice<kBW01, kBH01>(G0, acc + kOff0, xb0, yb0, prm.H2[0], prm.W2[0], lane);
+      write_slice<kBW01, kBH01>(G1, acc + kOff1, xb1, yb1, prm.H2[1], prm.W2[1], lane);
+      write_slice<kBW23, kBH23>(G2, acc + kOff2, xb2, yb2, prm.H2[2], prm.W2[2], lane);
+      write_slice<kBW23, kBH23>(G3, acc + kOff3, xb3, yb3, prm.H2[3], prm.W2[3], lane);
+    }
     __syncwarp();                                               // slice stores ordered before the atomics below
     const bool any_miss = (ta0.gate && !ta0.inbox) || (has1 && tb0.gate && !tb0.inbox) || (ta1.gate && !ta1.inbox) ||
                           (has1 && tb1.gate && !tb1.inbox) || (lane < 9 && tm.gate && !tm.inbox) ||
                           (ta2.gate && !ta2.inbox) || (has1 && tb2.gate && !tb2.inbox) || (ta3.gate && !ta3.inbox) ||
                           (has1 && tb3.gate && !tb3.inbox);
     if (__any_sync(0xffffffffu, any_miss)) {
-      __threadfence();
+      if (!ACC) __threadfence();
       btap_scatter_global(G0, ta0, true, ga0, prm.W2[0]);
       btap_scatter_global(G0, tb0, has1, gb0, prm.W2[0]);
       btap_scatter_global(G1, ta1, true, ga1, prm.W2[1]);
@@ -430,11 +462,35 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
 
 }  // namespace lgu
 
+namespace lgu {
+static int launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, const float* coords, const float* off0,
+                                   const float* off1_out, const float* mask, const float* corr_grad,
+                                   const float* off1_out_grad, float* gv0, float* gv1, float* gv2, float* gv3,
+                                   float* off0_grad, float* off1_grad, int E, int H, int W, int num_levels, int radius,
+                                   bool accumulate, void* stream);
+}
 extern "C" int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lvl1, const float* coords,
                                               const float* off0, const float* off1_out, const float* mask,
                                               const float* corr_grad, const float* off1_out_grad, float* gv0,
                                               float* gv1, float* gv2, float* gv3, float* off0_grad, float* off1_grad,
                                               int E, int H, int W, int num_levels, int radius, void* stream) {
+  return lgu::launch_lookup_fused_bwd(lvl0, lvl1, coords, off0, off1_out, mask, corr_grad, off1_out_grad, gv0, gv1, gv2,
+                                      gv3, off0_grad, off1_grad, E, H, W, num_levels, radius, false, stream);
+}
+extern "C" int lgu_corr_lookup_fused_backward_accumulate(const float* lvl0, const float* lvl1, const float* coords,
+                                                         const float* off0, const float* off1_out, const float* mask,
+                                                         const float* corr_grad, const float* off1_out_grad,
+                                                         float* gv0, float* gv1, float* gv2, float* gv3,
+                                                         float* off0_grad, float* off1_grad, int E, int H, int W,
+                                                         int num_levels, int radius, void* stream) {
+  return lgu::launch_lookup_fused_bwd(lvl0, lvl1, coords, off0, off1_out, mask, corr_grad, off1_out_grad, gv0, gv1, gv2,
+                                      gv3, off0_grad, off1_grad, E, H, W, num_levels, radius, true, stream);
+}
+static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, const float* coords, const float* off0,
+                                        const float* off1_out, const float* mask, const float* corr_grad,
+                                        const float* off1_out_grad, float* gv0, float* gv1, float* gv2, float* gv3,
+                                        float* off0_grad, float* off1_grad, int E, int H, int W, int num_levels,
+                                        int radius, bool accumulate, void* stream) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(lvl0 && lvl1 && coords && off0 && off1_out && mask && corr_grad && gv0 && gv1 && gv2 && gv3 &&
@@ -475,13 +531,13 @@ extern "C" int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lv
   prm.tiles_per_edge = P / fl::kTile;
   const long long nblk = (long long)E * prm.tiles_per_edge;
   LGU_REQUIRE(nblk < 2147483647LL, "lgu_corr_lookup_fused_backward: grid too large (%lld CTAs)", nblk);
-  cudaError_t e = cudaFuncSetAttribute(lookup_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       flb::kSmemBytes);
+  auto kern = accumulate ? lookup_fused_bwd_kernel<true> : lookup_fused_bwd_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, flb::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("lgu_corr_lookup_fused_backward: cannot opt in to %d B of shared memory: %s", flb::kSmemBytes,
               cudaGetErrorString(e));
     return LGU_ERR_LAUNCH;
   }
-  lookup_fused_bwd_kernel<<<(unsigned)nblk, fl::kThreads, flb::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
+  kern<<<(unsigned)nblk, fl::kThreads, flb::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
   return check_launch("lgu_corr_lookup_fused_backward");
 }

@@ -303,11 +303,14 @@ def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False, 
     return (corr, mask) if return_mask else corr
 
 
-def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad, off1_out_grad=None):
+def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad, off1_out_grad=None,
+                               accumulate_into=None):
     """Backward of corr_lookup_fused in one launch (what autograd runs for corr.py:88-109 in training).
     pyramid: the 4 levels (only levels 0-1 are read); off1_out: off1 after the forward; mask [E,H,W] from the
     forward; corr_grad [E,196,H,W]; off1_out_grad: upstream gradient on the post-mask offsets (later calls) or None.
-    Returns (gv0, gv1, gv2, gv3, off0_grad, off1_grad) -- dense level gradients, off1_grad w.r.t. the PRE-mask off1."""
+    Returns (gv0, gv1, gv2, gv3, off0_grad, off1_grad) -- dense level gradients, off1_grad w.r.t. the PRE-mask off1.
+    accumulate_into: 4 persistent level-gradient buffers (same shapes as the pyramid, zeroed once by the caller); the
+    launch ADDS this call's gradient into them, touching only the per-pixel footprints, and returns them as gv0..gv3."""
     E, H, W = pyramid[0].shape[:3]
     for l, t in enumerate(pyramid):
         _chk(t, f"pyramid[{l}]", 5)
@@ -320,17 +323,53 @@ def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad,
         if not (isinstance(o, torch.Tensor) and o.is_cuda and o.is_contiguous() and o.dtype == torch.float32
                 and o.numel() == E * H * W * 98):
             raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor with {E * H * W * 98} elements")
-    gv = [torch.empty_like(t) for t in pyramid]
+    if accumulate_into is not None:
+        gv = list(accumulate_into)
+        for l, (a, t) in enumerate(zip(gv, pyramid)):
+            _chk(a, f"accumulate_into[{l}]", 5)
+            if a.shape != t.shape or a.device != t.device:
+                raise RuntimeError(f"accumulate_into[{l}] must match pyramid[{l}]")
+        fn = _lib.lib().lgu_corr_lookup_fused_backward_accumulate
+    else:
+        gv = [torch.empty_like(t) for t in pyramid]
+        fn = _lib.lib().lgu_corr_lookup_fused_backward
     g0 = torch.empty(E, H, W, 98, dtype=torch.float32, device=coords.device)
     g1 = torch.empty_like(g0)
     with torch.cuda.device(coords.device):
-        st = _lib.lib().lgu_corr_lookup_fused_backward(
+        st = fn(
             _p(pyramid[0]), _p(pyramid[1]), _p(coords), _p(off0), _p(off1_out), _p(mask), _p(corr_grad),
             _p(off1_out_grad) if off1_out_grad is not None else ctypes.c_void_p(0),
             _p(gv[0]), _p(gv[1]), _p(gv[2]), _p(gv[3]), _p(g0), _p(g1), _i(E), _i(H), _i(W), _i(4), _i(3),
             _stream(coords))
     _lib.check(st, "corr_lookup_fused_backward")
     return gv[0], gv[1], gv[2], gv[3], g0, g1
+
+
+def build_backward_gauss(means, covs, den, lvl0, level_grads, radius):
+    """Gaussian-head gradients of the fused build straight from the four level gradients (no dense pass):
+    means, covs [E,H,W,2], den [E,H,W], lvl0 [E,H,W,H,W], level_grads = 4 tensors [E,H,W,H>>l,W>>l] or None.
+    Returns (means_grad, covs_grad, den_grad); see lgu_build_backward_gauss in include/lgu_corr.h."""
+    _chk(means, "means", 4); _chk(covs, "covs", 4); _chk(den, "den", 3); _chk(lvl0, "lvl0", 5)
+    E, H, W = lvl0.shape[:3]
+    if tuple(lvl0.shape) != (E, H, W, H, W) or tuple(means.shape) != (E, H, W, 2) or tuple(covs.shape) != (E, H, W, 2) \
+            or tuple(den.shape) != (E, H, W):
+        raise RuntimeError("build_backward_gauss: inconsistent shapes")
+    ptrs = []
+    for l, g in enumerate(level_grads):
+        if g is None:
+            ptrs.append(ctypes.c_void_p(0))
+            continue
+        _chk(g, f"level_grads[{l}]", 5)
+        if tuple(g.shape) != (E, H, W, H >> l, W >> l):
+            raise RuntimeError(f"level_grads[{l}] must be [E,H,W,{H >> l},{W >> l}]")
+        ptrs.append(_p(g))
+    gm, gc, gd = torch.empty_like(means), torch.empty_like(covs), torch.empty_like(den)
+    with torch.cuda.device(lvl0.device):
+        st = _lib.lib().lgu_build_backward_gauss(_p(means), _p(covs), _p(den), _p(lvl0), ptrs[0], ptrs[1], ptrs[2],
+                                                 ptrs[3], _p(gm), _p(gc), _p(gd), _i(E), _i(H), _i(W), _i(radius),
+                                                 _stream(lvl0))
+    _lib.check(st, "build_backward_gauss")
+    return gm, gc, gd
 
 
 def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj):

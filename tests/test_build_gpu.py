@@ -145,3 +145,49 @@ def test_build_other_grid_heights(ops, oracle, H):
         assert g_.shape == w_.shape
         err = (g_.cpu() - w_).abs().max().item()
         assert err <= ATOL, f"H={H} level {l}: max abs err {err}"
+
+
+def _gauss_head_reference(ops, mean, cov, den, lvl0, grads):
+    """The dense torch composition FusedBuild.backward used before lgu_build_backward_gauss existed (and what autograd
+    runs for gaussianMask_cuda.py:84-86 + 3 x avg_pool2d): merge the level gradients, recover V, call the drop-in
+    gaussianMask_backward, reduce the 1/den term."""
+    E, h, w = lvl0.shape[:3]
+
+    def up(g, k):
+        return g.repeat_interleave(k, dim=3).repeat_interleave(k, dim=4)
+
+    g = grads[0].clone()
+    for gl, k in ((grads[1], 2), (grads[2], 4), (grads[3], 8)):
+        g += up(gl, k) / float(k * k)
+    ones = torch.ones(1, device=g.device).expand_as(lvl0)
+    wgt, = ops.gaussianMask(mean, cov, ones.contiguous(), 4)
+    dn = den.view(E, h, w, 1, 1)
+    V = lvl0 / (1.0 + wgt / dn)
+    g_mean, g_cov = ops.gaussianMask_backward(mean, cov, V.contiguous(), (g / dn).contiguous(), 4)
+    g_den = -(g.double() * (lvl0 - V).double()).sum(dim=(3, 4)).float() / den
+    return g_mean, g_cov, g_den
+
+
+def test_build_backward_gauss_matches_dense_composition(ops, oracle):
+    """lgu_build_backward_gauss (one launch over the 9x9 windows, level gradients read in place) against the dense
+    composition above.  Bar: 1e-5 abs relative to the gradient scale (fp32; the window sums run in a different order)."""
+    dev = "cuda"
+    c = inputs.frontend_case(E=3, T=4, seed=33, half_fmaps=True)
+    pyr = _run(ops, oracle, c, 1, True)
+    lvl0 = pyr[0]
+    g = inputs.gen(34)
+    grads = [torch.randn(3, 48, 64, 48 >> l, 64 >> l, generator=g).to(dev) for l in range(4)]
+    mean, cov = c["means"].to(dev), c["covs"].to(dev)
+    den = (6.28 * torch.sqrt(cov[..., 0] * cov[..., 1])).contiguous()
+    want = _gauss_head_reference(ops, mean, cov, den, lvl0, grads)
+    got = ops.build_backward_gauss(mean, cov, den, lvl0, grads, 4)
+    for name, a, b in zip(("means_grad", "covs_grad", "den_grad"), got, want):
+        err = (a - b).abs().max().item()
+        scale = max(1.0, b.abs().max().item())
+        assert err <= 1e-5 * scale, f"{name}: {err} (scale {scale})"
+    # missing levels are treated as zero gradients
+    got2 = ops.build_backward_gauss(mean, cov, den, lvl0, [grads[0], None, grads[2], None], 4)
+    z = [grads[0], torch.zeros_like(grads[1]), grads[2], torch.zeros_like(grads[3])]
+    want2 = _gauss_head_reference(ops, mean, cov, den, lvl0, z)
+    for a, b in zip(got2, want2):
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())

@@ -219,7 +219,8 @@ def test_pooled_corrblock_matches_corrblock_through_add_and_remove():
         torch.backends.cudnn.allow_tf32 = prev
 
 
-def test_training_clip_fused_lookup_equals_per_op_autograd():
+@pytest.mark.parametrize("accumulate", [True, False])
+def test_training_clip_fused_lookup_equals_per_op_autograd(accumulate):
     """BASELINE configs[2] in miniature (train.py step shape: a clip's edges, several lookup iterations, one backward,
     droid_net.py:187-222): the same CorrBlock with the fused differentiable build + lookup (2 + 2 launches per
     iteration pair) and with the reference's per-operator autograd graph gives the same outputs and the same gradients
@@ -241,8 +242,12 @@ def test_training_clip_fused_lookup_equals_per_op_autograd():
             corr, ofsMap, ofs_residual, GA = _modules(dev, 6)
             f1, f2 = fm1.clone().requires_grad_(), fm2.clone().requires_grad_()
             # fused: differentiable tcgen05 build (FusedBuild) + differentiable fused lookup; else the reference's graph
-            blk = corr.CorrBlock(ofsMap, ofs_residual, GA, f1, f2, fused=fused_lookup, fused_lookup=fused_lookup)
+            # accumulate: the lookups' level gradients go into persistent buffers (LevelGradAccumulator), else every
+            # lookup returns dense gradients that autograd sums
+            blk = corr.CorrBlock(ofsMap, ofs_residual, GA, f1, f2, fused=fused_lookup, fused_lookup=fused_lookup,
+                                 accumulate_grads=accumulate)
             assert ("FusedBuild" in type(blk.corr_pyramid[0].grad_fn).__name__) == fused_lookup
+            assert (blk._gacc is not None) == (fused_lookup and accumulate)
             loss = 0.0
             outs = []
             for c, w in zip(coords, wts):
@@ -250,6 +255,8 @@ def test_training_clip_fused_lookup_equals_per_op_autograd():
                 outs.append(out.detach())
                 loss = loss + (out * w).mean() + 1e-3 * (mean_n.square().mean() + theta.mean())
             loss.backward()
+            if blk._gacc is not None:
+                assert blk._gacc.grads is None, "FusedBuild.backward must consume (and free) the accumulators"
             res.append((outs, [t.grad.clone() for t in (f1, f2, ofsMap.weight, ofs_residual.weight, GA.map.weight,
                                                          GA.covMap.weight, GA.meanMap.weight)]))
     finally:

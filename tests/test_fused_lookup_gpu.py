@@ -207,3 +207,34 @@ def test_fused_lookup_and_backward_on_other_grid_sizes(ops, H, W):
         assert (pa[l].grad - pb[l].grad).abs().max().item() <= 2e-5 * scale, f"level {l} volume grad"
     for a, b in ((a0, b0), (a1, b1)):
         assert (a.grad - b.grad).abs().max().item() <= 2e-5 * max(1.0, b.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("big", [False, True])
+def test_fused_backward_accumulate_equals_sum_of_dense_calls(ops, big):
+    """Training clip (droid_net.py:187-222): three lookups of one pyramid.  The accumulate entry point adds each call's
+    footprints into persistent buffers (16-byte L2 reductions); the dense entry point returns one dense gradient per
+    call.  The sequential fp32 sum of the dense results is what the accumulators must hold (fp32 add of the same
+    terms in the same order; the reductions flush denormals, hence the 1e-30 allowance), and the offset gradients
+    of every call must be bit-identical."""
+    E, dev = 2, "cuda"
+    g = inputs.gen(71)
+    pyr = [torch.randn(E, 48, 64, 48 >> l, 64 >> l, generator=g).to(dev) for l in range(4)]
+    acc = [torch.zeros_like(p) for p in pyr]
+    want = [torch.zeros_like(p) for p in pyr]
+    for step in range(3):
+        c = _case(E, 72 + step, big_offsets=big)
+        coords, off0, off1 = c["coords"].to(dev), c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+        _, mask = ops.corr_lookup_fused(pyr, coords, off0, off1, 3, return_mask=True)
+        g_corr = torch.randn(E, 196, 48, 64, generator=g).to(dev)
+        g_up = (0.1 * torch.randn(E, 48, 64, 98, generator=g)).to(dev)
+        dense = ops.corr_lookup_fused_backward(pyr, coords, off0, off1, mask, g_corr, g_up)
+        got = ops.corr_lookup_fused_backward(pyr, coords, off0, off1, mask, g_corr, g_up, accumulate_into=acc)
+        for l in range(4):
+            assert got[l] is acc[l]
+            want[l] += dense[l]
+        assert torch.equal(got[4], dense[4]) and torch.equal(got[5], dense[5]), "offset gradients differ"
+    for l in range(4):
+        err = (acc[l] - want[l]).abs().max().item()
+        # out-of-box taps (|offset| >= 4, `big`) go through scalar atomics whose order is not fixed
+        tol = 1e-30 if not big else 2e-5 * max(1.0, want[l].abs().max().item())
+        assert err <= tol, f"level {l}: accumulated gradient differs from the sum of dense calls by {err}"
