@@ -165,6 +165,46 @@ def test_altcorrblock_materialized_matches_lowmem_operators(strict_ref, half):
     assert d.abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("strict_ref", [True, False])
+def test_altcorr_cache_across_ba_steps(strict_ref):
+    """Global BA calls the block for the same chunk in every iteration (factor_graph.py:265-279) with new coords: the
+    cached block (offset heads and volumes kept per chunk) must return what the uncached block returns, call after
+    call, must be bit-reproducible, and must not let one call's mask leak into the next (the reference regenerates
+    the offsets on every call, corr.py:186-189)."""
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 8)
+    g = inputs.gen(21)
+    T, E = 6, 7
+    fmaps = torch.randn(1, T, 128, 48, 64, generator=g).half().to(dev)
+    chunks = [(torch.tensor([0, 1, 2, 3, 4, 5, 2], device=dev), torch.tensor([1, 2, 3, 4, 5, 4, 0], device=dev)),
+              (torch.tensor([5, 4, 3], device=dev), torch.tensor([0, 1, 2], device=dev))]
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            a = corr.AltCorrBlock(ofsMap, ofs_residual, GA, fmaps, strict_ref=strict_ref, cache=True, volume_cache_gb=1.0)
+            b = corr.AltCorrBlock(ofsMap, ofs_residual, GA, fmaps, strict_ref=strict_ref, cache=False)
+            assert a.materialize and b.materialize
+            first = {}
+            for step in range(3):
+                for ci, (ii, jj) in enumerate(chunks):
+                    n = ii.numel()
+                    coords = inputs.make_coords(n, 48, 64, 48, 64, inputs.gen(100 + 10 * ci + (step % 2)))
+                    coords = coords.permute(0, 2, 3, 1).contiguous().view(1, n, 48, 64, 2).to(dev)
+                    out_a, out_b = a(coords, ii, jj), b(coords, ii, jj)
+                    err = (out_a - out_b).abs().max().item()
+                    assert err <= 1e-4 * max(1.0, out_b.abs().max().item() / 10), f"step {step} chunk {ci}: {err}"
+                    if step == 0:
+                        first[ci] = out_a.clone()
+                    elif step == 2:            # same coords as step 0: two cached calls and a different one in between
+                        assert torch.equal(out_a, first[ci]), "cached calls must be bit-reproducible"
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert len(a._cache) == 2 and a._vol_bytes == (7 + 3) * 4 * 3072 * (3072 + 768 + 192 + 48)
+    a.clear_cache()
+    assert not a._cache and a._vol_bytes == 0
+
+
 def test_build_volume_matches_matmul(ops):
     dev = "cuda"
     g = inputs.gen(12)

@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--gather", default="none", choices=["none", "dst", "stream"])
     ap.add_argument("--lowmem-ops", action="store_true", help="reference op sequence (altcorr + 4 x lowMem_defSample)")
     ap.add_argument("--strict-ref", type=int, default=1)
+    ap.add_argument("--cache", type=int, default=0, help="1: keep per-chunk offsets and volumes across BA steps")
+    ap.add_argument("--volume-cache-gb", type=float, default=None, help="HBM budget of the volume cache (default: half of free)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -82,7 +84,7 @@ def main():
     coords_d, ii_d, jj_d = coords.to(dev), ii.to(dev), jj.to(dev)
     with torch.no_grad():
         blk = corr.AltCorrBlock(ofsMap, ofs_res, GA, fmaps.view(1, T, C, H, W), strict_ref=bool(a.strict_ref),
-                                materialize=not a.lowmem_ops)
+                                materialize=not a.lowmem_ops, cache=bool(a.cache), volume_cache_gb=a.volume_cache_gb)
         eng = sharded.ShardedBackendCorr(lambda c, i, j: blk(c, i, j)) if world > 1 else None
         if eng is not None:
             plan = eng.set_edges(ii, jj)
@@ -120,7 +122,8 @@ def main():
                           "chunks": len(plan.chunk_edges), "n_gpus": world, "ms_per_step": ms,
                           "edges_per_s": visited / ms * 1e3, "gather": a.gather,
                           "path": "lowMem operator sequence" if a.lowmem_ops else "tcgen05 volumes + fused lookup",
-                          "strict_ref": bool(a.strict_ref), "fmap_allgather_ms": gather_ms,
+                          "strict_ref": bool(a.strict_ref), "cache": bool(a.cache),
+                          "volume_cache_GB": round(blk._vol_bytes / 2**30, 1), "fmap_allgather_ms": gather_ms,
                           "edges_per_rank": plan.counts()}))
     if world > 1:
         dist.destroy_process_group()

@@ -92,6 +92,19 @@ int main() {
       float ms = time_it([&] { k<<<148, 128, smem>>>(m, (int)(R / 32), (int)C); }); CK(cudaGetLastError());
       printf("3D {32,32 rows,4 chunks} one store (16 KB)       : %7.1f us  %6.0f GB/s\n", ms * 1e3, GB / ms * 1e3);
     }
+    cuuint32_t b2c[3] = {32, 32, 2};
+    r = enc()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, d, s, b2c, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r) printf("enc 3D/2 failed %d\n", (int)r);
+    else {
+      auto k = store_kernel<1, 2, 8>; const int smem = 8 * 2 * 2 * 4096;
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      float ms = time_it([&] { k<<<148, 256, smem>>>(m, (int)(R / 32), (int)C); }); CK(cudaGetLastError());
+      printf("3D {32,32 rows,2 chunks} one store (8 KB), 8 warps x 2 bufs (128 KB smem): %7.1f us  %6.0f GB/s\n", ms * 1e3, GB / ms * 1e3);
+      auto k4 = store_kernel<1, 2, 4>; const int smem4 = 4 * 2 * 2 * 4096;
+      CK(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+      ms = time_it([&] { k4<<<148, 128, smem4>>>(m, (int)(R / 32), (int)C); }); CK(cudaGetLastError());
+      printf("3D {32,32 rows,2 chunks} one store (8 KB), 4 warps x 2 bufs: %7.1f us  %6.0f GB/s\n", ms * 1e3, GB / ms * 1e3);
+    }
   }
   {  // MODE 2: no swizzle, wide rows
     CUtensorMap m; cuuint64_t d[2] = {(cuuint64_t)C, (cuuint64_t)R}; cuuint64_t s[1] = {(cuuint64_t)C * 4}; cuuint32_t e[2] = {1, 1};
