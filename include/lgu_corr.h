@@ -202,6 +202,19 @@ LGU_API int lgu_build_backward_gauss(const float* means, const float* covs, cons
                                    float* means_grad, float* covs_grad, float* den_grad,
                                    int E, int H, int W, int radius, void* stream);
 
+/* Feature-map gradients of lgu_build_pyramid (backward of corr.py:144-152 through the 4-level pyramid, corr.py:83-86)
+ * on tcgen05, straight from the level gradients (average pooling commutes with the contraction):
+ *   g_f1[e,c,p]   = sum_l sum_q level_grads[l][e,p,q] * f2_l[e,c,q]        f2_l = avgpool_l(f2) / 16, TF32-split
+ *   g_f2[l][e,c,q] = sum_p level_grads[l][e,p,q] * f1[e,c,p]                f1 / 16, TF32-split
+ * (the caller adds g_f2 = sum_l upsample_l(g_f2[l]) / 4^l).  level_grads[l] [E,H*W,(H>>l)*(W>>l)] fp32 or NULL (level
+ * skipped; its g_f2[l] is left untouched); f1_hi/lo [E,C,H*W]; f2_hi/lo[l] [E,C,(H>>l)*(W>>l)]; outputs fp32.
+ * hi/lo come from lgu_tf32_split (x*scale = hi + lo, hi with 10 mantissa bits).  kind::tf32, 3 MMAs per product term
+ * (hi*hi + hi*lo + lo*hi), fp32 accumulation: ~2^-21 relative per product.  Needs C == 128, H*W % 128 == 0. */
+LGU_API int lgu_build_backward_fmaps(const float* const* level_grads, const float* f1_hi, const float* f1_lo,
+                                   const float* const* f2_hi, const float* const* f2_lo, float* g_f1,
+                                   float* const* g_f2, int num_levels, int E, int H, int W, int C, void* stream);
+LGU_API int lgu_tf32_split(const float* x, float scale, float* hi, float* lo, long long n, void* stream);
+
 /* Edge-slot pool variants (replace the whole-pyramid copies of CorrBlock.cat / CorrBlock.__getitem__,
  * corr.py:111-115,137-141, which the frontend pays on every keyframe: factor_graph.py:123,158).  The pyramid levels
  * and the offsets live in storage of `num_slots` edge slots ([num_slots,H,W,H>>l,W>>l], [num_slots,H,W,7,7,2]);

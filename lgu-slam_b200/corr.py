@@ -177,19 +177,10 @@ class FusedBuild(torch.autograd.Function):
         return tuple(pyr) + (token,)
 
     @staticmethod
-    def backward(ctx, g0, g1, g2, g3, _g_token=None):
-        f1, f2, mean, cov, det, den, lvl0 = ctx.saved_tensors
+    def _fmaps_grad_library(grads, f1, f2):
+        """The same two products on library GEMMs (cuBLAS fp32, no TF32) for shapes the tcgen05 kernel does not cover."""
         E, c, h, w = f1.shape
         P = h * w
-        grads = [g0, g1, g2, g3]
-        held = ctx.acc.take() if ctx.acc is not None else None
-        if held is not None:
-            grads = [a if g is None else a.add_(g) for a, g in zip(held, grads)]
-        grads = [None if g is None else g.float().contiguous() for g in grads]
-        if all(g is None for g in grads):
-            return (None,) * 7
-        g_mean, g_cov, g_den = ops.build_backward_gauss(mean, cov, den, lvl0, grads, GAUSS_RADIUS)
-        g_det = (g_den * (0.5 * 6.28) / torch.sqrt(det).view(E, h, w)).view_as(det)
         a1 = f1.reshape(E, c, P).float()
         g_f1 = torch.zeros(E, P, c, dtype=torch.float32, device=f1.device)
         g_f2 = torch.zeros(E, c, h, w, dtype=torch.float32, device=f1.device)
@@ -212,8 +203,27 @@ class FusedBuild(torch.autograd.Function):
                 g_f2 += t
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
-        g_f1 = (g_f1 / 16.0).transpose(1, 2).reshape(f1.shape)
-        g_f2 = g_f2 / 16.0
+        return (g_f1 / 16.0).transpose(1, 2).reshape(f1.shape), g_f2 / 16.0
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, g3, _g_token=None):
+        f1, f2, mean, cov, det, den, lvl0 = ctx.saved_tensors
+        E, c, h, w = f1.shape
+        P = h * w
+        grads = [g0, g1, g2, g3]
+        held = ctx.acc.take() if ctx.acc is not None else None
+        if held is not None:
+            grads = [a if g is None else a.add_(g) for a, g in zip(held, grads)]
+        grads = [None if g is None else g.float().contiguous() for g in grads]
+        if all(g is None for g in grads):
+            return (None,) * 7
+        g_mean, g_cov, g_den = ops.build_backward_gauss(mean, cov, den, lvl0, grads, GAUSS_RADIUS)
+        g_det = (g_den * (0.5 * 6.28) / torch.sqrt(det).view(E, h, w)).view_as(det)
+        if c == 128 and P % 128 == 0 and w % 32 == 0 and h % 8 == 0:
+            # tcgen05 kind::tf32 (3-term split): both products read the level gradients in place, once each
+            g_f1, g_f2 = ops.build_backward_fmaps(grads, f1, f2)
+        else:
+            g_f1, g_f2 = FusedBuild._fmaps_grad_library(grads, f1, f2)
         return (g_f1.to(f1.dtype), g_f2.view_as(f2).to(f2.dtype), g_mean, g_cov, g_det, None, None)
 
 

@@ -372,6 +372,62 @@ def build_backward_gauss(means, covs, den, lvl0, level_grads, radius):
     return gm, gc, gd
 
 
+def tf32_split(x, scale=1.0):
+    """x * scale = hi + lo with hi carrying 10 mantissa bits (exact split; the operand form of build_backward_fmaps)."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32):
+        raise RuntimeError("tf32_split: fp32 CUDA tensor expected")
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().lgu_tf32_split(_p(x), ctypes.c_float(scale), _p(hi), _p(lo), ctypes.c_longlong(x.numel()),
+                                       _stream(x))
+    _lib.check(st, "tf32_split")
+    return hi, lo
+
+
+def build_backward_fmaps(level_grads, f1, f2):
+    """Feature-map gradients of the fused build from the level gradients, on tcgen05 (kind::tf32, 3-term split).
+    level_grads: up to 4 tensors [E,H,W,H>>l,W>>l] or None; f1, f2 [E,C,H,W] fp32 (the maps the volume was built from).
+    Returns (g_f1, g_f2) [E,C,H,W] fp32: g_f1 = g_V f2 / 16, g_f2 = g_V^T f1 / 16 with g_V = sum_l avg_pool^T(level_grads[l])."""
+    import torch.nn.functional as F
+    E, C, H, W = f1.shape
+    L = len(level_grads)
+    f1h, f1l = tf32_split(f1.float().reshape(E, C, H * W), 1.0 / 16.0)
+    planes, cur = [], f2.float()
+    for l in range(L):
+        if l > 0:
+            cur = F.avg_pool2d(cur, 2, stride=2)
+        planes.append(tf32_split(cur.reshape(E, C, -1), 1.0 / 16.0) if level_grads[l] is not None else (None, None))
+    g_f1 = torch.empty(E, C, H * W, dtype=torch.float32, device=f1.device)
+    g_f2l = [torch.empty(E, C, (H >> l) * (W >> l), dtype=torch.float32, device=f1.device) if level_grads[l] is not None
+             else None for l in range(L)]
+    arr = ctypes.c_void_p * L
+
+    def ptrs(ts):
+        return arr(*[t.data_ptr() if t is not None else None for t in ts])
+
+    for l, g in enumerate(level_grads):
+        if g is not None:
+            _chk(g, f"level_grads[{l}]", 5)
+            if tuple(g.shape) != (E, H, W, H >> l, W >> l):
+                raise RuntimeError(f"level_grads[{l}] must be [E,H,W,{H >> l},{W >> l}]")
+    with torch.cuda.device(f1.device):
+        st = _lib.lib().lgu_build_backward_fmaps(ptrs(level_grads), _p(f1h), _p(f1l), ptrs([p[0] for p in planes]),
+                                                 ptrs([p[1] for p in planes]), _p(g_f1), ptrs(g_f2l), _i(L), _i(E), _i(H),
+                                                 _i(W), _i(C), _stream(f1))
+    _lib.check(st, "build_backward_fmaps")
+    g_f2 = None
+    for l, t in enumerate(g_f2l):
+        if t is None:
+            continue
+        t = t.view(E, C, H >> l, W >> l)
+        if l > 0:
+            k = 1 << l
+            t = (t / float(k * k)).repeat_interleave(k, dim=2).repeat_interleave(k, dim=3)
+        g_f2 = t if g_f2 is None else g_f2 + t
+    return g_f1.view(E, C, H, W), g_f2
+
+
 def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj):
     """volume[e,p,q] = sum_c f1[ii[e],p,c] * f2[jj[e],q,c] on tcgen05 (fp32 accumulate).  f1_* [T1,P,C],
     f2_* [T2,Q,C] contiguous CUDA fp16 planes (lo planes None for single-product precision); ii, jj int32 [E].

@@ -191,3 +191,55 @@ def test_build_backward_gauss_matches_dense_composition(ops, oracle):
     want2 = _gauss_head_reference(ops, mean, cov, den, lvl0, z)
     for a, b in zip(got2, want2):
         assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
+
+
+def _fmaps_grad_reference(level_grads, f1, f2):
+    """fp64 restatement of what autograd computes for corr.py:144-152 + 3 x avg_pool2d: merge the level gradients into
+    the dense volume gradient (avg_pool2d^T = nearest upsampling / 4^l), then the two matmul-backward products."""
+    E, C, H, W = f1.shape
+    g = torch.zeros(E, H, W, H, W, dtype=torch.float64, device=f1.device)
+    for l, gl in enumerate(level_grads):
+        if gl is None:
+            continue
+        k = 1 << l
+        g += gl.double().repeat_interleave(k, dim=3).repeat_interleave(k, dim=4) / float(k * k)
+    gm = g.view(E, H * W, H * W)
+    a1, a2 = f1.double().reshape(E, C, -1), f2.double().reshape(E, C, -1)
+    g_f1 = torch.bmm(a2, gm.transpose(1, 2)) / 16.0
+    g_f2 = torch.bmm(a1, gm) / 16.0
+    return g_f1.view_as(f1), g_f2.view_as(f2)
+
+
+@pytest.mark.parametrize("H,present", [(48, (1, 1, 1, 1)), (48, (1, 0, 1, 0)), (16, (0, 1, 1, 1)), (8, (1, 1, 1, 1))])
+def test_build_backward_fmaps_tf32_split_matches_fp64(ops, H, present):
+    """lgu_build_backward_fmaps (tcgen05 kind::tf32, hi*hi + hi*lo + lo*hi, transposing converters for the second
+    product) against an fp64 restatement.  Stated bound of the 3-term split: ~2^-21 relative PER PRODUCT; the sums
+    run over 3072-4080 terms with cancellation, and the tensor core's own accumulation is coarser than IEEE fp32
+    (measured floor 2-4e-6 of the RMS even for exactly representable inputs and K = 48, tools/diag/bb_diag.py), so the
+    stated bound of this kernel is 1e-5 of the RMS magnitude of the result (fp32 SIMT GEMMs: a few 1e-7)."""
+    dev = "cuda"
+    E, C, W = 2, 128, 64
+    g = inputs.gen(90 + H)
+    f1 = torch.randn(E, C, H, W, generator=g).to(dev)
+    f2 = torch.randn(E, C, H, W, generator=g).to(dev)
+    # gradients spanning many binades, including tiny values (fp16 splits would flush them)
+    grads = []
+    for l in range(4):
+        t = torch.randn(E, H, W, H >> l, W >> l, generator=g) * torch.exp2(torch.randint(-30, 4, (E, H, W, 1, 1), generator=g).float())
+        grads.append(t.to(dev) if present[l] else None)
+    g_f1, g_f2 = ops.build_backward_fmaps(grads, f1, f2)
+    w_f1, w_f2 = _fmaps_grad_reference(grads, f1, f2)
+    # g_f1[e, :, p] scales with row p of the gradients (the rows span 34 binades here): compare per source pixel;
+    # g_f2 mixes all rows: compare against its global RMS
+    rms1 = w_f1.square().mean(dim=1, keepdim=True).sqrt()
+    r1 = ((g_f1.double() - w_f1).abs() / rms1).max().item()
+    r2 = ((g_f2.double() - w_f2).abs().max() / w_f2.square().mean().sqrt()).item()
+    print(f"g_f1: max err / per-pixel rms {r1:.2e};  g_f2: max err / rms {r2:.2e}")
+    assert r1 <= 1e-5 and r2 <= 1e-5
+
+
+def test_tf32_split_is_exact(ops):
+    x = (torch.randn(100003, generator=inputs.gen(5)) * 1e3).cuda()
+    hi, lo = ops.tf32_split(x, 0.0625)
+    assert torch.equal(hi + lo, x * 0.0625)
+    assert (hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0

@@ -61,6 +61,39 @@ def test_corrblock_fused_inference_matches_per_op_path():
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def test_corrblock_on_a_grid_the_fused_kernels_do_not_cover(oracle):
+    """TUM-RGBD shape (240x320 images -> 30x40 maps; odd pooled sizes 15x20 / 7x10 / 3x5): neither the tcgen05 build
+    (W = 64) nor the fused lookup (W % 32 = 0) applies, so CorrBlock must run the reference's per-operator sequence on the
+    drop-in kernels -- checked against the CPU oracle's composition of the reference ops on the block's own pyramid."""
+    dev = "cuda"
+    import lgu_slam_b200
+    from importlib import import_module
+    corr = import_module("lgu-slam_b200.corr")
+    torch.manual_seed(3)
+    ofsMap = nn.Conv2d(256, 98, 3, padding=1).to(dev)
+    ofs_residual = nn.Conv2d(256, 98, 3, padding=1).to(dev)
+    GA = corr.GaussianMask(30, 40).to(dev)
+    g = inputs.gen(17)
+    b, n, h, w = 1, 2, 30, 40
+    fmap1 = torch.randn(b, n, 128, h, w, generator=g).to(dev)
+    fmap2 = torch.randn(b, n, 128, h, w, generator=g).to(dev)
+    coords = inputs.make_coords(n, h, w, h, w, g).permute(0, 2, 3, 1).contiguous().view(b, n, h, w, 2).to(dev)
+    with torch.no_grad():
+        blk = corr.CorrBlock(ofsMap, ofs_residual, GA, fmap1, fmap2)
+        assert [tuple(t.shape[3:]) for t in blk.corr_pyramid] == [(30, 40), (15, 20), (7, 10), (3, 5)]
+        assert not blk._can_fuse_lookup(coords)
+        pyr_cpu = [t.cpu().contiguous() for t in blk.corr_pyramid]
+        offs_cpu = [o.cpu().clone() for o in blk.offset]
+        for it in range(2):
+            out, _, _ = blk(coords)
+            want = oracle.corr_block_lookup(pyr_cpu, coords.view(n, h, w, 2).cpu(), offs_cpu, 3)
+            assert out.shape == (b, n, 196, h, w)
+            got = out.view(n, 196, h, w).cpu()
+            for l in (0, 2, 3):     # levels whose offsets do not pass through the mask: bit-exact
+                assert torch.equal(got[:, 49 * l:49 * (l + 1)], want[:, 49 * l:49 * (l + 1)]), f"call {it} level {l}"
+            assert (got[:, 49:98] - want[:, 49:98]).abs().max().item() <= 1e-5, f"call {it} level 1"
+
+
 def test_corrblock_training_path_has_gradients():
     dev = "cuda"
     corr, ofsMap, ofs_residual, GA = _modules(dev, 1)
