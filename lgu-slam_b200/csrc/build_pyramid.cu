@@ -28,6 +28,7 @@
 // Precision: PREC 1 = one fp16 product (exact for fp16-valued feature maps: the inference path);
 //            PREC 2 = hi/lo fp16 split of both operands, 3 MMAs (hi*hi + hi*lo + lo*hi): ~2^-21 relative
 //            per product, for fp32-valued feature maps (the training path).
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace lgu {
@@ -71,6 +72,7 @@ struct BpParams {
   float* lvl3;          // [E,P,Q/64] or null
   int E, P, H, gauss_radius, round_half, num_units, has_l1;
   const int32_t* out_slots;   // [E] or null: edge e is written to pyramid slot out_slots[e] (edge-slot pool)
+  int wide;     // 1: level-0 rows leave as pair-shared 16 KB boxes (512 contiguous bytes per source pixel; PREC 1, Q % 64 == 0)
   int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
   int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
 };
@@ -86,12 +88,12 @@ __device__ __forceinline__ float gauss_residual(float v, int x1, int y1, float m
   return __fadd_rn(__fdiv_rn(masked, den), v);
 }
 
-template <int PREC>
+template <int PREC, bool WIDE>
 __global__ void __launch_bounds__(kBpThreads, 1)
 build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                      const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                      const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
-                     const BpParams prm) {
+                     const __grid_constant__ CUtensorMap map_l0w, const BpParams prm) {
   using Cfg = BpCfg<PREC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -119,6 +121,7 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     prefetch_tmap(&map_bhi);
     if (PREC == 2) { prefetch_tmap(&map_lo); prefetch_tmap(&map_blo); }
     prefetch_tmap(&map_l0);
+    if (WIDE) prefetch_tmap(&map_l0w);
     if (prm.has_l1) prefetch_tmap(&map_l1);
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
@@ -267,6 +270,37 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
       }
       sbuf = (sbuf + 1 == Cfg::kStoreBufs) ? 0 : sbuf + 1;
     };
+    // Wide path (PREC 1, Q % 64 == 0): the two warps of a lane quadrant fill ONE 16 KB tile per target-row pair --
+    // chunks [ya | x0..31], [ya | x32..63], [yb | x0..31], [yb | x32..63], i.e. 512 CONTIGUOUS bytes per source pixel
+    // -- and one elected lane stores it with a single 3-D box.  Measured on the store stream alone
+    // (tools/micro/tma_store.cu): 5.7-5.9 TB/s against 5.2 TB/s for 32-row x 128-byte boxes, single-buffered.
+    uint8_t* pair_l0 = sStore + quad * 4 * 4096;
+    auto stage_row = [&](float (&v)[32], int chunk, bool patch, int yy, float mx, float my, float c1, float c2,
+                         float den, unsigned bx) {
+      float4* rowp = reinterpret_cast<float4*>(pair_l0 + chunk * 4096 + lane * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) rowp[c ^ rsw] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      if (patch) {
+        float* rowf = reinterpret_cast<float*>(rowp);
+        bool touched = false;
+        for (unsigned k = 0; k < rdg; ++k) {
+          const int x = (int)(bx + k);
+          const unsigned idx = (unsigned)(x - x0);
+          if (idx < 32u) {
+            const unsigned pos = (((idx >> 2) ^ (unsigned)rsw) << 2) | (idx & 3u);
+            rowf[pos] = gauss_residual(rowf[pos], x, yy, mx, my, c1, c2, den);
+            touched = true;
+          }
+        }
+        if (touched) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 t = rowp[c ^ rsw];
+            v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+          }
+        }
+      }
+    };
     // level 1: 16 floats (64 B) per lane, 64B-swizzled 32-row tile (2 KB of a staging buffer)
     auto store_l1 = [&](const float (&v)[16], int col, int row0) {
       if (lane == 0) tma_wait_read<Cfg::kStoreBufs - 1>();
@@ -331,13 +365,37 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
           const int ya = 4 * h + 2 * rp, yb = ya + 1;
           const bool pa = gr > 0 && ((unsigned)ya - by) < rdg;
           const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
-          if (ya * 64 + x0 < Q) store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx);   // flat mode: Q may
-          if (yb * 64 + x0 < Q) store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx);   // end mid-half
+          constexpr bool wide = Cfg::kPairL1 && WIDE;
+          if (wide) {
+            // A: the engine has read the pair's tiles of the previous row pair (the issuer waited), both warps may restage
+            if (xs == 0 && lane == 0) tma_wait_read<0>();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+            stage_row(a, xs, pa, ya, mx, my, c1, c2, den, bx);
+            stage_row(b, 2 + xs, pb, yb, mx, my, c1, c2, den, bx);
+          } else {
+            if (ya * 64 + x0 < Q) store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx);   // flat mode: Q may
+            if (yb * 64 + x0 < Q) store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx);   // end mid-half
+          }
           // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             l1[rp][i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a[2 * i], a[2 * i + 1]), b[2 * i]), b[2 * i + 1]), 0.25f);
-          if (prm.has_l1) {
+          if (wide) {
+            if (prm.has_l1) {
+              float4* rowp = reinterpret_cast<float4*>(pair_l1 + l1buf * 4096 + lane * 128);
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                rowp[(xs * 4 + c) ^ rsw] = make_float4(l1[rp][4 * c], l1[rp][4 * c + 1], l1[rp][4 * c + 2], l1[rp][4 * c + 3]);
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");        // B: both warps' halves are staged
+            if (xs == 0 && lane == 0) {
+              tma_store_3d(&map_l0w, pair_l0, 0, row0, 2 * ya);                 // chunks beyond Q / 32 are clipped
+              if (prm.has_l1) tma_store_2d(&map_l1, pair_l1 + l1buf * 4096, (2 * h + rp) * 32, row0);
+              tma_commit();
+            }
+            l1buf ^= 1;
+          } else if (prm.has_l1) {
             if (kL1Direct) {   // 64-byte rows cost the TMA store engine a full row slot each: use the idle LSU instead
               float4* o1 = reinterpret_cast<float4*>(prm.lvl1 + pix * (size_t)(Q >> 2) + (2 * h + rp) * 32 + xs * 16);
 #pragma unroll
@@ -460,11 +518,17 @@ __global__ void __launch_bounds__(256) pack_fmaps_vec_kernel(const SRC* __restri
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
+static inline bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
+
 template <int PREC>
 static int launch_build(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mbh, const CUtensorMap& mbl,
-                        const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st) {
+                        const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& m0w, const BpParams& prm,
+                        cudaStream_t st) {
   using Cfg = BpCfg<PREC>;
-  auto kern = build_pyramid_kernel<PREC>;
+  auto kern = (PREC == 1 && prm.wide) ? build_pyramid_kernel<PREC, PREC == 1> : build_pyramid_kernel<PREC, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("lgu_build_pyramid: cannot opt in to %d B of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
@@ -474,7 +538,7 @@ static int launch_build(const CUtensorMap& mh, const CUtensorMap& ml, const CUte
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = prm.num_units < sms ? prm.num_units : sms;
-  kern<<<grid, kBpThreads, Cfg::kSmemBytes, st>>>(mh, ml, mbh, mbl, m0, m1, prm);
+  kern<<<grid, kBpThreads, Cfg::kSmemBytes, st>>>(mh, ml, mbh, mbl, m0, m1, m0w, prm);
   return check_launch("lgu_build_pyramid");
 }
 
@@ -565,7 +629,16 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
                    precision == 1 ? 32 : 16, precision == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
 
+  CUtensorMap m0w = m0;
+  // measured at E = 48 (bench.py): the pair-shared 16 KB level-0 boxes do not pay in the pyramid build (593 vs 582 us:
+  // its epilogue, not the store shape, is the limit) -- opt-in only; the flat volumes below use them by default
+  const int wide = (precision == 1 && env_flag("LGU_BUILD_WIDE")) ? 1 : 0;
+  if (wide) {
+    rc = make_map_chunked(&m0w, lvl0, (uint64_t)S * P, P, 32, 4);
+    if (rc) return rc;
+  }
   BpParams prm;
+  prm.wide = wide;
   prm.ii = ii; prm.jj = jj; prm.means = means; prm.covs = covs; prm.den = den;
   prm.lvl1 = lvl1; prm.lvl2 = lvl2; prm.lvl3 = lvl3;
   prm.E = E; prm.P = P; prm.H = H; prm.gauss_radius = gauss_radius; prm.round_half = round_half;
@@ -574,8 +647,8 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   prm.out_slots = out_slots;
   prm.Q = P;
   prm.halves = H / 4;
-  if (precision == 1) return launch_build<1>(mh, ml, mh, ml, m0, m1, prm, (cudaStream_t)stream);
-  return launch_build<2>(mh, ml, mh, ml, m0, m1, prm, (cudaStream_t)stream);
+  if (precision == 1) return launch_build<1>(mh, ml, mh, ml, m0, m1, m0w, prm, (cudaStream_t)stream);
+  return launch_build<2>(mh, ml, mh, ml, m0, m1, m0w, prm, (cudaStream_t)stream);
 }
 
 extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
@@ -606,7 +679,16 @@ extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, co
   if (rc) return rc;
   rc = make_map_2d(&m0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, volume, (uint64_t)E * P, Q, 32, 32);
   if (rc) return rc;
+  CUtensorMap m0w = m0;
+  // flat volumes (no Gaussian patch, no pooled levels): 512 contiguous bytes per source pixel and store, -10 % on the
+  // backend's volume builds (tools/bench_backend.py: 41.7 -> 39.5 ms per step at 2048 edges)
+  const int wide = (precision == 1 && (Q % 64) == 0 && !env_flag("LGU_BUILD_NARROW")) ? 1 : 0;
+  if (wide) {
+    rc = make_map_chunked(&m0w, volume, (uint64_t)E * P, Q, 32, 4);
+    if (rc) return rc;
+  }
   BpParams prm;
+  prm.wide = wide;
   prm.ii = ii; prm.jj = jj; prm.means = nullptr; prm.covs = nullptr; prm.den = nullptr;
   prm.lvl1 = nullptr; prm.lvl2 = nullptr; prm.lvl3 = nullptr;
   prm.E = E; prm.P = P; prm.H = 0; prm.gauss_radius = 0; prm.round_half = 0;
@@ -615,6 +697,6 @@ extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, co
   prm.out_slots = nullptr;
   prm.Q = Q;
   prm.halves = (Q + 255) / 256;
-  if (precision == 1) return launch_build<1>(mh, ml, mbh, mbl, m0, m0, prm, (cudaStream_t)stream);
-  return launch_build<2>(mh, ml, mbh, mbl, m0, m0, prm, (cudaStream_t)stream);
+  if (precision == 1) return launch_build<1>(mh, ml, mbh, mbl, m0, m0, m0w, prm, (cudaStream_t)stream);
+  return launch_build<2>(mh, ml, mbh, mbl, m0, m0, m0w, prm, (cudaStream_t)stream);
 }
