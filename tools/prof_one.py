@@ -1,5 +1,5 @@
 """Minimal single-op driver for ncu captures:  python tools/prof_one.py <op> [--edges E] [--lvl L] [--iters N]
-ops: fwd | fwd1 | bwd | gauss | gauss_bwd | build"""
+ops: fwd | fwd1 | bwd | gauss | gauss_bwd | build | fused | fusedbwd | fusedbwd_acc | bbwd"""
 import argparse
 import os
 import sys
@@ -64,6 +64,22 @@ def main():
                 corr_, mask_ = ops.corr_lookup_fused(pyr, fc["coords"].to(dev), fc["offsets"][0].to(dev), o1, 3, return_mask=True)
                 fzb = (pyr, fc["coords"].to(dev), fc["offsets"][0].to(dev), o1, mask_, torch.randn(E, 196, H, W, device=dev, generator=g))
             ops.corr_lookup_fused_backward(fzb[0], fzb[1], fzb[2], fzb[3], fzb[4], fzb[5])
+        elif a.op == "fusedbwd_acc":
+            if "fza" not in globals():
+                global fza
+                fc = inputs.frontend_case(E=E, T=20, seed=5, half_fmaps=True)
+                pyr = [torch.randn(E, H, W, H >> l, W >> l, device=dev, generator=g) for l in range(4)]
+                o1 = fc["offsets"][1].to(dev)
+                corr_, mask_ = ops.corr_lookup_fused(pyr, fc["coords"].to(dev), fc["offsets"][0].to(dev), o1, 3, return_mask=True)
+                fza = (pyr, fc["coords"].to(dev), fc["offsets"][0].to(dev), o1, mask_, torch.randn(E, 196, H, W, device=dev, generator=g),
+                       [torch.zeros_like(p) for p in pyr])
+            ops.corr_lookup_fused_backward(fza[0], fza[1], fza[2], fza[3], fza[4], fza[5], accumulate_into=fza[6])
+        elif a.op == "bbwd":
+            if "bbw" not in globals():
+                global bbw
+                bbw = ([torch.randn(E, H, W, H >> l, W >> l, device=dev, generator=g) for l in range(4)],
+                       torch.randn(E, 128, H, W, device=dev, generator=g), torch.randn(E, 128, H, W, device=dev, generator=g))
+            ops.build_backward_fmaps(bbw[0], bbw[1], bbw[2])
         elif a.op == "fwd1":
             ops.corr_index_forward(vol, coords, 1)
         else:
