@@ -25,6 +25,7 @@
 //   g_var     = g_m * m * (1 - m)                             (sigmoid, corr.py:97)
 //   g_v[k]    = g_var * 2 (v[k] - mean) / 8                   (unbiased 9-tap variance, corr.py:96)
 //   gV_1     += corr_index_backward(g_v)                      (corrSample_kernel.cu:84-136)
+#include <cstdlib>
 #include "fused_common.cuh"
 
 namespace lgu {
@@ -38,7 +39,8 @@ constexpr int kWarpFloats = kSlots * kInSlotFloats + kAccFloats; // 2112 floats 
 constexpr int kSmemWarp = kWarps * kWarpFloats * 4;              // 67,584 B
 constexpr int kGWarpFloats = CH * kPixPerWarp;                   // per-warp upstream-gradient rows: 196 x 4 pixels
 constexpr int kSmemG = kWarps * kGWarpFloats * 4;                // 25,088 B
-constexpr int kSmemBytes = kSmemWarp + kSmemG + kWarps * kSlots * 8;
+constexpr int kZeroBytes = 8192;                                 // CTA-shared zero source of the bulk zero-fill
+constexpr int kSmemBytes = kSmemWarp + kSmemG + kWarps * kSlots * 8 + kZeroBytes;
 }  // namespace flb
 
 struct FusedLookupBwdParams {
@@ -161,6 +163,49 @@ __device__ __forceinline__ void write_slice(float* __restrict__ G, float* acc, i
   }
 }
 
+// Dense mode, levels 0 and 1: the rows of the slice that do not intersect the accumulator box are pure zeros --
+// 8 of the 12 KB of a level-0 slice.  Those contiguous ranges leave through the TMA engine (cp.async.bulk
+// shared -> global from a CTA-wide zero buffer, one elected lane, <= 8 KB per copy) instead of 16-byte st.cs from
+// every lane; only the band of box rows is streamed by the LSU (zeros left / right of the box, the accumulator inside).
+__device__ __forceinline__ void bulk_zero(float* dst, int bytes, const void* zero_smem) {
+  while (bytes > 0) {
+    const int n = bytes < flb::kZeroBytes ? bytes : flb::kZeroBytes;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(fl_smem_u32(zero_smem)), "r"(n)
+                 : "memory");
+    dst += n >> 2;
+    bytes -= n;
+  }
+}
+template <int BW, int BH>
+__device__ __forceinline__ void write_slice_bulk(float* __restrict__ G, float* acc, int xb, int yb, int H2, int W2, int lane,
+                                                 const void* zero_smem) {
+  const int W4 = W2 >> 2;                                        // callers guarantee 32 % W4 == 0 (W2 in {32, 64, 128})
+  int y0 = max(yb, 0), y1 = min(yb + BH, H2);                    // band of slice rows that meet the box
+  if (y1 <= y0) y0 = y1 = H2;                                    // box entirely outside: the whole slice is zero
+  if (lane == 0) {
+    bulk_zero(G, y0 * W2 * 4, zero_smem);
+    bulk_zero(G + (size_t)y1 * W2, (H2 - y1) * W2 * 4, zero_smem);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  float4* G4 = reinterpret_cast<float4*>(G);
+  const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  const int rpi = 32 / W4;
+  const int ly = lane / W4, lx = lane - ly * W4;
+  const unsigned rx = (unsigned)((lx << 2) - xb);
+  const bool col_in = rx < (unsigned)BW;
+  float* acol = acc + rx;
+  for (int y = y0 + ly; y < y1; y += rpi) {
+    const unsigned ry = (unsigned)(y - yb);                      // < BH inside the band
+    float4 v = z;
+    if (col_in) {
+      float4* a = reinterpret_cast<float4*>(acol + ry * BW);
+      v = *a;
+      *a = z;
+    }
+    __stcs(G4 + y * W4 + lx, v);
+  }
+}
+
 // Accumulate mode (training, several lookups per pyramid): the gradient buffers persist across launches, so only the
 // accumulator box is touched -- one 16-byte reduction (RED.ADD.F32x4, resolved in L2, nothing returns to the SM) per
 // non-zero box cell that lies inside the slice; the accumulator is re-zeroed on the fly.  The slice is private to this
@@ -185,7 +230,7 @@ __device__ __forceinline__ void add_box(float* __restrict__ G, float* acc, int x
   }
 }
 
-template <bool ACC>
+template <bool ACC, bool BULK>
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupBwdParams prm) {
   using namespace flb;
@@ -196,6 +241,13 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
   float* acc = wmem + kSlots * kInSlotFloats;                    // acc0 | acc1 | acc2 | acc3 (offsets kOff0..3)
   float* s_g = reinterpret_cast<float*>(smem + kSmemWarp) + warp * kGWarpFloats;   // this warp's [CH][4 pixels]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemWarp + kSmemG) + warp * kSlots;
+  uint8_t* zero_smem = smem + kSmemWarp + kSmemG + kWarps * kSlots * 8;
+  if (BULK && !ACC) {
+    for (int q = threadIdx.x; q < kZeroBytes / 16; q += kThreads)
+      reinterpret_cast<float4*>(zero_smem)[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
 
   const int P = prm.P;
   const int n = blockIdx.x / prm.tiles_per_edge;
@@ -430,8 +482,13 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       add_box<kBW23, kBH23>(G2, acc + kOff2, xb2, yb2, prm.H2[2], prm.W2[2], lane);
       add_box<kBW23, kBH23>(G3, acc + kOff3, xb3, yb3, prm.H2[3], prm.W2[3], lane);
     } else {
-      write_slice<kBW01, kBH01>(G0, acc + kOff0, xb0, yb0, prm.H2[0], prm.W2[0], lane);
-      write_slice<kBW01, kBH01>(G1, acc + kOff1, xb1, yb1, prm.H2[1], prm.W2[1], lane);
+      if (BULK) {
+        write_slice_bulk<kBW01, kBH01>(G0, acc + kOff0, xb0, yb0, prm.H2[0], prm.W2[0], lane, zero_smem);
+        write_slice_bulk<kBW01, kBH01>(G1, acc + kOff1, xb1, yb1, prm.H2[1], prm.W2[1], lane, zero_smem);
+      } else {
+        write_slice<kBW01, kBH01>(G0, acc + kOff0, xb0, yb0, prm.H2[0], prm.W2[0], lane);
+        write_slice<kBW01, kBH01>(G1, acc + kOff1, xb1, yb1, prm.H2[1], prm.W2[1], lane);
+      }
       write_slice<kBW23, kBH23>(G2, acc + kOff2, xb2, yb2, prm.H2[2], prm.W2[2], lane);
       write_slice<kBW23, kBH23>(G3, acc + kOff3, xb3, yb3, prm.H2[3], prm.W2[3], lane);
     }
@@ -441,6 +498,10 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
                           (ta2.gate && !ta2.inbox) || (has1 && tb2.gate && !tb2.inbox) || (ta3.gate && !ta3.inbox) ||
                           (has1 && tb3.gate && !tb3.inbox);
     if (__any_sync(0xffffffffu, any_miss)) {
+      if (BULK && !ACC) {                                       // the zero ranges must have landed before the atomics
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
       if (!ACC) __threadfence();
       btap_scatter_global(G0, ta0, true, ga0, prm.W2[0]);
       btap_scatter_global(G0, tb0, has1, gb0, prm.W2[0]);
@@ -457,6 +518,10 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       const float nx = __shfl_sync(0xffffffffu, cmine.x, k + 2), ny = __shfl_sync(0xffffffffu, cmine.y, k + 2);
       if (lane == 0) issue(k + 2, nx, ny);
     }
+  }
+  if (BULK && !ACC) {                                           // the zero buffer must outlive the engine's reads
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
 }
 
@@ -531,7 +596,11 @@ static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, co
   prm.tiles_per_edge = P / fl::kTile;
   const long long nblk = (long long)E * prm.tiles_per_edge;
   LGU_REQUIRE(nblk < 2147483647LL, "lgu_corr_lookup_fused_backward: grid too large (%lld CTAs)", nblk);
-  auto kern = accumulate ? lookup_fused_bwd_kernel<true> : lookup_fused_bwd_kernel<false>;
+  // bulk zero-fill needs row bands that tile a warp (W2 / 4 divides 32 at levels 0 and 1)
+  const char* nb = getenv("LGU_BWD_NOBULK");
+  const bool bulk = !accumulate && (W == 64 || W == 128) && !(nb != nullptr && nb[0] != '\0' && nb[0] != '0');
+  auto kern = accumulate ? lookup_fused_bwd_kernel<true, false>
+                         : (bulk ? lookup_fused_bwd_kernel<false, true> : lookup_fused_bwd_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, flb::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("lgu_corr_lookup_fused_backward: cannot opt in to %d B of shared memory: %s", flb::kSmemBytes,
