@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblgu_corr.so")
+LIB_PATH = os.environ.get("LGU_CORR_LIB") or os.path.join(_HERE, "liblgu_corr.so")   # override: kernel A/B experiments
 ABI_VERSION = 1
 
 _lib = None

@@ -26,6 +26,15 @@
 
 namespace lgu {
 
+#ifndef LGU_FWD_SLOTS
+#define LGU_FWD_SLOTS 2   // measured (E = 48): 2 slots 239 us, 3 slots 248 us, 4 slots (one CTA per SM) 409 us
+#endif
+namespace flf {
+constexpr int kSlots = LGU_FWD_SLOTS;                               // TMA ring depth of the forward (boxes in flight per warp)
+constexpr int kSmemBoxes = fl::kWarps * kSlots * fl::kSlotBytes;
+constexpr int kSmemBytes = kSmemBoxes + fl::kSmemOut + fl::kWarps * kSlots * 8;
+}  // namespace flf
+
 struct FusedLookupParams {
   const float* lvl[4];
   const float* coords;   // [E,P,2] (x,y) level-0 units
@@ -44,6 +53,7 @@ template <bool PC>   // PC: per-corner gating (lowMem / altcorr semantics, Q4) i
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupParams prm) {
   using namespace fl;
+  constexpr int kSlots = flf::kSlots, kSmemBoxes = flf::kSmemBoxes;
   extern __shared__ __align__(1024) uint8_t smem[];              // no static shared memory: base is 1024-aligned
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* boxes = reinterpret_cast<float*>(smem) + warp * kSlots * kSlotFloats;
@@ -57,8 +67,8 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
   const int ns = prm.slots != nullptr ? __ldg(prm.slots + n) : n;   // storage slot of this edge (pyramid, offsets)
 
   if (lane == 0) {
-    fl_mbar_init(bars + 0, 1);
-    fl_mbar_init(bars + 1, 1);
+#pragma unroll
+    for (int q = 0; q < kSlots; ++q) fl_mbar_init(bars + q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -69,7 +79,7 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     cmine = __ldg(reinterpret_cast<const float2*>(prm.coords) + (size_t)n * P + min(pw + lane, P - 1));
 
   auto issue = [&](int k, float cx, float cy) {                 // lane 0 only
-    const int slot = k & 1;
+    const int slot = k % kSlots;
     const int pix = ns * P + min(pw + k, P - 1);
     float* dst = boxes + slot * kSlotFloats;
     fl_mbar_expect_tx(bars + slot, kSlotBytes);
@@ -85,13 +95,10 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
       sy = __fmul_rn(sy, 0.5f);
     }
   };
-  {
-    const float c0x = __shfl_sync(0xffffffffu, cmine.x, 0), c0y = __shfl_sync(0xffffffffu, cmine.y, 0);
-    const float c1x = __shfl_sync(0xffffffffu, cmine.x, 1), c1y = __shfl_sync(0xffffffffu, cmine.y, 1);
-    if (lane == 0) {
-      issue(0, c0x, c0y);
-      issue(1, c1x, c1y);
-    }
+#pragma unroll
+  for (int q = 0; q < kSlots && q < kPixPerWarp; ++q) {
+    const float cqx = __shfl_sync(0xffffffffu, cmine.x, q), cqy = __shfl_sync(0xffffffffu, cmine.y, q);
+    if (lane == 0) issue(q, cqx, cqy);
   }
 
   const int t0 = lane, t1 = lane + 32;                          // this lane's taps (t1 valid for lane < 17)
@@ -157,7 +164,7 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 
 #pragma unroll 1
   for (int k = 0; k < kPixPerWarp; ++k) {
-    const int slot = k & 1;
+    const int slot = k % kSlots;
     const int p = pw + k;
     const bool live = p < P;                                    // warp-uniform
     const size_t pix = (size_t)ns * P + min(p, P - 1);          // slice index in the pyramid storage
@@ -166,7 +173,7 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     if (lane == CENTER) o00 = make_float2(0.0f, 0.0f);          // Q5: the centre tap reads as 0
     if (k + 1 < kPixPerWarp) load_offsets(k + 1);
 
-    fl_mbar_wait(bars + slot, (k >> 1) & 1);
+    fl_mbar_wait(bars + slot, (k / kSlots) & 1);
     const float* box = boxes + slot * kSlotFloats;
     float* so = s_out + warp * kPixPerWarp + k;                 // column of this pixel in the output tile
 
@@ -223,9 +230,9 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
       if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[(size_t)n * P + p] = m;
     }
     __syncwarp();                                               // every lane is done with this slot
-    if (k + 2 < kPixPerWarp) {
-      const float nx = __shfl_sync(0xffffffffu, cmine.x, k + 2), ny = __shfl_sync(0xffffffffu, cmine.y, k + 2);
-      if (lane == 0) issue(k + 2, nx, ny);
+    if (k + kSlots < kPixPerWarp) {
+      const float nx = __shfl_sync(0xffffffffu, cmine.x, k + kSlots), ny = __shfl_sync(0xffffffffu, cmine.y, k + kSlots);
+      if (lane == 0) issue(k + kSlots, nx, ny);
     }
   }
 
@@ -308,11 +315,11 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
   prm.slots = slots;
   LGU_REQUIRE(!(shared_offsets && apply_mask), "lgu_*_lookup_fused: apply_mask needs per-edge offsets");
   auto kern = per_corner ? lookup_fused_kernel<true> : lookup_fused_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fl::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, flf::kSmemBytes);
   if (e != cudaSuccess) {
-    set_error("lgu_corr_lookup_fused: cannot opt in to %d B of shared memory: %s", fl::kSmemBytes, cudaGetErrorString(e));
+    set_error("lgu_corr_lookup_fused: cannot opt in to %d B of shared memory: %s", flf::kSmemBytes, cudaGetErrorString(e));
     return LGU_ERR_LAUNCH;
   }
-  kern<<<(unsigned)nblk, fl::kThreads, fl::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
+  kern<<<(unsigned)nblk, fl::kThreads, flf::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
   return check_launch("lgu_corr_lookup_fused");
 }
