@@ -14,6 +14,7 @@ instead.  What differs is underneath:
 The learned heads (ofsMap / ofs_residual convs, the GaussianMask MLP) stay torch modules, as in the reference.
 """
 import math
+import weakref
 
 import torch
 import torch.nn as nn
@@ -94,15 +95,23 @@ class LevelGradAccumulator:
     `levels` are the FusedBuild outputs the buffers belong to (identity-checked by the lookup)."""
 
     def __init__(self):
-        self.levels = None
-        self.grads = None
+        self._levels = None        # weak references: the autograd graph (FusedBuild's ctx) points at this object, so strong
+        self.grads = None          # references to the build's outputs would close a cycle through the graph
+
+    @property
+    def levels(self):
+        return None if self._levels is None else tuple(r() for r in self._levels)
+
+    @levels.setter
+    def levels(self, tensors):
+        self._levels = None if tensors is None else tuple(weakref.ref(t) for t in tensors)
 
     def owns(self, pyramid):
-        return self.levels is not None and all(a is b for a, b in zip(self.levels, pyramid))
+        return self._levels is not None and all(r() is b for r, b in zip(self._levels, pyramid))
 
     def buffers(self):
         if self.grads is None:
-            self.grads = [torch.zeros_like(t) for t in self.levels]
+            self.grads = [torch.zeros_like(r()) for r in self._levels]
         return self.grads
 
     def take(self):
