@@ -21,11 +21,13 @@
 // K-major 128B-swizzled layout the validated descriptors of build_pyramid.cu describe.
 //
 // One CTA per output tile (128 rows x 128 channels), 320 threads:
-//   warp 0    : TMA producer (A k-block 128 x 32 fp32 or raw 32 x 128, B_hi / B_lo k-blocks), ring of kStages
+//   warp 0    : TMA producer (A k-block 128 x 32 fp32 or raw 32 x 128, B_hi / B_lo k-blocks), ring of kStages (4 in the
+//               default .ts form, where A_hi / A_lo live in tensor memory: 64 columns per stage next to the accumulators)
 //   warp 1    : tcgen05.mma issuer (M128 N128 K8, 12 MMAs per k-block) + TMEM allocation (2 x 128 columns)
 //   warps 2-5 : converters (thread == tile row: mask / subtract / (transpose), fence.proxy.async)
 //   warps 6-9 : drain + epilogue (tcgen05.ld 32x32b.x32 of every finished chunk -> register sums -> 128-byte
 //               coalesced stores along the pixel axis of the [E, C, P] output)
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace lgu {
@@ -37,12 +39,17 @@ constexpr int kTile = 128;                 // M and N
 constexpr int kKB = 32;                    // k-block: 32 fp32 = one 128-byte swizzle atom row
 constexpr int kTileBytes = kTile * 128;    // 16 KB operand k-block
 constexpr int kMaxSeg = 4;
-template <bool TR>
+// TS = false: A_hi / A_lo k-blocks live in shared memory (SS form of tcgen05.mma).
+// TS = true : the converters write A_hi / A_lo into TENSOR MEMORY (tcgen05.st, thread == lane == tile row) and the MMAs
+//             take A from there (.ts form): a stage is raw A | B_hi | B_lo = 48 KB (4 stages), and per k-block 80 KB
+//             less crosses the SM's shared memory (the SS form is shared-memory-bandwidth bound).
+template <bool TR, bool TS>
 struct Cfg {
-  static constexpr int kStages = TR ? 2 : 3;
-  static constexpr int kStageBytes = (TR ? 5 : 4) * kTileBytes;   // [raw] | A_hi | A_lo | B_hi | B_lo
+  static constexpr int kStages = TS ? 4 : (TR ? 2 : 3);
+  static constexpr int kStageBytes = (TS ? 3 : (TR ? 5 : 4)) * kTileBytes;   // [raw] | A_hi | A_lo | B_hi | B_lo
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kSmemBytes = kBarOffset + 256 + 1024;      // + barriers + alignment slack
+  static constexpr int kTmemCols = TS ? 512 : 256;                // accumulators 0..255, A ring 256 + 64 * stage
 };
 }  // namespace bb
 
@@ -72,15 +79,25 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 constexpr uint32_t kTf32Mask = 0xFFFFE000u;   // sign, exponent, 10 mantissa bits
 
 // TR = false: A k-block = rows [row0, row0+128) x columns [kb*32, +32) of the segment's tensor (K contiguous).
 // TR = true : A k-block = TRANSPOSE of rows [edge_row0 + kb*32, +32) x columns [mt*128, +128) (K = rows).
-template <bool TR>
+template <bool TR, bool TS>
 __global__ void __launch_bounds__(bb::kThreads, 1)
 build_bwd_kernel(const __grid_constant__ BbMaps maps, const BbParams prm) {
   using namespace bb;
-  using C_ = Cfg<TR>;
+  using C_ = Cfg<TR, TS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::kBarOffset);
@@ -94,9 +111,9 @@ build_bwd_kernel(const __grid_constant__ BbMaps maps, const BbParams prm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x / prm.tiles_m, mt = blockIdx.x - e * prm.tiles_m;
   constexpr int kRawOff = 0;
-  constexpr int kAhiOff = TR ? kTileBytes : 0;
+  constexpr int kAhiOff = (TR && !TS) ? kTileBytes : 0;            // TS: the raw tile is the only A copy in shared memory
   constexpr int kAloOff = kAhiOff + kTileBytes;
-  constexpr int kBhiOff = kAloOff + kTileBytes;
+  constexpr int kBhiOff = TS ? kTileBytes : kAloOff + kTileBytes;
   constexpr int kBloOff = kBhiOff + kTileBytes;
 
   if (warp == 0 && lane == 0) {
@@ -114,7 +131,7 @@ build_bwd_kernel(const __grid_constant__ BbMaps maps, const BbParams prm) {
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  if (warp == 1) tmem_alloc(tmem_ptr, C_::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -169,10 +186,18 @@ build_bwd_kernel(const __grid_constant__ BbMaps maps, const BbParams prm) {
           const uint32_t off = kk * 32;                           // K = 8 tf32 = 32 bytes inside the swizzle atom
           const uint64_t ahi = make_kmajor_sw128_desc(st + kAhiOff + off), alo = make_kmajor_sw128_desc(st + kAloOff + off);
           const uint64_t bhi = make_kmajor_sw128_desc(st + kBhiOff + off), blo = make_kmajor_sw128_desc(st + kBloOff + off);
-          tc_mma_tf32(d_tmem, ahi, bhi, idesc, acc);
-          acc = 1;
-          tc_mma_tf32(d_tmem, ahi, blo, idesc, 1);
-          tc_mma_tf32(d_tmem, alo, bhi, idesc, 1);
+          if (TS) {
+            const uint32_t a_t = tmem_base + 256 + s * 64 + kk * 8;   // A_hi columns; A_lo 32 columns further
+            tc_mma_tf32_ts(d_tmem, a_t, bhi, idesc, acc);
+            acc = 1;
+            tc_mma_tf32_ts(d_tmem, a_t, blo, idesc, 1);
+            tc_mma_tf32_ts(d_tmem, a_t + 32, bhi, idesc, 1);
+          } else {
+            tc_mma_tf32(d_tmem, ahi, bhi, idesc, acc);
+            acc = 1;
+            tc_mma_tf32(d_tmem, ahi, blo, idesc, 1);
+            tc_mma_tf32(d_tmem, alo, bhi, idesc, 1);
+          }
         }
         tc_commit(empty + s);
         if ((it % kChunk) == kChunk - 1 || i == total - 1) tc_commit(chunk_full + buf);
@@ -180,7 +205,8 @@ build_bwd_kernel(const __grid_constant__ BbMaps maps, const BbParams prm) {
     }
   } else if (warp < 6) {
     // =============================== converters (warps 2..5) ===============================
-    const int row = threadIdx.x - 64;                             // tile row owned by this thread (0..127)
+    // tile row owned by this thread; with TS it is also the TMEM lane, which a warp may only touch in its own quadrant
+    const int row = TS ? ((warp & 3) * 32 + lane) : (threadIdx.x - 64);
     const int rsw = row & 7;                                      // 128B swizzle phase of the row
     int total = 0;
 #pragma unroll
@@ -193,7 +219,33 @@ build_bwd_kernel(const __grid_constant__ BbMaps maps, const BbParams prm) {
       uint8_t* st = smem + s * C_::kStageBytes;
       float4* hi_row = reinterpret_cast<float4*>(st + kAhiOff + row * 128);
       float4* lo_row = reinterpret_cast<float4*>(st + kAloOff + row * 128);
-      if (!TR) {
+      if (TS) {
+        // this row's 32 k values in K order (non-TR: undo the TMA's chunk swizzle; TR: one raw column), split, and
+        // written to the stage's tensor-memory columns
+        uint32_t h[32], l[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[4];
+          if (TR) {
+            const float* raw = reinterpret_cast<const float*>(st + kRawOff) + row;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = raw[(4 * c + q) * kTile];
+          } else {
+            const float4 t = hi_row[c ^ rsw];
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            h[4 * c + q] = __float_as_uint(v[q]) & kTf32Mask;
+            l[4 * c + q] = __float_as_uint(__fsub_rn(v[q], __uint_as_float(h[4 * c + q])));
+          }
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256 + s * 64;
+        tmem_st32(ta, h);
+        tmem_st32(ta + 32, l);
+        tmem_wait_st();
+        tc_fence_before();
+      } else if (!TR) {
         // in place and elementwise, so the TMA's chunk swizzle does not matter for correctness -- but the eight rows
         // of a swizzle group must touch eight DIFFERENT chunks per access (visiting chunk c of every row at once is a
         // 32-way bank conflict: measured 2.4 us per k-block instead of 0.8)
@@ -267,7 +319,7 @@ build_bwd_kernel(const __grid_constant__ BbMaps maps, const BbParams prm) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, C_::kTmemCols);
 }
 
 // x * scale -> hi (low 13 mantissa bits cleared) and lo = x * scale - hi (exact).
@@ -282,10 +334,10 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict
   }
 }
 
-template <bool TR>
-static int launch_bb(const BbMaps& maps, const BbParams& prm, int E, cudaStream_t st) {
-  using C_ = bb::Cfg<TR>;
-  auto kern = build_bwd_kernel<TR>;
+template <bool TR, bool TS>
+static int launch_bb_impl(const BbMaps& maps, const BbParams& prm, int E, cudaStream_t st) {
+  using C_ = bb::Cfg<TR, TS>;
+  auto kern = build_bwd_kernel<TR, TS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("lgu_build_backward_fmaps: cannot opt in to %d B of shared memory: %s", C_::kSmemBytes, cudaGetErrorString(e));
@@ -293,6 +345,13 @@ static int launch_bb(const BbMaps& maps, const BbParams& prm, int E, cudaStream_
   }
   kern<<<(unsigned)(E * prm.tiles_m), bb::kThreads, C_::kSmemBytes, st>>>(maps, prm);
   return check_launch("lgu_build_backward_fmaps");
+}
+
+template <bool TR>
+static int launch_bb(const BbMaps& maps, const BbParams& prm, int E, cudaStream_t st) {
+  const char* v = getenv("LGU_BBWD_SS");                           // 1: keep the A operand in shared memory (SS form)
+  if (v != nullptr && v[0] != '\0' && v[0] != '0') return launch_bb_impl<TR, false>(maps, prm, E, st);
+  return launch_bb_impl<TR, true>(maps, prm, E, st);
 }
 
 }  // namespace lgu
