@@ -31,6 +31,39 @@
 #include <cstdlib>
 #include "tc_common.cuh"
 
+// LGU_BP_TRACE (diagnostic builds only): per epilogue warp, cycles spent waiting for (0) the accumulator half, (1) a
+// free staging buffer (the TMA store engine), (2) the quadrant's pair barriers, and (3) in total.  lane 0 of every
+// epilogue warp adds its four counters to prm.trace[4] with atomics at kernel end (tools/diag/bp_trace.py).
+#ifdef LGU_BP_TRACE
+#define BP_T0() const long long _t0 = clock64()
+#define BP_ADD(slot) tr[slot] += clock64() - _t0
+#else
+#define BP_T0()
+#define BP_ADD(slot)
+#endif
+// LGU_BP_TRACE == 2: the slots are re-used for (0) the tcgen05.ld pairs, (1) staging writes + Gaussian patch,
+// (2) fence.proxy.async + __syncwarp + store issue
+#if defined(LGU_BP_TRACE) && LGU_BP_TRACE == 2
+#define BP2_T0() const long long _u0 = clock64()
+#define BP2_ADD(slot) tr[slot] += clock64() - _u0
+#undef BP_ADD
+#define BP_ADD(slot)
+#else
+#define BP2_T0()
+#define BP2_ADD(slot)
+#endif
+// LGU_BP_TRACE == 3: (0) 2x2 pooling of the row pair, (1) the whole level-1 path (pair barriers, staging, store),
+// (2) levels 2 / 3 (pooling + direct stores)
+#if defined(LGU_BP_TRACE) && LGU_BP_TRACE == 3
+#define BP3_T0() const long long _w0 = clock64()
+#define BP3_ADD(slot) tr[slot] += clock64() - _w0
+#undef BP_ADD
+#define BP_ADD(slot)
+#else
+#define BP3_T0()
+#define BP3_ADD(slot)
+#endif
+
 namespace lgu {
 
 // ---------------------------------------------------------------------------------------------
@@ -72,6 +105,7 @@ struct BpParams {
   float* lvl3;          // [E,P,Q/64] or null
   int E, P, H, gauss_radius, round_half, num_units, has_l1;
   const int32_t* out_slots;   // [E] or null: edge e is written to pyramid slot out_slots[e] (edge-slot pool)
+  unsigned long long* trace;   // LGU_BP_TRACE builds: 4 cycle counters (null otherwise)
   int wide;     // 1: level-0 rows leave as pair-shared 16 KB boxes (512 contiguous bytes per source pixel; PREC 1, Q % 64 == 0)
   int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
   int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
@@ -215,6 +249,10 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     }
   } else {
     // =============================== epilogue (warps 2..9) ===============================
+#ifdef LGU_BP_TRACE
+    long long tr[4] = {0, 0, 0, 0};
+    const long long tr_begin = clock64();
+#endif
     const int quad = warp & 3;                          // TMEM lane quadrant this warp may read (warp id % 4)
     const int xs = (warp - 2) >> 2;                     // which 32-column half of the 64 target columns
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -231,13 +269,18 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
     // stage one 32-float row segment per lane and hand the 32x32 tile to the TMA store engine
     auto store_tile = [&](float (&v)[32], int col, int row0, bool patch, int yy, float mx, float my, float c1, float c2,
                           float den, unsigned bx) {
-      if (lane == 0) {
-        // the tile staged in this buffer two level-0 stores ago must have been read; the issuer warp has one
-        // level-1 group between them, so it may leave one more group pending
-        if (l1_issuer) tma_wait_read<Cfg::kStoreBufs>();
-        else tma_wait_read<Cfg::kStoreBufs - 1>();
+      {
+        BP_T0();
+        if (lane == 0) {
+          // the tile staged in this buffer two level-0 stores ago must have been read; the issuer warp has one
+          // level-1 group between them, so it may leave one more group pending
+          if (l1_issuer) tma_wait_read<Cfg::kStoreBufs>();
+          else tma_wait_read<Cfg::kStoreBufs - 1>();
+        }
+        __syncwarp();
+        BP_ADD(1);
       }
-      __syncwarp();
+      BP2_T0();
       float4* rowp = reinterpret_cast<float4*>(my_store + sbuf * 4096 + lane * 128);
 #pragma unroll
       for (int c = 0; c < 8; ++c) rowp[c ^ rsw] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -262,11 +305,16 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
           }
         }
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&map_l0, my_store + sbuf * 4096, col, row0);
-        tma_commit();
+      BP2_ADD(1);
+      {
+        BP2_T0();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_l0, my_store + sbuf * 4096, col, row0);
+          tma_commit();
+        }
+        BP2_ADD(2);
       }
       sbuf = (sbuf + 1 == Cfg::kStoreBufs) ? 0 : sbuf + 1;
     };
@@ -340,15 +388,23 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
 
       for (int h = 0; h < halves; ++h, ++half_it) {
         const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
-        mbar_wait(t_full + buf, buf_use & 1);
+        {
+          BP_T0();
+          mbar_wait(t_full + buf, buf_use & 1);
+          BP_ADD(0);
+        }
         tc_fence_after();
         const uint32_t tcol = tmem_base + lane_base + buf * 256 + xs * 32;
         float l1[2][16];
 #pragma unroll
         for (int rp = 0; rp < 2; ++rp) {
           float a[32], b[32];
-          tmem_ld32(tcol + (2 * rp) * 64, a);
-          tmem_ld32(tcol + (2 * rp + 1) * 64, b);
+          {
+            BP2_T0();
+            tmem_ld32(tcol + (2 * rp) * 64, a);
+            tmem_ld32(tcol + (2 * rp + 1) * 64, b);
+            BP2_ADD(0);
+          }
           if (rp == 1) {
             // last TMEM read of this half: hand the accumulator back to the MMA issuer
             tc_fence_before();
@@ -377,9 +433,14 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
             if (yb * 64 + x0 < Q) store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx);   // end mid-half
           }
           // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
+          {
+            BP3_T0();
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            l1[rp][i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a[2 * i], a[2 * i + 1]), b[2 * i]), b[2 * i + 1]), 0.25f);
+            for (int i = 0; i < 16; ++i)
+              l1[rp][i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a[2 * i], a[2 * i + 1]), b[2 * i]), b[2 * i + 1]), 0.25f);
+            BP3_ADD(0);
+          }
+          BP3_T0();
           if (wide) {
             if (prm.has_l1) {
               float4* rowp = reinterpret_cast<float4*>(pair_l1 + l1buf * 4096 + lane * 128);
@@ -404,13 +465,21 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
             } else if (Cfg::kPairL1) {
               // named barrier of the quadrant's two warps (ids 1..4).  A: the issuer's waits before its two level-0
               // stores of this row pair guarantee that the tile stored from this buffer two rows ago has been read.
-              asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+              {
+                BP_T0();
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                BP_ADD(2);
+              }
               float4* rowp = reinterpret_cast<float4*>(pair_l1 + l1buf * 4096 + lane * 128);
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 rowp[(xs * 4 + c) ^ rsw] = make_float4(l1[rp][4 * c], l1[rp][4 * c + 1], l1[rp][4 * c + 2], l1[rp][4 * c + 3]);
               fence_proxy_async();
-              asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");      // B: both halves are in the tile
+              {
+                BP_T0();
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");    // B: both halves are in the tile
+                BP_ADD(2);
+              }
               if (xs == 0 && lane == 0) {
                 tma_store_2d(&map_l1, pair_l1 + l1buf * 4096, (2 * h + rp) * 32, row0);
                 tma_commit();
@@ -420,7 +489,9 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
               store_l1(l1[rp], (2 * h + rp) * 32 + xs * 16, row0);
             }
           }
+          BP3_ADD(1);
         }
+        BP3_T0();
         if (prm.lvl2 != nullptr) {
           float l2[8];
 #pragma unroll
@@ -443,10 +514,16 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
                 make_float4(l3[0], l3[1], l3[2], l3[3]);
           }
         }
+        BP3_ADD(2);
       }
     }
     if (lane == 0) tma_wait_all();                      // all bulk stores complete before the CTA exits
     __syncwarp();
+#ifdef LGU_BP_TRACE
+    tr[3] = clock64() - tr_begin;
+    if (lane == 0 && prm.trace != nullptr)
+      for (int q = 0; q < 4; ++q) atomicAdd(prm.trace + q, (unsigned long long)tr[q]);
+#endif
   }
 
   tc_fence_before();
@@ -639,6 +716,10 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   }
   BpParams prm;
   prm.wide = wide;
+  prm.trace = nullptr;
+#ifdef LGU_BP_TRACE
+  if (const char* tp = getenv("LGU_BP_TRACE_PTR")) prm.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
+#endif
   prm.ii = ii; prm.jj = jj; prm.means = means; prm.covs = covs; prm.den = den;
   prm.lvl1 = lvl1; prm.lvl2 = lvl2; prm.lvl3 = lvl3;
   prm.E = E; prm.P = P; prm.H = H; prm.gauss_radius = gauss_radius; prm.round_half = round_half;
@@ -689,6 +770,7 @@ extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, co
   }
   BpParams prm;
   prm.wide = wide;
+  prm.trace = nullptr;
   prm.ii = ii; prm.jj = jj; prm.means = nullptr; prm.covs = nullptr; prm.den = nullptr;
   prm.lvl1 = nullptr; prm.lvl2 = nullptr; prm.lvl3 = nullptr;
   prm.E = E; prm.P = P; prm.H = 0; prm.gauss_radius = 0; prm.round_half = 0;
