@@ -14,6 +14,7 @@ constexpr int kOff0 = 0, kOff1 = kBW01 * kBH01, kOff2 = 2 * kBW01 * kBH01, kOff3
 constexpr int kSlotFloats = kOff3 + kBW23 * kBH23;                 // 832 floats = 3328 B (26 x 128 B)
 constexpr int kSlotBytes = kSlotFloats * 4;
 constexpr int kSlots = 2;
+constexpr int kZeroBytes = 8192;
 constexpr int kOutPitch = kTile + 1;
 constexpr int kSmemBoxes = kWarps * kSlots * kSlotBytes;           // 53,248 B
 constexpr int kSmemOut = CH * kOutPitch * 4;                       // 25,872 B
@@ -44,6 +45,18 @@ __device__ __forceinline__ void fl_tma_box(void* dst, const CUtensorMap* map, ui
           fl_smem_u32(dst)),
       "l"(map), "r"(fl_smem_u32(bar)), "r"(x), "r"(y), "r"(z)
       : "memory");
+}
+
+// Zero ranges of a dense gradient slice leave through the TMA engine: cp.async.bulk shared -> global from a CTA-wide
+// zero buffer of kZeroBytes (16-byte aligned destination and size), issued by one lane into its current bulk group.
+__device__ __forceinline__ void bulk_zero(float* dst, int bytes, const void* zero_smem) {
+  while (bytes > 0) {
+    const int n = bytes < fl::kZeroBytes ? bytes : fl::kZeroBytes;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(fl_smem_u32(zero_smem)), "r"(n)
+                 : "memory");
+    dst += n >> 2;
+    bytes -= n;
+  }
 }
 
 // Box origin of a level: columns start at (floor(c) - reach) rounded down to a multiple of 4 (16-byte TMA

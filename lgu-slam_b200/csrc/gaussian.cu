@@ -23,10 +23,20 @@ __device__ __forceinline__ float gauss_weight(int x1, int y1, float mx, float my
   return expf(__fmul_rn(s, -0.5f));
 }
 
+constexpr int kGaZeroBytes = 8192;
+
+template <bool BULK>
 __global__ void __launch_bounds__(kGaWarps * 32)
 gaussian_fwd_kernel(const float* __restrict__ means, const float* __restrict__ covs,
                     const float* __restrict__ volume, float* __restrict__ out, long long npix, int H2, int W2,
                     int r) {
+  __shared__ __align__(16) uint8_t zero_smem[BULK ? kGaZeroBytes : 16];
+  if (BULK) {
+    for (int q = threadIdx.x; q < kGaZeroBytes / 16; q += blockDim.x)
+      reinterpret_cast<float4*>(zero_smem)[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -42,7 +52,34 @@ gaussian_fwd_kernel(const float* __restrict__ means, const float* __restrict__ c
     float* O = out + (size_t)pix * Q;
     if ((W2 & 3) == 0 && ((reinterpret_cast<uintptr_t>(O) | reinterpret_cast<uintptr_t>(V)) & 15) == 0) {
       const int W4 = W2 >> 2;
-      for (int q4 = lane; q4 < (Q >> 2); q4 += 32) {
+      int q4_begin = 0, q4_end = Q >> 2;
+      if (BULK) {
+        // rows that miss the window are pure zeros: they leave as cp.async.bulk copies from the CTA's zero buffer
+        // (one elected lane); only the band of window rows is evaluated and stored by the lanes
+        long long yb0 = (long long)cy - r, yb1 = yb0 + rd;       // cy may be a saturated conversion: 64-bit
+        int y0 = (int)(yb0 < 0 ? 0 : (yb0 > H2 ? H2 : yb0)), y1 = (int)(yb1 < 0 ? 0 : (yb1 > H2 ? H2 : yb1));
+        if (y1 <= y0) y0 = y1 = H2;
+        if (lane == 0) {
+          float* d = O;
+          for (int bytes = y0 * W2 * 4; bytes > 0;) {
+            const int nb = bytes < kGaZeroBytes ? bytes : kGaZeroBytes;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d),
+                         "r"((uint32_t)__cvta_generic_to_shared(zero_smem)), "r"(nb) : "memory");
+            d += nb >> 2; bytes -= nb;
+          }
+          d = O + (size_t)y1 * W2;
+          for (int bytes = (H2 - y1) * W2 * 4; bytes > 0;) {
+            const int nb = bytes < kGaZeroBytes ? bytes : kGaZeroBytes;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d),
+                         "r"((uint32_t)__cvta_generic_to_shared(zero_smem)), "r"(nb) : "memory");
+            d += nb >> 2; bytes -= nb;
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        q4_begin = y0 * W4;
+        q4_end = y1 * W4;
+      }
+      for (int q4 = q4_begin + lane; q4 < q4_end; q4 += 32) {
         const int y1 = q4 / W4, x1 = (q4 - y1 * W4) << 2;
         float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         const bool row_in = ((unsigned)y1 - by) < rd;
@@ -67,6 +104,10 @@ gaussian_fwd_kernel(const float* __restrict__ means, const float* __restrict__ c
         __stcs(O + q, v);
       }
     }
+  }
+  if (BULK) {                                                    // the zero buffer must outlive the engine's reads
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
 }
 
@@ -221,8 +262,15 @@ extern "C" int lgu_gaussian_mask_forward(const float* means, const float* covs, 
   LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_gaussian_mask_forward: H2*W2 too large");
   const long long npix = (long long)E * H1 * W1;
   const unsigned grid = lgu::grid_for_warps(npix, lgu::kGaWarps, 8);
-  lgu::gaussian_fwd_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(means, covs, volume, volume1, npix,
-                                                                                 H2, W2, radius);
+  // rows outside the window leave through the TMA engine when the slice rows are 16-byte multiples and aligned
+  const bool bulk = (W2 & 3) == 0 && ((reinterpret_cast<uintptr_t>(volume1) | reinterpret_cast<uintptr_t>(volume)) & 15) == 0 &&
+                    (((long long)H2 * W2) & 3) == 0;
+  if (bulk)
+    lgu::gaussian_fwd_kernel<true><<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(means, covs, volume, volume1,
+                                                                                         npix, H2, W2, radius);
+  else
+    lgu::gaussian_fwd_kernel<false><<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(means, covs, volume, volume1,
+                                                                                          npix, H2, W2, radius);
   return lgu::check_launch("lgu_gaussian_mask_forward");
 }
 

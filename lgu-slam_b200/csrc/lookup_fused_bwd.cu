@@ -39,7 +39,7 @@ constexpr int kWarpFloats = kSlots * kInSlotFloats + kAccFloats; // 2112 floats 
 constexpr int kSmemWarp = kWarps * kWarpFloats * 4;              // 67,584 B
 constexpr int kGWarpFloats = CH * kPixPerWarp;                   // per-warp upstream-gradient rows: 196 x 4 pixels
 constexpr int kSmemG = kWarps * kGWarpFloats * 4;                // 25,088 B
-constexpr int kZeroBytes = 8192;                                 // CTA-shared zero source of the bulk zero-fill
+using fl::kZeroBytes;                                            // CTA-shared zero source of the bulk zero-fill
 constexpr int kSmemBytes = kSmemWarp + kSmemG + kWarps * kSlots * 8 + kZeroBytes;
 }  // namespace flb
 
@@ -167,15 +167,6 @@ __device__ __forceinline__ void write_slice(float* __restrict__ G, float* acc, i
 // 8 of the 12 KB of a level-0 slice.  Those contiguous ranges leave through the TMA engine (cp.async.bulk
 // shared -> global from a CTA-wide zero buffer, one elected lane, <= 8 KB per copy) instead of 16-byte st.cs from
 // every lane; only the band of box rows is streamed by the LSU (zeros left / right of the box, the accumulator inside).
-__device__ __forceinline__ void bulk_zero(float* dst, int bytes, const void* zero_smem) {
-  while (bytes > 0) {
-    const int n = bytes < flb::kZeroBytes ? bytes : flb::kZeroBytes;
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(fl_smem_u32(zero_smem)), "r"(n)
-                 : "memory");
-    dst += n >> 2;
-    bytes -= n;
-  }
-}
 template <int BW, int BH>
 __device__ __forceinline__ void write_slice_bulk(float* __restrict__ G, float* acc, int xb, int yb, int H2, int W2, int lane,
                                                  const void* zero_smem) {

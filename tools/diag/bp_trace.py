@@ -21,6 +21,9 @@ for gauss in (True, False):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); ops.build_pyramid(*args, **k); b.record(); torch.cuda.synchronize()
     t = trace.tolist(); tot = t[3]
+    if tot == 0:
+        print(f"gauss={gauss}: {a.elapsed_time(b)*1e3:.0f} us (library built without -DLGU_BP_TRACE: no counters)")
+        continue
     if os.environ.get("LGU_BP_TRACE_MODE") == "2":
         print(f"gauss={gauss}: {a.elapsed_time(b)*1e3:.0f} us; tcgen05.ld pairs {100*t[0]/tot:.1f} %, staging writes + Gaussian patch "
               f"{100*t[1]/tot:.1f} %, fence.proxy.async + syncwarp + store issue {100*t[2]/tot:.1f} %, everything else {100*(tot-t[0]-t[1]-t[2])/tot:.1f} %")
