@@ -1,0 +1,46 @@
+// build_common.cuh -- parameter block and Gaussian residual shared by build_pyramid.cu (8 epilogue warps; every
+// precision / flat volumes) and build_pyramid16.cu (16 epilogue warps; the fp16-input pyramid build).
+#pragma once
+#include "tc_common.cuh"
+
+namespace lgu {
+
+constexpr int kTileM = 128;      // source pixels per unit
+constexpr int kChunkN = 128;     // target pixels per MMA chunk (2 target rows of 64)
+constexpr int kC = 128;          // channels (K)
+constexpr int kAtomBytes = 128 * 128;   // one 64-channel swizzle atom column of a 128-row tile: 16 KB
+constexpr int kPlaneBytes = 2 * kAtomBytes;   // 128 rows x 128 ch fp16 = 32 KB
+
+struct BpParams {
+  const int32_t* ii;
+  const int32_t* jj;
+  const float* means;   // [E,P,2] or null
+  const float* covs;    // [E,P,2]
+  const float* den;     // [E,P]
+  float* lvl1;          // [E,P,Q/4] or null (direct-store path)
+  float* lvl2;          // [E,P,Q/16] or null
+  float* lvl3;          // [E,P,Q/64] or null
+  int E, P, H, gauss_radius, round_half, num_units, has_l1;
+  const int32_t* out_slots;   // [E] or null: edge e is written to pyramid slot out_slots[e] (edge-slot pool)
+  unsigned long long* trace;   // LGU_BP_TRACE builds: 4 cycle counters (null otherwise)
+  int wide;     // 1: level-0 rows leave as pair-shared 16 KB boxes (512 contiguous bytes per source pixel; PREC 1, Q % 64 == 0)
+  int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
+  int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
+};
+
+// Gaussian residual of one element (gaussianAttn.cu:58-64 + gaussianMask_cuda.py:85-86), fp32, no contraction.
+__device__ __forceinline__ float gauss_residual(float v, int x1, int y1, float mx, float my, float c1, float c2,
+                                                float den) {
+  const float ddx = __fsub_rn((float)x1, mx), ddy = __fsub_rn((float)y1, my);
+  const float t1 = __fdiv_rn(ddx, c1), t2 = __fdiv_rn(ddy, c2);
+  const float s = __fmaf_rn(ddy, t2, __fmul_rn(t1, ddx));
+  const float e = expf(__fmul_rn(s, -0.5f));
+  const float masked = __fmul_rn(__fmul_rn(v, 3.0f), e);
+  return __fadd_rn(__fdiv_rn(masked, den), v);
+}
+
+
+// The 16-epilogue-warp kernel (build_pyramid16.cu).  Returns LGU_OK / an error code.
+int launch_build16(const CUtensorMap& mh, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st);
+
+}  // namespace lgu

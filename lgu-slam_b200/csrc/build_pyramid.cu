@@ -29,7 +29,7 @@
 //            PREC 2 = hi/lo fp16 split of both operands, 3 MMAs (hi*hi + hi*lo + lo*hi): ~2^-21 relative
 //            per product, for fp32-valued feature maps (the training path).
 #include <cstdlib>
-#include "tc_common.cuh"
+#include "build_common.cuh"
 
 // LGU_BP_TRACE (diagnostic builds only): per epilogue warp, cycles spent waiting for (0) the accumulator half, (1) a
 // free staging buffer (the TMA store engine), (2) the quadrant's pair barriers, and (3) in total.  lane 0 of every
@@ -72,11 +72,6 @@ namespace lgu {
 constexpr int kBpThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr bool kL1Direct = false;   // measured: direct 64-byte row stores are slower (727 vs 610 us at E=48)
-constexpr int kTileM = 128;      // source pixels per unit
-constexpr int kChunkN = 128;     // target pixels per MMA chunk (2 target rows of 64)
-constexpr int kC = 128;          // channels (K)
-constexpr int kAtomBytes = 128 * 128;   // one 64-channel swizzle atom column of a 128-row tile: 16 KB
-constexpr int kPlaneBytes = 2 * kAtomBytes;   // 128 rows x 128 ch fp16 = 32 KB
 
 template <int PREC>
 struct BpCfg {
@@ -93,34 +88,6 @@ struct BpCfg {
   static constexpr int kBarOffset = kABytes + kStages * kStageBytes + kStoreBytes + kL1Bytes;
   static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // + barriers + 1 KB alignment slack
 };
-
-struct BpParams {
-  const int32_t* ii;
-  const int32_t* jj;
-  const float* means;   // [E,P,2] or null
-  const float* covs;    // [E,P,2]
-  const float* den;     // [E,P]
-  float* lvl1;          // [E,P,Q/4] or null (direct-store path)
-  float* lvl2;          // [E,P,Q/16] or null
-  float* lvl3;          // [E,P,Q/64] or null
-  int E, P, H, gauss_radius, round_half, num_units, has_l1;
-  const int32_t* out_slots;   // [E] or null: edge e is written to pyramid slot out_slots[e] (edge-slot pool)
-  unsigned long long* trace;   // LGU_BP_TRACE builds: 4 cycle counters (null otherwise)
-  int wide;     // 1: level-0 rows leave as pair-shared 16 KB boxes (512 contiguous bytes per source pixel; PREC 1, Q % 64 == 0)
-  int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
-  int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
-};
-
-// Gaussian residual of one element (gaussianAttn.cu:58-64 + gaussianMask_cuda.py:85-86), fp32, no contraction.
-__device__ __forceinline__ float gauss_residual(float v, int x1, int y1, float mx, float my, float c1, float c2,
-                                                float den) {
-  const float ddx = __fsub_rn((float)x1, mx), ddy = __fsub_rn((float)y1, my);
-  const float t1 = __fdiv_rn(ddx, c1), t2 = __fdiv_rn(ddy, c2);
-  const float s = __fmaf_rn(ddy, t2, __fmul_rn(t1, ddx));
-  const float e = expf(__fmul_rn(s, -0.5f));
-  const float masked = __fmul_rn(__fmul_rn(v, 3.0f), e);
-  return __fadd_rn(__fdiv_rn(masked, den), v);
-}
 
 template <int PREC, bool WIDE>
 __global__ void __launch_bounds__(kBpThreads, 1)
@@ -728,6 +695,9 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   prm.out_slots = out_slots;
   prm.Q = P;
   prm.halves = H / 4;
+  // fp16-valued maps, all four levels: the 16-epilogue-warp kernel (build_pyramid16.cu); LGU_BUILD_EPI8=1 keeps this one
+  if (precision == 1 && lvl1 != nullptr && lvl2 != nullptr && lvl3 != nullptr && !wide && !env_flag("LGU_BUILD_EPI8"))
+    return launch_build16(mh, m0, m1, prm, (cudaStream_t)stream);
   if (precision == 1) return launch_build<1>(mh, ml, mh, ml, m0, m1, m0w, prm, (cudaStream_t)stream);
   return launch_build<2>(mh, ml, mh, ml, m0, m1, m0w, prm, (cudaStream_t)stream);
 }

@@ -1,0 +1,311 @@
+// build_pyramid16.cu -- the fused pyramid build of build_pyramid.cu with SIXTEEN epilogue warps (fp16-valued feature
+// maps, all four levels; the frontend / CorrBlock.__init__ case).  Same producer, same tcgen05 issuer, same outputs
+// bit for bit; what changes is who drains the accumulator.
+//
+// Why: a clock64 trace of the 8-warp kernel (-DLGU_BP_TRACE, tools/diag/bp_trace.py) shows its epilogue warps waiting
+// 3 % of their time for a free staging buffer, 4-8 % for the accumulator and 2 % at barriers -- the other ~90 % is their
+// own, latency-bound instruction stream (two epilogue warps per scheduler, 24 % issue slots used), while the TMA store
+// engine has >= 20 % headroom.  More warps per TMEM lane quadrant is the lever.
+//
+// Epilogue split: the four warps of a TMEM lane quadrant (warp id % 4) take (column half xs) x (row pair rp) of every
+// accumulator half (4 target rows x 64 columns):
+//   * one row at a time: tcgen05.ld 32 columns -> [fp16 rounding] -> staged in the warp's 4 KB swizzled tile (Gaussian
+//     window patched in shared memory) -> TMA store; the horizontal pair sums a[2i] + a[2i+1] of the upper row are kept
+//     (16 registers) so the 2x2 average keeps ATen's order ((a0 + a1) + b0) + b1 without holding both rows;
+//   * level 1: the two xs-warps of a row pair fill one 32-row x 128-byte tile; the quadrant's two tiles (rp = 0, 1) are
+//     stored by one elected lane after a quadrant barrier;
+//   * levels 2 / 3: after that barrier every warp reads the two level-1 tiles back from shared memory and produces a
+//     quarter of the level-2 row (4 columns, one 16-byte store per lane) and, every second half, 2 columns of level 3.
+// Shared memory: A 32 KB + 3 x 32 KB operand stages + 16 x 4 KB level-0 staging + 8 x 4 KB level-1 tiles = 224 KB.
+#include "build_common.cuh"
+
+namespace lgu {
+
+namespace b16 {
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (2 + kEpiWarps) * 32;       // 576
+constexpr int kStages = 3;
+constexpr int kABytes = kPlaneBytes;                 // 32 KB
+constexpr int kStageBytes = kPlaneBytes;             // 32 KB
+constexpr int kStoreBytes = kEpiWarps * 4096;        // 64 KB, one staging tile per warp
+constexpr int kL1Bytes = 4 * 2 * 4096;               // [quad][rp][32 rows][128 B]
+constexpr int kBarOffset = kABytes + kStages * kStageBytes + kStoreBytes + kL1Bytes;
+constexpr int kSmemBytes = kBarOffset + 256 + 1024;
+}  // namespace b16
+
+__global__ void __launch_bounds__(b16::kThreads, 1)
+build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_l0,
+                       const __grid_constant__ CUtensorMap map_l1, const BpParams prm) {
+  using namespace b16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kABytes;
+  uint8_t* sStore = sB + kStages * kStageBytes;        // [epilogue warp][32 rows][128 B]
+  uint8_t* sL1 = sStore + kStoreBytes;                 // [quad][rp][32 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOffset);
+  uint64_t* a_full = bars + 0;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;
+  uint64_t* b_empty = bars + 2 + kStages;
+  uint64_t* t_full = bars + 2 + 2 * kStages;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = prm.P;
+  const int tiles_m = P / kTileM;
+  const int halves = prm.halves;
+  const int Q = prm.Q;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_hi);
+    prefetch_tmap(&map_l0);
+    prefetch_tmap(&map_l1);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(t_full + b, 1);
+      mbar_init(t_empty + b, kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer (as in build_pyramid.cu, one fp16 plane) ===============================
+    if (lane == 0) {
+      uint32_t unit_it = 0, chunk_it = 0;
+      for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x, ++unit_it) {
+        const int e = u / tiles_m, mt = u - e * tiles_m;
+        const int a_row = __ldg(prm.ii + e) * P + mt * kTileM;
+        const int b_row0 = __ldg(prm.jj + e) * Q;
+        mbar_wait(a_empty, (unit_it & 1) ^ 1);
+        mbar_expect_tx(a_full, kABytes);
+        tma_load_2d(sA, &map_hi, a_full, 0, a_row);
+        tma_load_2d(sA + kAtomBytes, &map_hi, a_full, 64, a_row);
+        const int nchunks = halves * 2;
+        for (int c = 0; c < nchunks; ++c, ++chunk_it) {
+          const int s = chunk_it % kStages;
+          const uint32_t use = chunk_it / kStages;
+          mbar_wait(b_empty + s, (use & 1) ^ 1);
+          uint8_t* dst = sB + s * kStageBytes;
+          const int b_row = b_row0 + c * kChunkN;
+          mbar_expect_tx(b_full + s, kStageBytes);
+          tma_load_2d(dst, &map_hi, b_full + s, 0, b_row);
+          tma_load_2d(dst + kAtomBytes, &map_hi, b_full + s, 64, b_row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (as in build_pyramid.cu) ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kTileM, kChunkN);
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      uint32_t unit_it = 0, chunk_it = 0, half_it = 0;
+      for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x, ++unit_it) {
+        mbar_wait(a_full, unit_it & 1);
+        for (int h = 0; h < halves; ++h, ++half_it) {
+          const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
+          mbar_wait(t_empty + buf, (buf_use & 1) ^ 1);
+          tc_fence_after();
+          for (int c = 0; c < 2; ++c, ++chunk_it) {
+            const int s = chunk_it % kStages;
+            const uint32_t use = chunk_it / kStages;
+            mbar_wait(b_full + s, use & 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * 256 + c * kChunkN;
+            const uint32_t bs = b_addr + s * kStageBytes;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < kC / 16; ++k) {
+              const uint32_t koff = (k >> 2) * kAtomBytes + (k & 3) * 32;
+              tc_mma_f16(d_tmem, make_kmajor_sw128_desc(a_addr + koff), make_kmajor_sw128_desc(bs + koff), idesc, acc);
+              acc = 1;
+            }
+            tc_commit(b_empty + s);
+          }
+          tc_commit(t_full + buf);
+        }
+        tc_commit(a_empty);
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..17) ===============================
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may read (warp id % 4)
+    const int sub = (warp - 2) >> 2;                    // 0..3 inside the quadrant
+    const int xs = sub & 1, rp = sub >> 1;              // column half, row pair
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint8_t* my_store = sStore + (warp - 2) * 4096;
+    uint8_t* l1_mine = sL1 + (quad * 2 + rp) * 4096;    // the level-1 tile this warp half-fills
+    const uint8_t* l1_rows[2] = {sL1 + (quad * 2 + 0) * 4096, sL1 + (quad * 2 + 1) * 4096};
+    const bool l1_issuer = sub == 0;                    // issues the quadrant's two level-1 tiles
+    const int gr = prm.gauss_radius;
+    const unsigned rdg = 2u * (unsigned)gr + 1u;
+    const int rsw = lane & 7;                           // 128B swizzle phase of this thread's staging row
+    const int x0 = xs * 32;
+    const int bar_id = 1 + quad;                        // named barrier of the quadrant's four warps (128 threads)
+
+    // stage one 32-float row segment per lane (single staging tile: the previous store must have been read) and hand the
+    // 32 x 32 tile to the TMA store engine; patched values are read back into v (they feed the pooled levels)
+    auto store_tile = [&](float (&v)[32], int col, int row0, bool patch, int yy, float mx, float my, float c1, float c2,
+                          float den, unsigned bx) {
+      if (lane == 0) tma_wait_read<0>();
+      __syncwarp();
+      float4* rowp = reinterpret_cast<float4*>(my_store + lane * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) rowp[c ^ rsw] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      if (patch) {
+        float* rowf = reinterpret_cast<float*>(rowp);
+        bool touched = false;
+        for (unsigned k = 0; k < rdg; ++k) {
+          const int x = (int)(bx + k);
+          const unsigned idx = (unsigned)(x - x0);
+          if (idx < 32u) {
+            const unsigned pos = (((idx >> 2) ^ (unsigned)rsw) << 2) | (idx & 3u);
+            rowf[pos] = gauss_residual(rowf[pos], x, yy, mx, my, c1, c2, den);
+            touched = true;
+          }
+        }
+        if (touched) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 t = rowp[c ^ rsw];
+            v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_l0, my_store, col, row0);
+        tma_commit();
+      }
+    };
+
+    uint32_t half_it = 0;
+    for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x) {
+      const int e = u / tiles_m, mt = u - e * tiles_m;
+      const int es = prm.out_slots != nullptr ? __ldg(prm.out_slots + e) : e;
+      const int row0 = es * P + mt * kTileM + quad * 32;
+      const size_t pix = (size_t)row0 + lane;
+      float mx = 0.f, my = 0.f, c1 = 1.f, c2 = 1.f, den = 1.f;
+      unsigned bx = 0, by = 0;
+      if (gr > 0) {
+        const size_t ipix = (size_t)e * P + mt * kTileM + quad * 32 + lane;
+        const float2 m = __ldg(reinterpret_cast<const float2*>(prm.means) + ipix);
+        const float2 c = __ldg(reinterpret_cast<const float2*>(prm.covs) + ipix);
+        mx = m.x; my = m.y; c1 = c.x; c2 = c.y;
+        den = __ldg(prm.den + ipix);
+        bx = (unsigned)floor_to_int(mx) - (unsigned)gr;
+        by = (unsigned)floor_to_int(my) - (unsigned)gr;
+      }
+      float l2_prev[4] = {0.f, 0.f, 0.f, 0.f};
+
+      for (int h = 0; h < halves; ++h, ++half_it) {
+        const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
+        mbar_wait(t_full + buf, buf_use & 1);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + lane_base + buf * 256 + xs * 32;
+        const int ya = 4 * h + 2 * rp, yb = ya + 1;
+        float ha[16], l1[16];
+        {
+          float a[32];
+          tmem_ld32(tcol + (2 * rp) * 64, a);
+          if (prm.round_half) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = __half2float(__float2half_rn(a[i]));
+          }
+          const bool pa = gr > 0 && ((unsigned)ya - by) < rdg;
+          store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ha[i] = __fadd_rn(a[2 * i], a[2 * i + 1]);
+        }
+        {
+          float b[32];
+          tmem_ld32(tcol + (2 * rp + 1) * 64, b);
+          tc_fence_before();                            // last TMEM read of this half by this warp
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + buf);
+          if (prm.round_half) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) b[i] = __half2float(__float2half_rn(b[i]));
+          }
+          const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
+          store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx);
+          // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) l1[i] = __fmul_rn(__fadd_rn(__fadd_rn(ha[i], b[2 * i]), b[2 * i + 1]), 0.25f);
+        }
+        // ---- level 1: quadrant barrier A (the tiles of the previous half were read by the engine -- the issuer's
+        // wait_read before its level-0 stores of this half -- and by every warp's level-2 pass), stage, barrier B, store
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        {
+          float4* rowp = reinterpret_cast<float4*>(l1_mine + lane * 128);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            rowp[(xs * 4 + c) ^ rsw] = make_float4(l1[4 * c], l1[4 * c + 1], l1[4 * c + 2], l1[4 * c + 3]);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (l1_issuer && lane == 0) {
+          tma_store_2d(&map_l1, l1_rows[0], (2 * h) * 32, row0);
+          tma_store_2d(&map_l1, l1_rows[1], (2 * h + 1) * 32, row0);
+          tma_commit();
+        }
+        // ---- level 2 (and 3): this warp's quarter of the row, from the two level-1 tiles in shared memory
+        {
+          const float4* r0 = reinterpret_cast<const float4*>(l1_rows[0] + lane * 128);
+          const float4* r1 = reinterpret_cast<const float4*>(l1_rows[1] + lane * 128);
+          const float4 u0 = r0[(2 * sub) ^ rsw], u1 = r0[(2 * sub + 1) ^ rsw];
+          const float4 w0 = r1[(2 * sub) ^ rsw], w1 = r1[(2 * sub + 1) ^ rsw];
+          float l2[4];
+          l2[0] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(u0.x, u0.y), w0.x), w0.y), 0.25f);
+          l2[1] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(u0.z, u0.w), w0.z), w0.w), 0.25f);
+          l2[2] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(u1.x, u1.y), w1.x), w1.y), 0.25f);
+          l2[3] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(u1.z, u1.w), w1.z), w1.w), 0.25f);
+          *reinterpret_cast<float4*>(prm.lvl2 + pix * (size_t)(Q >> 4) + h * 16 + sub * 4) =
+              make_float4(l2[0], l2[1], l2[2], l2[3]);
+          if ((h & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) l2_prev[i] = l2[i];
+          } else {
+            const float l3a = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(l2_prev[0], l2_prev[1]), l2[0]), l2[1]), 0.25f);
+            const float l3b = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2], l2_prev[3]), l2[2]), l2[3]), 0.25f);
+            *reinterpret_cast<float2*>(prm.lvl3 + pix * (size_t)(Q >> 6) + (h >> 1) * 8 + sub * 2) = make_float2(l3a, l3b);
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int launch_build16(const CUtensorMap& mh, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(build_pyramid16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b16::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("lgu_build_pyramid: cannot opt in to %d B of shared memory: %s", b16::kSmemBytes, cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = prm.num_units < sms ? prm.num_units : sms;
+  build_pyramid16_kernel<<<grid, b16::kThreads, b16::kSmemBytes, st>>>(mh, m0, m1, prm);
+  return check_launch("lgu_build_pyramid(16)");
+}
+
+}  // namespace lgu
