@@ -108,6 +108,25 @@ __device__ __forceinline__ void btap_scatter_global(float* G, const BTap& t, boo
     if (t.xo && t.yo) atomicAdd(p + W2 + 1, __fmul_rn(__fmul_rn(t.dy, t.dx), g));
   }
 }
+// Fixed-point variant of the deformable scatter.  atomicAdd(float) on shared memory is a compare-and-swap loop per
+// corner (ATOMS.CAST.SPIN: 16 dependent loops per pixel and lane, 22 % of the kernel); integer adds are ONE native
+// ATOMS.ADD each, need no retry and are associative -- the accumulated gradient no longer depends on the order in
+// which colliding taps arrive.  The contributions of a pixel are scaled by a power of two chosen from the largest
+// upstream gradient magnitude of the pixel (|w g| 2^s < 2^23, so even 196 colliding corners cannot overflow) and rounded
+// to nearest: absolute error <= 2^-24 of that magnitude per contribution, below fp32's own rounding of the large terms.
+template <int BW>
+__device__ __forceinline__ void btap_scatter_fxp(int* acc, const BTap& t, bool active, float g, float scale) {
+  const float omdx = __fsub_rn(1.0f, t.dx), omdy = __fsub_rn(1.0f, t.dy);
+  const bool on = active && t.gate && t.inbox;
+  const float gs = __fmul_rn(g, scale);                          // exact (power of two), |gs| < 2^23
+  if (on) {
+    atomicAdd(acc + t.idx, __float2int_rn(__fmul_rn(__fmul_rn(omdy, omdx), gs)));
+    if (t.xo) atomicAdd(acc + t.idx + 1, __float2int_rn(__fmul_rn(__fmul_rn(omdy, t.dx), gs)));
+    if (t.yo) atomicAdd(acc + t.idx + BW, __float2int_rn(__fmul_rn(__fmul_rn(t.dy, omdx), gs)));
+    if (t.xo && t.yo) atomicAdd(acc + t.idx + BW + 1, __float2int_rn(__fmul_rn(__fmul_rn(t.dy, t.dx), gs)));
+  }
+}
+
 // Offset gradient of a tap (defCorrSample_kernel.cu:156-157, the reference's SASS operation order).
 __device__ __forceinline__ float2 offset_grad(float q11, float q21, float q12, float q22, float dx, float dy, float g) {
   const float omdx = __fsub_rn(1.0f, dx), omdy = __fsub_rn(1.0f, dy);
@@ -221,7 +240,7 @@ __device__ __forceinline__ void add_box(float* __restrict__ G, float* acc, int x
   }
 }
 
-template <bool ACC, bool BULK>
+template <bool ACC, bool BULK, bool FXP>
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupBwdParams prm) {
   using namespace flb;
@@ -343,8 +362,28 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
 
     // ---------------- deformable levels 0 and 1: offset gradients + scatter
     BTap ta0, tb0, ta1, tb1;                                    // kept for the global slow path after the slice write
-    float ga0, gb0, ga1, gb1;
+    float ga0 = sg[t0 * kPixPerWarp], gb0 = sg[t1c * kPixPerWarp];
+    float ga1 = sg[(TAPS + t0) * kPixPerWarp], gb1 = sg[(TAPS + t1c) * kPixPerWarp];
     float gm_part = 0.0f;
+    // fixed-point scale of this pixel: 2^(22 - exponent of the largest |gradient|); warp-uniform.  Falls back to the
+    // float path for non-finite or vanishing gradients.
+    float fxp_scale = 0.0f, fxp_inv = 0.0f;
+    if (FXP) {
+      float mx = fmaxf(fmaxf(fabsf(ga0), fabsf(ga1)), has1 ? fmaxf(fabsf(gb0), fabsf(gb1)) : 0.0f);
+      // NaN sampling positions make NaN weights, which must propagate like in the reference: float path.  (Infinite or
+      // huge positions are gated out -- a gated-in tap has a fraction in [0, 1), so |w g| <= |g|.)
+      const float pn = (o00.x + x0) + (o00.y + y0) + (o10.x + x1c) + (o10.y + y1c) +
+                       (has1 ? (o01.x + x0) + (o01.y + y0) + (o11.x + x1c) + (o11.y + y1c) : 0.0f);
+      const bool bad = !(isfinite(ga0) && isfinite(ga1) && (!has1 || (isfinite(gb0) && isfinite(gb1)))) || isnan(pn);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const int ex = ((__float_as_int(mx) >> 23) & 0xff) - 127;
+      if (!__any_sync(0xffffffffu, bad) && ex > -100) {
+        fxp_scale = __int_as_float((127 + 22 - ex) << 23);
+        fxp_inv = __int_as_float((127 - 22 + ex) << 23);
+      }
+    }
+    const bool fxp = FXP && fxp_scale != 0.0f;
     const int xb0 = box_origin_x(floor_to_int(x0), 7, prm.W2[0]), yb0 = box_origin_y(floor_to_int(y0), 7, prm.H2[0]);
     const int xb1 = box_origin_x(floor_to_int(x1c), 7, prm.W2[1]), yb1 = box_origin_y(floor_to_int(y1c), 7, prm.H2[1]);
     auto deform_bwd = [&](int l, const float* bx, int xb, int yb, float cx, float cy, float2 oa, float2 ob, BTap& ta,
@@ -362,8 +401,6 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
         tb.dx = __fsub_rn(px, (float)fx); tb.dy = __fsub_rn(py, (float)fy);
         btap_setup<kBW01, kBH01>(tb, xb, yb, fx, fy, i1, j1, R, H2, W2);
       }
-      ga = sg[(l * TAPS + t0) * kPixPerWarp];
-      gb = sg[(l * TAPS + t1c) * kPixPerWarp];
       // corner values (zero-filled out of bounds by the TMA unit) for the offset gradient
       float qa[4], qb[4];
       {
@@ -389,8 +426,13 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       goa = ta.gate ? offset_grad(qa[0], qa[1], qa[2], qa[3], ta.dx, ta.dy, ga) : make_float2(0.0f, 0.0f);
       gob = (has1 && tb.gate) ? offset_grad(qb[0], qb[1], qb[2], qb[3], tb.dx, tb.dy, gb) : make_float2(0.0f, 0.0f);
       float* ac = acc + (l == 0 ? kOff0 : kOff1);
-      btap_scatter<kBW01, true>(ac, ta, true, ga);
-      btap_scatter<kBW01, true>(ac, tb, has1, gb);
+      if (fxp) {
+        btap_scatter_fxp<kBW01>(reinterpret_cast<int*>(ac), ta, true, ga, fxp_scale);
+        btap_scatter_fxp<kBW01>(reinterpret_cast<int*>(ac), tb, has1, gb, fxp_scale);
+      } else {
+        btap_scatter<kBW01, true>(ac, ta, true, ga);
+        btap_scatter<kBW01, true>(ac, tb, has1, gb);
+      }
     };
     {
       float2 goa, gob;
@@ -413,6 +455,13 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       if (has1) GO[t1] = make_float2(__fmul_rn(gob.x, m), __fmul_rn(gob.y, m));
     }
     __syncwarp();                                               // shared atomics of this warp are done
+    if (fxp) {                                                  // fixed-point sums -> fp32, in place (both deformable boxes)
+      for (int q = lane; q < 2 * kBW01 * kBH01; q += 32) {
+        const int v = reinterpret_cast<const int*>(acc)[q];
+        acc[q] = __fmul_rn(__int2float_rn(v), fxp_inv);
+      }
+      __syncwarp();
+    }
 
     // ---------------- mask path: g_m -> sigmoid -> 9-tap variance -> level-1 scatter (r = 1 plain lookup)
     BTap tm;
@@ -457,6 +506,7 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       btap_setup<kBW23, kBH23>(ta, xb, yb, fx, fy, i0, j0, R, H2, W2);
       btap_setup<kBW23, kBH23>(tb, xb, yb, fx, fy, i1, j1, R, H2, W2);
       float* ac = acc + (l == 2 ? kOff2 : kOff3);
+      // (fixed-point adds were tried here too: no gain over the conflict-free read-modify-write phases)
       btap_scatter<kBW23, false>(ac, ta, true, sg[(l * TAPS + t0) * kPixPerWarp]);
       btap_scatter<kBW23, false>(ac, tb, has1, sg[(l * TAPS + t1c) * kPixPerWarp]);
     };
@@ -590,8 +640,12 @@ static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, co
   // bulk zero-fill needs row bands that tile a warp (W2 / 4 divides 32 at levels 0 and 1)
   const char* nb = getenv("LGU_BWD_NOBULK");
   const bool bulk = !accumulate && (W == 64 || W == 128) && !(nb != nullptr && nb[0] != '\0' && nb[0] != '0');
-  auto kern = accumulate ? lookup_fused_bwd_kernel<true, false>
-                         : (bulk ? lookup_fused_bwd_kernel<false, true> : lookup_fused_bwd_kernel<false, false>);
+  // LGU_BWD_FLOAT_ATOMICS=1: the first version's float compare-and-swap scatter instead of the fixed-point one
+  const char* fa = getenv("LGU_BWD_FLOAT_ATOMICS");
+  const bool fxp = !(fa != nullptr && fa[0] != '\0' && fa[0] != '0');
+  auto kern = accumulate ? (fxp ? lookup_fused_bwd_kernel<true, false, true> : lookup_fused_bwd_kernel<true, false, false>)
+              : bulk     ? (fxp ? lookup_fused_bwd_kernel<false, true, true> : lookup_fused_bwd_kernel<false, true, false>)
+                         : (fxp ? lookup_fused_bwd_kernel<false, false, true> : lookup_fused_bwd_kernel<false, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, flb::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("lgu_corr_lookup_fused_backward: cannot opt in to %d B of shared memory: %s", flb::kSmemBytes,
