@@ -294,10 +294,13 @@ def _generate_offsets(ofsMap, ofs_residual, t):
     o1 = F.interpolate(ofs_residual(F.avg_pool2d(t, kernel_size=2, stride=2)), (h, w))
     o0 = torch.tanh(per_Corr_Normalization(o0, [1, 2, 3])) * 4
     o1 = (torch.tanh(per_Corr_Normalization(o1, [1, 2, 3])) * 4 + o0) / 2
-    o0 = o0.permute(0, 2, 3, 1).contiguous()        # [E,h,w,98]: the layout the kernels read, materialised once
-    o1 = o1.permute(0, 2, 3, 1).contiguous()
-    z = torch.zeros_like(o0)
-    return [o0, o1, z.detach(), z.clone().detach()]
+    # [E,h,w,98] as PERMUTED VIEWS, like the reference (corr.py:129-134): `.contiguous()` at the samplers then copies,
+    # so the in-place centre-tap zeroing (quirk Q5) lands in a temporary and the stored centre values survive for the
+    # `offset[1] * mask` backward -- until cat / __getitem__ make the tensors contiguous, exactly as in the reference.
+    # zeros_like keeps the permuted strides, as it does there.
+    o0 = o0.permute(0, 2, 3, 1)
+    o1 = o1.permute(0, 2, 3, 1)
+    return [o0, o1, torch.zeros_like(o0).detach(), torch.zeros_like(o0).detach()]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -435,7 +438,18 @@ class CorrPool:
         return [self.free.pop() for _ in range(n)]
 
     def release(self, slots):
-        self.free.extend(reversed(list(slots)))
+        slots = list(slots)
+        self.check(slots)
+        if set(slots) & set(self.free):
+            raise RuntimeError("CorrPool: double release of a slot")
+        self.free.extend(reversed(slots))
+
+    def check(self, slots):
+        """Host-side range check of a slot list before it is uploaded: a device-side slot >= capacity would read and
+        write out of bounds through the TMA store maps and the offset pointers."""
+        bad = [s for s in slots if not 0 <= int(s) < self.capacity]
+        if bad or len(set(slots)) != len(slots):
+            raise RuntimeError(f"CorrPool: invalid slot list {slots} for capacity {self.capacity}")
 
 
 class PooledCorrBlock:
@@ -457,6 +471,10 @@ class PooledCorrBlock:
             offs = _generate_offsets(ofsMap, ofs_residual, t.float())
             mean, cov, det = GA.params(t.permute(0, 2, 3, 1).float())
             self.slots = pool.alloc(E)
+            # slots go back to the pool when the block is dropped in any way (self.corr = None, an exception, GC), not
+            # only through __getitem__ / release(); the box is shared with the finalizer and updated by cat / __getitem__
+            self._owned = [list(self.slots)]
+            self._finalizer = weakref.finalize(self, PooledCorrBlock._give_back, pool, self._owned)
             sl = torch.tensor(self.slots, dtype=torch.int32, device=fmap1.device)
             idx = sl.long()
             pool.off0[idx] = offs[0]
@@ -472,8 +490,20 @@ class PooledCorrBlock:
         self.theta = 2 * det.view(E, h, w)
         self._sl = sl
 
+    @staticmethod
+    def _give_back(pool, owned):
+        slots, owned[0] = owned[0], []
+        if slots:
+            pool.release(slots)
+
+    def _set_slots(self, slots):
+        self.slots = slots
+        self._owned[0] = list(slots)
+        self._sl = None
+
     def _slot_tensor(self, device):
         if self._sl is None or self._sl.numel() != len(self.slots):
+            self.pool.check(self.slots)
             self._sl = torch.tensor(self.slots, dtype=torch.int32, device=device)
         return self._sl
 
@@ -492,26 +522,28 @@ class PooledCorrBlock:
 
     def cat(self, other):
         assert other.pool is self.pool, "cat needs blocks of the same CorrPool"
-        self.slots = self.slots + other.slots
-        other.slots = []
+        taken = list(other.slots)
+        other._set_slots([])
+        self._set_slots(self.slots + taken)
         self.mean_n = torch.cat([self.mean_n, other.mean_n], 0)
         self.theta = torch.cat([self.theta, other.theta], 0)
-        self._sl = None
         return self
 
     def __getitem__(self, index):
         n = len(self.slots)
         keep = torch.arange(n)[index.cpu() if isinstance(index, torch.Tensor) else index].tolist()
         kept = set(keep)
-        self.pool.release([s for i, s in enumerate(self.slots) if i not in kept])
-        self.slots = [self.slots[i] for i in keep]
+        dropped = [s for i, s in enumerate(self.slots) if i not in kept]
+        self._set_slots([self.slots[i] for i in keep])
+        self.pool.release(dropped)
         self.mean_n, self.theta = self.mean_n[index], self.theta[index]
-        self._sl = None
         return self
 
     def release(self):
-        self.pool.release(self.slots)
+        """Return every slot to the pool (idempotent; also runs when the block is garbage-collected)."""
         self.slots = []
+        self._sl = None
+        PooledCorrBlock._give_back(self.pool, self._owned)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -79,7 +79,7 @@ __device__ __forceinline__ float sample_tap(const float* __restrict__ V, float x
 // branch-free phases so that every global load of a phase is in flight at once (the kernel is
 // latency-bound otherwise: ncu showed 16 serialized ~5k-cycle waits per warp with one phase per tap group):
 //   A: coords + offset records (coalesced float2 rows)   B: 4 corner gathers per tap   C: blend + smem transpose
-template <int R, bool DEFORM, int EXP = 0>
+template <int R, bool DEFORM>
 __global__ void __launch_bounds__(kLkThreads, 2)
 lookup_fwd_kernel(const float* __restrict__ volume, const float* __restrict__ coords, float* __restrict__ offset,
                   float* __restrict__ corr, int P, int W1, int H2, int W2, int tiles_per_edge) {
@@ -128,11 +128,10 @@ lookup_fwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
       const int t = min(ps * 32 + lane, TAPS - 1);
       const int i = t / RD, j = t - i * RD;                       // i: x tap, j: y tap (quirk Q1)
       ta[k][ps] = tap_setup<DEFORM>(x0[k], y0[k], o[k][ps].x, o[k][ps].y, i, j, R, H2, W2);
-      if (EXP & 2) { q[k][ps][0] = q[k][ps][1] = q[k][ps][2] = q[k][ps][3] = 1.0f; } else {
       q[k][ps][0] = __ldg(V[k] + ta[k][ps].i11);
       q[k][ps][1] = __ldg(V[k] + ta[k][ps].i21);
       q[k][ps][2] = __ldg(V[k] + ta[k][ps].i12);
-      q[k][ps][3] = __ldg(V[k] + ta[k][ps].i22); }
+      q[k][ps][3] = __ldg(V[k] + ta[k][ps].i22);
     }
   }
   // ---- phase C: blend, transpose through shared memory
@@ -154,10 +153,10 @@ lookup_fwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
   float* out = corr + (size_t)n * TAPS * P + p0 + lane;
 #pragma unroll 1
   for (int t = warp; t < TAPS; t += kLkWarps)
-    if (live && !((EXP & 4) && s_out[t][lane] != 12345.f)) out[(size_t)t * P] = s_out[t][lane];
+    if (live) out[(size_t)t * P] = s_out[t][lane];
   // ... and is zeroed in the caller's tensor LAST: a global store ahead of the gathers of the same warp
   // stalls them (measured 2.7x on the whole kernel), and no other warp reads this pixel's record.
-  if (DEFORM && !(EXP & 1) && lane < kLkPixPerWarp) {
+  if (DEFORM && lane < kLkPixPerWarp) {
     const int p = p0 + warp * kLkPixPerWarp + lane;
     if (p < P) reinterpret_cast<float2*>(offset)[((size_t)n * P + p) * TAPS + CENTER] = make_float2(0.0f, 0.0f);
   }
@@ -241,16 +240,7 @@ static int launch_lookup_fwd(const float* volume, const float* coords, float* of
       lookup_fwd_kernel<1, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
       break;
     case 2: lookup_fwd_kernel<2, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
-    case 3: {
-      const char* ex = getenv("LGU_EXP");
-      const int exv = ex ? atoi(ex) : 0;
-      if (exv == 1) lookup_fwd_kernel<3, DEFORM, 1><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
-      else if (exv == 2) lookup_fwd_kernel<3, DEFORM, 2><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
-      else if (exv == 4) lookup_fwd_kernel<3, DEFORM, 4><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
-      else if (exv == 7) lookup_fwd_kernel<3, DEFORM, 7><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
-      else lookup_fwd_kernel<3, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);
-      break;
-    }
+    case 3: lookup_fwd_kernel<3, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
     case 4: lookup_fwd_kernel<4, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles); break;
     default: {
       const long long npix = (long long)E * P;

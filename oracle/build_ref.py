@@ -6,6 +6,11 @@ kernels recompiled for B200:
 
   oracle/_ref/defCorrSample_ref*.so   <- /root/reference/offersample_LGS/{droid.cpp,*.cu}
   oracle/_ref/altcorr_ref*.so         <- /root/reference/src/altcorr_kernel.cu + oracle/altcorr_ref_binding.cpp
+  oracle/_ref/py/{corr,gaussianMask_cuda}.py  <- byte-for-byte copies of the reference's Python callers
+                                         (droid_slam/modules/corr.py, droid_slam/gaussianMask_cuda.py), staged
+                                         so that the GPU box -- where /root/reference does not exist -- can run
+                                         the reference's OWN CorrBlock / AltCorrBlock / GaussianMask on either
+                                         extension (tests/test_dropin_gpu.py)
 
 Sources are compiled from where they lie (never copied); outputs go only into
 oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun).  The
@@ -56,7 +61,57 @@ def build(verbose=False, force=False):
                  extra_cuda_cflags=["-O3"], extra_cflags=["-O3"],
                  verbose=verbose, is_python_module=False)
             _promote(d, "altcorr_ref")
+    if have_ref:
+        _stage_python()
     return {n: (_built(n) or [None])[0] for n in ("defCorrSample_ref", "altcorr_ref")}
+
+
+PY_FILES = {"corr.py": ("droid_slam", "modules", "corr.py"), "gaussianMask_cuda.py": ("droid_slam", "gaussianMask_cuda.py")}
+
+
+def _stage_python():
+    """Stage the reference's Python callers, unmodified, under oracle/_ref/py (git-ignored like the .so files)."""
+    import shutil
+    d = os.path.join(OUT, "py")
+    os.makedirs(d, exist_ok=True)
+    for name, rel in PY_FILES.items():
+        src = os.path.join(REF, *rel)
+        dst = os.path.join(d, name)
+        if os.path.isfile(src) and (not os.path.isfile(dst) or open(src, "rb").read() != open(dst, "rb").read()):
+            shutil.copyfile(src, dst)
+
+
+def staged_python():
+    d = os.path.join(OUT, "py")
+    return d if all(os.path.isfile(os.path.join(d, n)) for n in PY_FILES) else None
+
+
+def load_ref_python(def_corr_sample, droid_backends, tag):
+    """Execute the staged, unmodified reference modules with `import defCorrSample` / `import droid_backends`
+    resolved to the given objects (the compiled reference extension or the drop-in).  Returns (corr_module,
+    gaussianMask_cuda_module) under private names, so that several bindings can live in one process; None if the
+    files were not staged."""
+    import importlib.util
+    d = staged_python()
+    if d is None:
+        return None
+    saved = {k: sys.modules.get(k) for k in ("defCorrSample", "droid_backends")}
+    sys.modules["defCorrSample"] = def_corr_sample
+    sys.modules["droid_backends"] = droid_backends
+    try:
+        mods = []
+        for name in ("corr.py", "gaussianMask_cuda.py"):
+            spec = importlib.util.spec_from_file_location(f"ref_{name[:-3]}_{tag}", os.path.join(d, name))
+            m = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(m)
+            mods.append(m)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return tuple(mods)
 
 
 def _promote(build_dir, name):

@@ -326,7 +326,7 @@ def test_training_clip_fused_lookup_equals_per_op_autograd(accumulate):
             for c, w in zip(coords, wts):
                 out, mean_n, theta = blk(c)
                 outs.append(out.detach())
-                loss = loss + (out * w).mean() + 1e-3 * (mean_n.square().mean() + theta.mean())
+                loss = loss + (out * w * 0.05).sum() + 1e-2 * (mean_n.square().sum() + theta.sum())
             loss.backward()
             if blk._gacc is not None:
                 assert blk._gacc.grads is None, "FusedBuild.backward must consume (and free) the accumulators"
@@ -339,14 +339,18 @@ def test_training_clip_fused_lookup_equals_per_op_autograd(accumulate):
         assert (a - bb).abs().max().item() <= 2e-5, f"lookup {k}"
     names = ("fmap1", "fmap2", "ofsMap.weight", "ofs_residual.weight", "GA.map.weight", "GA.covMap.weight",
              "GA.meanMap.weight")
-    # the two graphs sum the same fp32 terms in different orders (shared-memory reductions in the fused backward); the
-    # feature-map gradients then pass through a 3072-term matmul with heavy cancellation -> compare against the RMS
+    # both graphs are pinned directly against the reference's compiled kernels in tests/test_dropin_gpu.py; here the two
+    # paths of this repo must agree to the same bar: |err| <= 1e-5 * max(1, max|per-op gradient|)
+    # (learned-parameter gradients are cuDNN / cuBLAS reductions of the per-pixel gradients over N = E*H*W positions:
+    # rounding-level differences of the summands accumulate as sqrt(N) -> 8 * 2^-24 * sqrt(N) relative, see test_dropin_gpu)
+    n_pos = b * n * 48 * 64
     report = []
     for name, a, bb in zip(names, grads_a, grads_b):
-        rms = bb.square().mean().sqrt().item()
+        tol = 1e-5 if name.startswith("fmap") else max(1e-5, 8 * 2.0 ** -24 * n_pos ** 0.5)
+        scale = max(1.0, bb.abs().max().item())
         err = (a - bb).abs().max().item()
-        report.append(f"{name}: max err {err:.3e}, rms {rms:.3e}")
-        assert err <= 2e-2 * rms + 1e-12, "; ".join(report)
+        report.append(f"{name}: max err {err:.3e}, max |g| {bb.abs().max().item():.3e}")
+        assert err <= tol * scale, "; ".join(report)
     print("\n".join(report))
 
 
