@@ -151,6 +151,17 @@ LGU_API int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const fl
                           const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                           int E, int H, int W, int num_levels, int radius, void* stream);
 
+/* lgu_corr_lookup_fused without the write-back of offset[1] (392 of its 4112 B per pixel): the block keeps its
+ * level-1 offsets PRISTINE (off1, read only) and a per-pixel running product of all masks so far in
+ * cum_mask [num_slots or E, H, W] (in/out; the caller initialises it to 1).  The lookup samples level 1 with
+ * off1 * (cum_mask * m) and stores cum_mask <- cum_mask * m -- the reference's cumulative `self.offset[1] *= mask`
+ * (quirk Q7) up to the association of the fp32 products ((o*m1)*m2 there, o*(m1*m2) here: <= 2 ulp of the offset).
+ * slots may be NULL (edge e lives in slot e; num_slots is then ignored). */
+LGU_API int lgu_corr_lookup_fused_cum(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                              const float* coords, const float* off0, const float* off1, float* cum_mask,
+                              float* corr, float* mask_out, const int32_t* slots, int num_slots,
+                              int E, int H, int W, int num_levels, int radius, void* stream);
+
 /* The same fused lookup with the BACKEND path's semantics (AltCorrBlock.corr_fn, corr.py:174-215, whose samplers
  * are lowMem_defSample.cu:27-134 and src/altcorr_kernel.cu:27-149): every bilinear corner is gated on its own
  * (quirk Q4) and fractions are x - floor(x).  lvl_l here is the volume of level 0 source maps against the level-l
@@ -161,6 +172,17 @@ LGU_API int lgu_altcorr_lookup_fused(const float* lvl0, const float* lvl1, const
                              const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                              int E, int H, int W, int num_levels, int radius,
                              int shared_offsets, int apply_mask, void* stream);
+
+/* lgu_altcorr_lookup_fused writing into a caller-owned destination: edge e's 196 rows go to row out_index[e] of
+ * `corr` ([E_out,196,H,W]; out_index NULL: row e), as fp32 (out_half = 0) or fp16 rounded to nearest (out_half = 1:
+ * what `update_op` reads under autocast, factor_graph.py:284-286).  `corr` may live in ANOTHER GPU's memory mapped into
+ * this process (CUDA IPC / peer access): a rank of the edge-sharded backend then returns its per-edge outputs through
+ * its own store stream over NVLink, with no collective on the data path (lgu-slam_b200/sharded.py). */
+LGU_API int lgu_altcorr_lookup_fused_into(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                  const float* coords, const float* off0, float* off1, void* corr,
+                                  const int32_t* out_index, int out_half, float* mask_out,
+                                  int E, int H, int W, int num_levels, int radius,
+                                  int shared_offsets, int apply_mask, void* stream);
 
 /* Backward of lgu_corr_lookup_fused = what autograd runs for corr.py:88-109 in training (4 x
  * defCorr_index_backward, the offset[1]*mask / sigmoid / var chain, corr_index_backward), in one launch:

@@ -303,6 +303,70 @@ def _generate_offsets(ofsMap, ofs_residual, t):
     return [o0, o1, torch.zeros_like(o0).detach(), torch.zeros_like(o0).detach()]
 
 
+class _Offsets(list):
+    """The block's `offset` list (corr.py:57,117-135) with the level-1 entry optionally kept FACTORED as
+    base * cum_mask: the fused inference lookup then leaves the 392 B / pixel of offset[1] untouched and only updates
+    the per-pixel running product of its masks (lgu_corr_lookup_fused_cum; the reference re-multiplies and re-writes
+    the whole tensor on every call, corr.py:99).  Reading `offset[1]` materialises base * cum_mask, i.e. exactly the
+    tensor the reference holds at that point; assigning to it (cat / __getitem__ / the per-operator path) stores the
+    given tensor and drops the factor."""
+
+    def __init__(self, items):
+        super().__init__(items)
+        self.cum = None
+
+    def _get(self, i):
+        v = list.__getitem__(self, i)
+        if i in (1, 1 - len(self)) and self.cum is not None:
+            v = v * self.cum.unsqueeze(-1)
+        return v
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._get(k) for k in range(*i.indices(len(self)))]
+        return self._get(i)
+
+    def __iter__(self):
+        return (self._get(k) for k in range(len(self)))
+
+    def __setitem__(self, i, v):
+        if i in (1, 1 - len(self)):
+            self.cum = None
+        list.__setitem__(self, i, v)
+
+    def _raw(self):
+        return [list.__getitem__(self, k) for k in range(len(self))]
+
+    def cat(self, other):
+        """corr.py:111-115 on the factored form: base and cum_mask are concatenated separately, so a block that grows
+        edge by edge keeps sampling with base * (m1 * m2 * ...) exactly like the edge-slot pool does."""
+        a, b = self._raw(), (other._raw() if isinstance(other, _Offsets) else list(other))
+        out = _Offsets([torch.cat([x, y], 0) for x, y in zip(a, b)])
+        oc = other.cum if isinstance(other, _Offsets) else None
+        if self.cum is not None or oc is not None:
+            ones = lambda t: torch.ones(t.shape[:3], dtype=torch.float32, device=t.device)
+            out.cum = torch.cat([self.cum if self.cum is not None else ones(a[1]),
+                                 oc if oc is not None else ones(b[1])], 0)
+        return out
+
+    def index(self, index):
+        """corr.py:137-141 on the factored form."""
+        out = _Offsets([t[index] for t in self._raw()])
+        if self.cum is not None:
+            out.cum = self.cum[index]
+        return out
+
+    def factored(self):
+        """(base, cum_mask) of level 1; creates the factor (ones) on first use."""
+        base = list.__getitem__(self, 1)
+        if not (base.is_contiguous() and base.dtype == torch.float32):
+            base = base.float().contiguous()
+            list.__setitem__(self, 1, base)
+        if self.cum is None:
+            self.cum = torch.ones(base.shape[:3], dtype=torch.float32, device=base.device)
+        return base, self.cum
+
+
 # ------------------------------------------------------------------------------------------------
 # CorrBlock
 # ------------------------------------------------------------------------------------------------
@@ -332,7 +396,7 @@ class CorrBlock:
             autocast_rounding = False
 
         t = torch.cat((fmap1.reshape(E, c, h, w), fmap2.reshape(E, c, h, w)), dim=1)
-        self.offset = _generate_offsets(ofsMap, ofs_residual, t.float())
+        self.offset = _Offsets(_generate_offsets(ofsMap, ofs_residual, t.float()))
         self.t = t.permute(0, 2, 3, 1).contiguous()
 
         if fused:
@@ -361,24 +425,30 @@ class CorrBlock:
                 and all(t.dtype == torch.float32 for t in self.corr_pyramid))
 
     def _needs_grad(self, coords):
-        return torch.is_grad_enabled() and any(t.requires_grad for t in self.corr_pyramid + self.offset[:2])
+        return torch.is_grad_enabled() and any(t.requires_grad for t in self.corr_pyramid + [
+            list.__getitem__(self.offset, 0), list.__getitem__(self.offset, 1)])
 
     def __call__(self, coords):
         batch, num, ht, wd, _ = coords.shape
         E, rd = batch * num, 2 * self.radius + 1
         if self._can_fuse_lookup(coords):
             # one TMA-staged launch: mask lookup + var + sigmoid + offset[1] *= mask + 4 deformable lookups + cat
-            for i in (0, 1):
-                if not (self.offset[i].is_contiguous() and self.offset[i].dtype == torch.float32):
-                    self.offset[i] = self.offset[i].float().contiguous()
+            if not isinstance(self.offset, _Offsets):        # a caller replaced the list: adopt it
+                self.offset = _Offsets(self.offset)
+            if not (self.offset[0].is_contiguous() and self.offset[0].dtype == torch.float32):
+                self.offset[0] = self.offset[0].float().contiguous()
             pyr = [t if t.is_contiguous() else t.contiguous() for t in self.corr_pyramid]
             c = coords.detach().reshape(E, ht, wd, 2).float().contiguous()
             if self._needs_grad(coords):                     # training: differentiable fused op (1 + 1 launches)
                 # (with the fused build, level gradients accumulate in self._gacc's persistent buffers)
+                off1 = self.offset[1]
+                if not (off1.is_contiguous() and off1.dtype == torch.float32):
+                    off1 = off1.float().contiguous()
                 out, self.offset[1], _ = FusedCorrLookup.apply(pyr[0], pyr[1], pyr[2], pyr[3], c, self.offset[0],
-                                                               self.offset[1], self._token, self._gacc)
-            else:                                            # inference: offset[1] updated in place
-                out = ops.corr_lookup_fused(pyr, c, self.offset[0], self.offset[1], self.radius)
+                                                               off1, self._token, self._gacc)
+            else:                                            # inference: offset[1] stays factored as base * cum_mask
+                base, cum = self.offset.factored()
+                out = ops.corr_lookup_fused(pyr, c, self.offset[0], base, self.radius, cum_mask=cum)
             return out.view(batch, num, -1, ht, wd), self.mean_n, self.theta
         coords = coords.permute(0, 1, 4, 2, 3).contiguous().view(E, 2, ht, wd)
 
@@ -396,13 +466,14 @@ class CorrBlock:
     def cat(self, other):
         for i in range(self.num_levels):
             self.corr_pyramid[i] = torch.cat([self.corr_pyramid[i], other.corr_pyramid[i]], 0)
-            self.offset[i] = torch.cat([self.offset[i], other.offset[i]], 0)
+        self.offset = _Offsets(self.offset).cat(other.offset) if not isinstance(self.offset, _Offsets) \
+            else self.offset.cat(other.offset)
         return self
 
     def __getitem__(self, index):
         for i in range(self.num_levels):
             self.corr_pyramid[i] = self.corr_pyramid[i][index]
-            self.offset[i] = self.offset[i][index]
+        self.offset = (self.offset if isinstance(self.offset, _Offsets) else _Offsets(self.offset)).index(index)
         return self
 
     @staticmethod
@@ -430,6 +501,7 @@ class CorrPool:
         nch = 2 * (2 * radius + 1) ** 2
         self.off0 = torch.zeros(capacity, h, w, nch, dtype=torch.float32, device=device)
         self.off1 = torch.zeros(capacity, h, w, nch, dtype=torch.float32, device=device)
+        self.cum = torch.ones(capacity, h, w, dtype=torch.float32, device=device)    # running product of each slot's masks (Q7)
         self.free = list(range(capacity - 1, -1, -1))
 
     def alloc(self, n):
@@ -479,6 +551,7 @@ class PooledCorrBlock:
             idx = sl.long()
             pool.off0[idx] = offs[0]
             pool.off1[idx] = offs[1]
+            pool.cum[idx] = 1.0
             frames = torch.cat((f1, f2), dim=0).contiguous()
             hi, lo = ops.pack_fmaps(frames, split=frames.dtype == torch.float32)
             ar = torch.arange(2 * E, dtype=torch.int32, device=frames.device)
@@ -517,7 +590,7 @@ class PooledCorrBlock:
         assert E == len(self.slots), f"coords carry {E} edges, the block holds {len(self.slots)}"
         c = coords.reshape(E, ht, wd, 2).float().contiguous()
         out = ops.corr_lookup_fused(self.pool.levels, c, self.pool.off0, self.pool.off1, self.radius,
-                                    slots=self._slot_tensor(c.device))
+                                    slots=self._slot_tensor(c.device), cum_mask=self.pool.cum)
         return out.view(batch, num, -1, ht, wd), self.mean_n.view(batch, num, ht, wd, 2), self.theta.view(batch, num, ht, wd)
 
     def cat(self, other):
@@ -629,7 +702,7 @@ class AltCorrBlock:
         t = torch.cat(((f1 * 4.0).permute(0, 3, 1, 2), (f2 * 4.0).permute(0, 3, 1, 2)), dim=1).float()
         return _generate_offsets(self.ofsMap, self.ofs_residual, t)
 
-    def _corr_materialized(self, coords, ii, jj):
+    def _corr_materialized(self, coords, ii, jj, out=None, out_index=None):
         B, N, H, W, S, _ = coords.shape
         assert B == 1 and S == 1, "the materialised path serves the reference's only call shape (B = S = 1)"
         planes = self._level_planes()
@@ -668,13 +741,17 @@ class AltCorrBlock:
                 if ent is not None and self._vol_bytes + nbytes <= self._vol_budget:
                     ent["vols"][s] = vols
                     self._vol_bytes += nbytes
+            # out / out_index: this pass's edges are written straight to their rows of the caller's buffer
+            dst = dict(out=out, out_index=(out_index[e].contiguous() if out_index is not None else
+                                           torch.arange(e.start, e.stop, dtype=torch.int32, device=c.device))) \
+                if out is not None else {}
             if self.strict_ref:
                 o, m = ops.altcorr_lookup_fused(vols, c[e], slab0[0], slab0[1], self.radius, shared_offsets=True,
-                                                apply_mask=False, return_mask=True)
+                                                apply_mask=False, return_mask=True, **dst)
             else:
                 o1 = off1[e].clone()                                      # updated in place: offset[1] * mask
                 o, m = ops.altcorr_lookup_fused(vols, c[e], off0[e].contiguous(), o1, self.radius, shared_offsets=False,
-                                                apply_mask=True, return_mask=True)
+                                                apply_mask=True, return_mask=True, **dst)
                 new_off1.append(o1)
             outs.append(o)
             masks.append(m)
@@ -687,14 +764,18 @@ class AltCorrBlock:
                 self.offset[1] = slab0[1]
         else:
             self.offset[1] = torch.cat(new_off1, 0) if len(new_off1) > 1 else new_off1[0]
-        out = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
-        return out.view(B, N, -1, H, W, 1)
+        if out is not None:
+            return out
+        res = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+        return res.view(B, N, -1, H, W, 1)
 
-    def corr_fn(self, coords, ii, jj):
+    def corr_fn(self, coords, ii, jj, out=None, out_index=None):
         B, N, H, W, S, _ = coords.shape
         rd = 2 * self.radius + 1
         if self.materialize and B == 1 and S == 1:
-            return self._corr_materialized(coords, ii, jj)
+            return self._corr_materialized(coords, ii, jj, out, out_index)
+        if out is not None:
+            raise RuntimeError("out= needs the materialised path (4 levels, r = 3, C = 128, B = S = 1)")
         f1 = self.pyramid[0][:, ii]
         f1 = f1.reshape((B * N,) + f1.shape[2:])
         f2 = self.pyramid[0][:, jj]
@@ -721,11 +802,16 @@ class AltCorrBlock:
             out.append(corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2))
         return torch.cat(out, dim=2)
 
-    def __call__(self, coords, ii, jj):
+    def __call__(self, coords, ii, jj, out=None, out_index=None):
+        """corr.py:238-249.  out / out_index (materialised path only): write edge e's [196,H,W] result into row
+        out_index[e] of `out` ([E_out,196,H,W], fp32 or fp16 -- possibly another GPU's memory, see sharded.PeerOutput)
+        instead of returning a new tensor; `out` is returned."""
         squeeze = coords.dim() == 5
         if squeeze:
             coords = coords.unsqueeze(dim=-2)
-        corr = self.corr_fn(coords, ii, jj)
+        corr = self.corr_fn(coords, ii, jj, out, out_index)
+        if out is not None:
+            return out
         if squeeze:
             corr = corr.squeeze(dim=-1)
         return corr.contiguous()

@@ -1,6 +1,10 @@
 // abi.cu -- library identification + error plumbing of the C ABI (include/lgu_corr.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 #define LGU_STR2(x) #x
 #define LGU_STR(x) LGU_STR2(x)
 #include "common.cuh"
@@ -22,6 +26,67 @@ int check_launch(const char* what) {
     return LGU_ERR_LAUNCH;
   }
   return LGU_OK;
+}
+
+// ---- one-time launch plumbing ------------------------------------------------------------------------------------
+static std::mutex g_plumb_mutex;
+
+int optin_smem(const void* kernel, int bytes, const char* who) {
+  struct Done { int dev; const void* kernel; int bytes; };
+  static std::vector<Done> done;                                // a few dozen (device, kernel) pairs at most
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_plumb_mutex);
+    for (const auto& d : done)
+      if (d.dev == dev && d.kernel == kernel && d.bytes >= bytes) return LGU_OK;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cannot opt in to %d B of shared memory: %s", who, bytes, cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  std::lock_guard<std::mutex> lk(g_plumb_mutex);
+  for (auto& d : done)
+    if (d.dev == dev && d.kernel == kernel) { d.bytes = bytes; return LGU_OK; }
+  done.push_back({dev, kernel, bytes});
+  return LGU_OK;
+}
+
+namespace {
+struct KeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) h = (h ^ x) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+struct KeyEq {
+  bool operator()(const MapKey& a, const MapKey& b) const { return memcmp(a.v, b.v, sizeof(a.v)) == 0; }
+};
+struct Map128 {
+  unsigned char b[128];
+};
+constexpr size_t kMapCacheMax = 512;
+std::unordered_map<MapKey, Map128, KeyHash, KeyEq>& map_cache() {
+  static std::unordered_map<MapKey, Map128, KeyHash, KeyEq> c;
+  return c;
+}
+}  // namespace
+
+bool map_cache_get(const MapKey& key, void* map128) {
+  std::lock_guard<std::mutex> lk(g_plumb_mutex);
+  auto it = map_cache().find(key);
+  if (it == map_cache().end()) return false;
+  memcpy(map128, it->second.b, 128);
+  return true;
+}
+void map_cache_put(const MapKey& key, const void* map128) {
+  std::lock_guard<std::mutex> lk(g_plumb_mutex);
+  if (map_cache().size() >= kMapCacheMax) map_cache().clear();   // geometry churn: start over (maps are cheap to redo)
+  Map128 m;
+  memcpy(m.b, map128, 128);
+  map_cache()[key] = m;
 }
 }  // namespace lgu
 

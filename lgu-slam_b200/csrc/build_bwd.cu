@@ -338,11 +338,7 @@ template <bool TR, bool TS>
 static int launch_bb_impl(const BbMaps& maps, const BbParams& prm, int E, cudaStream_t st) {
   using C_ = bb::Cfg<TR, TS>;
   auto kern = build_bwd_kernel<TR, TS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes);
-  if (e != cudaSuccess) {
-    set_error("lgu_build_backward_fmaps: cannot opt in to %d B of shared memory: %s", C_::kSmemBytes, cudaGetErrorString(e));
-    return LGU_ERR_LAUNCH;
-  }
+  if (int rc = optin_smem(reinterpret_cast<const void*>(kern), C_::kSmemBytes, "lgu_build_backward_fmaps")) return rc;
   kern<<<(unsigned)(E * prm.tiles_m), bb::kThreads, C_::kSmemBytes, st>>>(maps, prm);
   return check_launch("lgu_build_backward_fmaps");
 }

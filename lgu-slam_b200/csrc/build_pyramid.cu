@@ -573,11 +573,7 @@ static int launch_build(const CUtensorMap& mh, const CUtensorMap& ml, const CUte
                         cudaStream_t st) {
   using Cfg = BpCfg<PREC>;
   auto kern = (PREC == 1 && prm.wide) ? build_pyramid_kernel<PREC, PREC == 1> : build_pyramid_kernel<PREC, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-  if (e != cudaSuccess) {
-    set_error("lgu_build_pyramid: cannot opt in to %d B of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
-    return LGU_ERR_LAUNCH;
-  }
+  if (int rc = optin_smem(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes, "lgu_build_pyramid")) return rc;
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

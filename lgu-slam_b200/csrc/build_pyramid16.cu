@@ -295,11 +295,7 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
 }
 
 int launch_build16(const CUtensorMap& mh, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(build_pyramid16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b16::kSmemBytes);
-  if (e != cudaSuccess) {
-    set_error("lgu_build_pyramid: cannot opt in to %d B of shared memory: %s", b16::kSmemBytes, cudaGetErrorString(e));
-    return LGU_ERR_LAUNCH;
-  }
+  if (int rc = optin_smem(reinterpret_cast<const void*>(build_pyramid16_kernel), b16::kSmemBytes, "lgu_build_pyramid")) return rc;
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -22,6 +22,17 @@ int check_launch(const char* what);
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Host-side launch plumbing that is paid ONCE, not per call (abi.cu):
+//  * the opt-in to more than 48 KB of dynamic shared memory is a per-(device, kernel) function attribute;
+//  * a CUtensorMap depends only on (device, base pointer, geometry): encoded maps are kept in a small table, so the
+//    steady state of a frontend / backend loop (same pyramid storage, same shapes) re-encodes nothing.
+int optin_smem(const void* kernel, int bytes, const char* who);
+struct MapKey {
+  uint64_t v[12];
+};
+bool map_cache_get(const MapKey& key, void* map128);          // map128: CUtensorMap (128 bytes)
+void map_cache_put(const MapKey& key, const void* map128);
+
 __device__ __forceinline__ bool in_bounds(int h, int w, int H, int W) {
   return h >= 0 && h < H && w >= 0 && w < W;
 }

@@ -121,6 +121,12 @@ typedef CUresult (*FlEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static inline int make_slice_map(CUtensorMap* map, const float* base, long long nslices, int H2, int W2, int bw, int bh) {
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is expected to be 128 bytes");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const MapKey key = {{1u, (uint64_t)dev, (uint64_t)reinterpret_cast<uintptr_t>(base), (uint64_t)nslices, (uint64_t)H2,
+                       (uint64_t)W2, (uint64_t)bw, (uint64_t)bh, 0, 0, 0, 0}};
+  if (map_cache_get(key, map)) return LGU_OK;
   static FlEncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;
@@ -145,6 +151,7 @@ static inline int make_slice_map(CUtensorMap* map, const float* base, long long 
               W2, bw, bh);
     return LGU_ERR_LAUNCH;
   }
+  map_cache_put(key, map);
   return LGU_OK;
 }
 

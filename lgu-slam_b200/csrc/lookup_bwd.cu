@@ -321,11 +321,7 @@ static int launch_bwd_cfg(const float* volume, const float* coords, float* offse
   const size_t smem = (size_t)(((TAPS * (kBwTile + 1) + 3) & ~3) + WARPS * Qpad) * sizeof(float);
   auto kern = lookup_bwd_kernel<R, DEFORM, WARPS>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("lookup backward: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-      return LGU_ERR_LAUNCH;
-    }
+    if (int rc = optin_smem(reinterpret_cast<const void*>(kern), (int)smem, "lookup backward")) return rc;
   }
   const int tiles = (P + kBwTile - 1) / kBwTile;
   kern<<<(unsigned)((long long)E * tiles), WARPS * 32, smem, st>>>(volume, coords, offset, corr_grad, volume_grad,

@@ -22,227 +22,278 @@
 // Index logic is the reference's, bit for bit (defCorrSample_kernel.cu:56-67, corrSample_kernel.cu:52-60;
 // quirks Q1, Q3, Q5, Q7): levels 0, 2, 3 are bit-identical to defCorr_index_forward; level 1 differs only through
 // the fp32 rounding of the 9-tap variance / sigmoid that scales its offsets.
+#include <cuda_fp16.h>
 #include "fused_common.cuh"
 
 namespace lgu {
 
-#ifndef LGU_FWD_SLOTS
-#define LGU_FWD_SLOTS 2   // measured (E = 48): 2 slots 239 us, 3 slots 248 us, 4 slots (one CTA per SM) 409 us
-#endif
+// Round-2 structure (profiles/r02_fused_lookup.md).  The round-1 kernel ran 9 tap passes per pixel (2 per level with 17
+// of 32 lanes idle in every second one, plus the mask pass) at ~1000 warp instructions per pixel and was ISSUE-limited
+// (53 % issue-active with 4 warps per scheduler) while DRAM sat at 53 % of peak.  Here the 196 taps of a pixel are ONE
+// flat index space g = level*49 + tap walked in 7 passes of 32 lanes (6.1 needed); the 9 taps of the r=1 mask lookup
+// ride in the idle lanes of the last pass, which runs first.  Everything level-dependent (level coordinates, box
+// origin, box address and pitch, level extent) comes from a per-warp table in shared memory that the TMA-issuing lanes
+// fill, so the pass body is branch-free and identical for every lane: 2 LDS.128 + ~35 ALU + 4 LDS + 1 STS.
 namespace flf {
-constexpr int kSlots = LGU_FWD_SLOTS;                               // TMA ring depth of the forward (boxes in flight per warp)
-constexpr int kSmemBoxes = fl::kWarps * kSlots * fl::kSlotBytes;
-constexpr int kSmemBytes = kSmemBoxes + fl::kSmemOut + fl::kWarps * kSlots * 8;
+constexpr int kRing = 2;                                            // TMA ring depth (boxes in flight per warp)
+constexpr int kPasses = 7;                                           // ceil(196 / 32)
+constexpr int kRecBytes = 32;                                        // one table record = 2 x 16 B
+constexpr int kRingBytes = fl::kWarps * kRing * fl::kSlotBytes;     // 53,248 B
+constexpr int kSmemTab = fl::kWarps * kRing * fl::LEVELS * kRecBytes;   // 2,048 B
+constexpr int kSmemBars = fl::kWarps * kRing * 8;
+constexpr int kFwdSmemBytes = kRingBytes + fl::kSmemOut + kSmemTab + kSmemBars;
 }  // namespace flf
 
 struct FusedLookupParams {
   const float* lvl[4];
   const float* coords;   // [E,P,2] (x,y) level-0 units
   const float* off0;     // [E,P,49,2]  read only (its centre tap is read as 0, Q5)
-  float* off1;           // [E,P,49,2]  <- off1 * mask (Q7), every tap; the centre tap is read as 0
-  float* out;            // [E,196,P]
+  float* off1;           // [E,P,49,2]  write_back: <- off1 * mask (Q7), every tap; the centre tap is read as 0
+  void* out;             // [E_out,196,P] fp32 (or fp16, see HALF): edge n is written to row out_index[n] (or n)
+  const int32_t* out_index;    // [E] or null: destination row of every edge -- lets a rank of the sharded backend store
+                               // straight into the gathered buffer on another GPU (NVLink peer memory), sharded.py
   float* mask_out;       // [E,P] or null: the sigmoid(var) mask of this call
+  float* cum_mask;       // [slots,P] or null: running product of the masks of all calls so far (in/out); off1 stays pristine
   int P, tiles_per_edge;
   int H2[4], W2[4];
   long long off_edge_stride;   // float2 elements between the offset slabs of consecutive edges (0: every edge reads slab 0, Q2)
-  int apply_mask;              // 1: off1 <- off1 * sigmoid(var) of this call (CorrBlock); 0: offsets are used as given
+  int apply_mask;              // 1: level-1 offsets are scaled by sigmoid(var) of this call (CorrBlock); 0: used as given
   const int32_t* slots;        // [E] or null: edge n lives in pyramid / offset slot slots[n] (edge-slot pool)
 };
 
-template <bool PC>   // PC: per-corner gating (lowMem / altcorr semantics, Q4) instead of top-left gating (Q3)
+__device__ __forceinline__ float4 flf_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float flf_lds(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// PC: per-corner gating (lowMem / altcorr semantics, Q4) instead of top-left gating (Q3)
+// HALF: the 196-channel rows are stored as fp16 (round-to-nearest) -- what `update_op` reads under autocast
+//       (factor_graph.py:284-286); halves the output stream (and the NVLink traffic of the sharded backend)
+template <bool PC, bool HALF>
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupParams prm) {
   using namespace fl;
-  constexpr int kSlots = flf::kSlots, kSmemBoxes = flf::kSmemBoxes;
+  using namespace flf;
   extern __shared__ __align__(1024) uint8_t smem[];              // no static shared memory: base is 1024-aligned
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* boxes = reinterpret_cast<float*>(smem) + warp * kSlots * kSlotFloats;
-  float* s_out = reinterpret_cast<float*>(smem + kSmemBoxes);    // [CH][kOutPitch]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBoxes + kSmemOut) + warp * kSlots;
+  float* s_out = reinterpret_cast<float*>(smem + kRingBytes);    // [CH][kOutPitch]
+  const uint32_t box_base = fl_smem_u32(smem) + warp * kRing * kSlotBytes;
+  const uint32_t tab_base = fl_smem_u32(smem) + kRingBytes + kSmemOut + warp * kRing * LEVELS * kRecBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes + kSmemOut + kSmemTab) + warp * kRing;
 
   const int P = prm.P;
   const int n = blockIdx.x / prm.tiles_per_edge;
   const int p0 = (blockIdx.x - n * prm.tiles_per_edge) * kTile;
-  const int pw = p0 + warp * kPixPerWarp;                       // first pixel of this warp
+  const int pw = p0 + warp * kPixPerWarp;                       // first pixel of this warp (tiles are always full)
   const int ns = prm.slots != nullptr ? __ldg(prm.slots + n) : n;   // storage slot of this edge (pyramid, offsets)
 
+  // ---- per-lane level record: lanes 0..3 own level `lane` of the warp's table (static half written once)
+  const int myl = lane & 3;
+  const int myW2 = prm.W2[myl], myH2 = prm.H2[myl];
+  if (lane < LEVELS * kRing) {
+    const int q = lane >> 2;                                    // slot
+    const int boff = myl == 0 ? kOff0 : (myl == 1 ? kOff1 : (myl == 2 ? kOff2 : kOff3));
+    const int bw = myl < 2 ? kBW01 : kBW23;
+    const uint32_t rec = tab_base + (q * LEVELS + myl) * kRecBytes;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rec + 16), "r"(box_base + q * kSlotBytes + boff * 4),
+                 "r"(bw * 4), "r"(myW2), "r"(myH2)
+                 : "memory");
+  }
   if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < kSlots; ++q) fl_mbar_init(bars + q, 1);
+    for (int q = 0; q < kRing; ++q) fl_mbar_init(bars + q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
 
   // coords of the warp's pixels: lane k (< 4) loads pixel k, everyone gets them by shuffle
   float2 cmine = make_float2(0.0f, 0.0f);
-  if (lane < kPixPerWarp)
-    cmine = __ldg(reinterpret_cast<const float2*>(prm.coords) + (size_t)n * P + min(pw + lane, P - 1));
+  if (lane < kPixPerWarp) cmine = __ldg(reinterpret_cast<const float2*>(prm.coords) + (size_t)n * P + pw + lane);
 
-  auto issue = [&](int k, float cx, float cy) {                 // lane 0 only
-    const int slot = k % kSlots;
-    const int pix = ns * P + min(pw + k, P - 1);
-    float* dst = boxes + slot * kSlotFloats;
-    fl_mbar_expect_tx(bars + slot, kSlotBytes);
-    float sx = cx, sy = cy;
+  // Issue the four boxes of pixel k: lane l (< 4) scales the coordinates to level l (coords / 2^l as successive exact
+  // halvings, corr.py:103), derives the box origin and writes the dynamic half of its record; lane 0 launches the copies.
+  auto issue = [&](int k, float cx, float cy) {
+    const int slot = k % kRing;
 #pragma unroll
-    for (int l = 0; l < LEVELS; ++l) {
-      const int fx = floor_to_int(sx), fy = floor_to_int(sy);
-      const int reach = l < 2 ? 7 : 3;
-      const int xb = box_origin_x(fx, reach, prm.W2[l]), yb = box_origin_y(fy, reach, prm.H2[l]);
-      const int o = l == 0 ? kOff0 : (l == 1 ? kOff1 : (l == 2 ? kOff2 : kOff3));
-      fl_tma_box(dst + o, &maps.m[l], bars + slot, xb, yb, pix);
-      sx = __fmul_rn(sx, 0.5f);
-      sy = __fmul_rn(sy, 0.5f);
+    for (int q = 1; q < LEVELS; ++q)
+      if (myl >= q) { cx = __fmul_rn(cx, 0.5f); cy = __fmul_rn(cy, 0.5f); }
+    const int reach = myl < 2 ? 7 : 3;
+    const int xb = box_origin_x(floor_to_int(cx), reach, myW2), yb = box_origin_y(floor_to_int(cy), reach, myH2);
+    if (lane < LEVELS)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tab_base + (slot * LEVELS + myl) * kRecBytes),
+                   "r"(__float_as_int(cx)), "r"(__float_as_int(cy)), "r"(xb), "r"(yb)
+                   : "memory");
+    int xs[LEVELS], ys[LEVELS];
+#pragma unroll
+    for (int l = 0; l < LEVELS; ++l) { xs[l] = __shfl_sync(0xffffffffu, xb, l); ys[l] = __shfl_sync(0xffffffffu, yb, l); }
+    if (lane == 0) {
+      const int pix = ns * P + pw + k;
+      const uint32_t dst = box_base + slot * kSlotBytes;
+      fl_mbar_expect_tx(bars + slot, kSlotBytes);
+#pragma unroll
+      for (int l = 0; l < LEVELS; ++l) {
+        const int o = l == 0 ? kOff0 : (l == 1 ? kOff1 : (l == 2 ? kOff2 : kOff3));
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                dst + o * 4),
+            "l"(&maps.m[l]), "r"(fl_smem_u32(bars + slot)), "r"(xs[l]), "r"(ys[l]), "r"(pix)
+            : "memory");
+      }
     }
+    __syncwarp();                                               // table records visible to the whole warp
   };
 #pragma unroll
-  for (int q = 0; q < kSlots && q < kPixPerWarp; ++q) {
-    const float cqx = __shfl_sync(0xffffffffu, cmine.x, q), cqy = __shfl_sync(0xffffffffu, cmine.y, q);
-    if (lane == 0) issue(q, cqx, cqy);
+  for (int q = 0; q < kRing && q < kPixPerWarp; ++q)
+    issue(q, __shfl_sync(0xffffffffu, cmine.x, q), __shfl_sync(0xffffffffu, cmine.y, q));
+
+  // ---- per-lane tap constants of the 7 passes: g = pass*32 + lane -> (level, i - r, j - r); the mask taps (r = 1 on
+  // level 1) sit on lanes 4..12 of the last pass, whose lanes 0..3 are taps 45..48 of level 3
+  constexpr int CENTER = R * RD + R;                            // tap 24
+  int recoff[kPasses], di[kPasses], dj[kPasses];
+#pragma unroll
+  for (int ps = 0; ps < kPasses; ++ps) {
+    const int g = ps * 32 + lane;
+    int l = min(g, CH - 1) / TAPS;
+    int t = min(g, CH - 1) - l * TAPS;
+    int i = t / RD, j = t - i * RD, r = R;
+    if (ps == kPasses - 1 && lane >= 4) {                       // mask taps (lanes 13..31: harmless duplicates of tap 8)
+      const int mt = min(lane - 4, 8);
+      l = 1; r = 1; i = mt / 3; j = mt - i * 3;
+    }
+    recoff[ps] = l * kRecBytes;
+    di[ps] = i - r;
+    dj[ps] = j - r;
   }
+  const bool is_mask_lane = lane >= 4 && lane < 13;
 
-  const int t0 = lane, t1 = lane + 32;                          // this lane's taps (t1 valid for lane < 17)
-  const int i0 = t0 / RD, j0 = t0 - i0 * RD;
-  const int t1c = min(t1, TAPS - 1);
-  const int i1 = t1c / RD, j1 = t1c - i1 * RD;
-  const bool has1 = t1 < TAPS;
-  constexpr int CENTER = R * RD + R;                            // tap 24 (lane 24, pass 0)
-  const int mi = min(lane, 8) / 3, mj = min(lane, 8) - mi * 3;  // r=1 mask taps on lanes 0..8
-
-  float2 a0, a1, b0, b1;                                        // level-0 / level-1 offsets of taps t0, t1
+  // offsets of the deformable levels: flat taps g < 98 live in passes 0..3 (pass 3: lanes 0, 1 only)
+  float2 onext[4];
   auto load_offsets = [&](int k) {
-    const size_t opix = (size_t)ns * prm.off_edge_stride + (size_t)min(pw + k, P - 1) * TAPS;
+    const size_t opix = (size_t)ns * prm.off_edge_stride + (size_t)(pw + k) * TAPS;
     const float2* O0 = reinterpret_cast<const float2*>(prm.off0) + opix;
     const float2* O1 = reinterpret_cast<const float2*>(prm.off1) + opix;
-    a0 = O0[t0]; a1 = O0[t1c]; b0 = O1[t0]; b1 = O1[t1c];
+    onext[0] = O0[lane];
+    onext[1] = lane < 17 ? O0[32 + lane] : O1[lane - 17];
+    onext[2] = O1[15 + lane];
+    onext[3] = lane < 2 ? O1[47 + lane] : make_float2(0.0f, 0.0f);
   };
   load_offsets(0);
 
-  // One deformable level: both tap passes fetched together (8 shared loads in flight), then blended.
-  auto deform_level = [&](const float* bx, const float* V, int H2, int W2, float cx, float cy, float2 oa, float2 ob,
-                          float* so) {
-    const int xb = box_origin_x(floor_to_int(cx), 7, W2), yb = box_origin_y(floor_to_int(cy), 7, H2);
-    Tap ta, tb;
-    {
-      const float px = __fadd_rn(oa.x, cx), py = __fadd_rn(oa.y, cy);        // defCorrSample_kernel.cu:56-61
-      const int fx = floor_to_int(px), fy = floor_to_int(py);
-      ta.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);     // lowMem_defSample.cu:87-88 uses floor()
-      ta.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
-      tap_fetch<kBW01, kBH01, PC>(ta, bx, xb, yb, fx, fy, i0, j0, R, H2, W2);
-    }
-    {
-      const float px = __fadd_rn(ob.x, cx), py = __fadd_rn(ob.y, cy);
-      const int fx = floor_to_int(px), fy = floor_to_int(py);
-      tb.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);
-      tb.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
-      tap_fetch<kBW01, kBH01, PC>(tb, bx, xb, yb, fx, fy, i1, j1, R, H2, W2);
-    }
-    if (__any_sync(0xffffffffu, ta.miss || tb.miss)) {          // |offset| >= 4: rare
-      tap_patch_from_global<PC>(ta, V, H2, W2);
-      tap_patch_from_global<PC>(tb, V, H2, W2);
-    }
-    so[t0 * kOutPitch] = tap_value(ta);
-    if (has1) so[t1 * kOutPitch] = tap_value(tb);
-  };
-  // One zero-offset level (levels 2, 3): px = 0 + c, so floor / fraction are warp-uniform.
-  auto uniform_level = [&](const float* bx, const float* V, int H2, int W2, float cx, float cy, float* so) {
-    const float px = __fadd_rn(0.0f, cx), py = __fadd_rn(0.0f, cy);
+  // One bilinear tap of the flat index space against the staged boxes (defCorrSample_kernel.cu:56-86).
+  auto tap = [&](int slot, int ps, float2 o, size_t pix) -> float {
+    const uint32_t rec = tab_base + slot * LEVELS * kRecBytes + recoff[ps];
+    const float4 a = flf_lds128(rec);
+    const float4 b = flf_lds128(rec + 16);
+    const int xb = __float_as_int(a.z), yb = __float_as_int(a.w);
+    const uint32_t baddr = (uint32_t)__float_as_int(b.x);
+    const int pitch = __float_as_int(b.y);                      // box row pitch in bytes (80 or 48)
+    const int W2 = __float_as_int(b.z), H2 = __float_as_int(b.w);
+    const float px = __fadd_rn(o.x, a.x), py = __fadd_rn(o.y, a.y);
     const int fx = floor_to_int(px), fy = floor_to_int(py);
-    const int xb = box_origin_x(fx, 3, W2), yb = box_origin_y(fy, 3, H2);
-    Tap ta, tb;
-    ta.dx = tb.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);
-    ta.dy = tb.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
-    tap_fetch<kBW23, kBH23, PC>(ta, bx, xb, yb, fx, fy, i0, j0, R, H2, W2);
-    tap_fetch<kBW23, kBH23, PC>(tb, bx, xb, yb, fx, fy, i1, j1, R, H2, W2);
-    if (__any_sync(0xffffffffu, ta.miss || tb.miss)) {          // only for clamped (far out-of-range) coords
-      tap_patch_from_global<PC>(ta, V, H2, W2);
-      tap_patch_from_global<PC>(tb, V, H2, W2);
+    Tap t;
+    t.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);     // lowMem_defSample.cu:87-88 uses floor()
+    t.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
+    t.x1 = (int)((unsigned)fx + (unsigned)di[ps]);
+    t.y1 = (int)((unsigned)fy + (unsigned)dj[ps]);
+    t.gate = PC ? true : (((unsigned)t.x1 < (unsigned)W2) && ((unsigned)t.y1 < (unsigned)H2));   // Q3 / Q4
+    const unsigned rx = (unsigned)t.x1 - (unsigned)xb, ry = (unsigned)t.y1 - (unsigned)yb;
+    // box extents from the pitch: 20 x 16 (pitch 80) or 12 x 8 (pitch 48)
+    const bool inbox = rx < (unsigned)((pitch >> 2) - 1) && ry < (unsigned)(pitch == kBW01 * 4 ? kBH01 - 1 : kBH23 - 1);
+    t.miss = t.gate && !inbox;
+    const uint32_t ad = baddr + (inbox ? ry * (unsigned)pitch + rx * 4u : 0u);
+    t.q11 = flf_lds(ad);
+    t.q21 = flf_lds(ad + 4);
+    t.q12 = flf_lds(ad + pitch);
+    t.q22 = flf_lds(ad + pitch + 4);
+    if (__any_sync(0xffffffffu, t.miss)) {                      // |offset| >= 4 or clamped far-out coords: rare
+      const int l = recoff[ps] / kRecBytes;
+      tap_patch_from_global<PC>(t, prm.lvl[l] + pix * (size_t)(H2 * W2), H2, W2);
     }
-    so[t0 * kOutPitch] = tap_value(ta);
-    if (has1) so[t1 * kOutPitch] = tap_value(tb);
+    return tap_value(t);
   };
 
 #pragma unroll 1
   for (int k = 0; k < kPixPerWarp; ++k) {
-    const int slot = k % kSlots;
+    const int slot = k % kRing;
     const int p = pw + k;
-    const bool live = p < P;                                    // warp-uniform
-    const size_t pix = (size_t)ns * P + min(p, P - 1);          // slice index in the pyramid storage
-    const float x0 = __shfl_sync(0xffffffffu, cmine.x, k), y0 = __shfl_sync(0xffffffffu, cmine.y, k);
-    float2 o00 = a0, o01 = a1, o10 = b0, o11 = b1;              // this pixel's offsets (loaded one iteration ahead)
-    if (lane == CENTER) o00 = make_float2(0.0f, 0.0f);          // Q5: the centre tap reads as 0
+    const size_t pix = (size_t)ns * P + p;                      // slice index in the pyramid storage
+    float2 o[4] = {onext[0], onext[1], onext[2], onext[3]};     // this pixel's offsets (loaded one iteration ahead)
     if (k + 1 < kPixPerWarp) load_offsets(k + 1);
+    float cum = 1.0f;
+    if (prm.cum_mask != nullptr) cum = __ldg(prm.cum_mask + (size_t)ns * P + p);
 
-    fl_mbar_wait(bars + slot, (k / kSlots) & 1);
-    const float* box = boxes + slot * kSlotFloats;
+    fl_mbar_wait(bars + slot, (k / kRing) & 1);
     float* so = s_out + warp * kPixPerWarp + k;                 // column of this pixel in the output tile
 
-    // ---------------- level 1: r=1 mask lookup (corrSample_kernel.cu:52-77) -> var -> sigmoid
-    const float x1c = __fmul_rn(x0, 0.5f), y1c = __fmul_rn(y0, 0.5f);
-    const float* V1 = prm.lvl[1] + pix * (size_t)(prm.H2[1] * prm.W2[1]);
+    // ---------------- last pass first: level-3 taps 45..48 (lanes 0..3) + the r=1 mask taps on level 1 (lanes 4..12,
+    // corrSample_kernel.cu:52-77) -> unbiased variance over the 9 taps (torch.var default, corr.py:96) -> sigmoid
     float m;
     {
-      const int H2 = prm.H2[1], W2 = prm.W2[1];
-      const int fx = floor_to_int(x1c), fy = floor_to_int(y1c);
-      const int xb = box_origin_x(fx, 7, W2), yb = box_origin_y(fy, 7, H2);
-      Tap tm;
-      tm.dx = __fsub_rn(x1c, floorf(x1c));
-      tm.dy = __fsub_rn(y1c, floorf(y1c));
-      tap_fetch<kBW01, kBH01, PC>(tm, box + kOff1, xb, yb, fx, fy, mi, mj, 1, H2, W2);
-      if (__any_sync(0xffffffffu, tm.miss)) tap_patch_from_global<PC>(tm, V1, H2, W2);
-      const float v = lane < 9 ? tap_value(tm) : 0.0f;
-      // unbiased variance over the 9 taps (torch.var default, corr.py:96), then sigmoid (corr.py:97)
-      float s = v;
+      const float v = tap(slot, kPasses - 1, make_float2(0.0f, 0.0f), pix);
+      if (lane < 4) so[((kPasses - 1) * 32 + lane) * kOutPitch] = v;
+      const float vm = is_mask_lane ? v : 0.0f;
+      float s = vm;
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);    // lanes 9..15 contribute 0
+      for (int sh = 8; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);    // lanes 0..3, 13..15 contribute 0
       const float mean = __shfl_sync(0xffffffffu, s, 0) / 9.0f;
-      const float d = lane < 9 ? (v - mean) : 0.0f;
+      const float d = is_mask_lane ? (vm - mean) : 0.0f;
       float ss = d * d;
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      for (int sh = 8; sh > 0; sh >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sh);
       const float var = __shfl_sync(0xffffffffu, ss, 0) * 0.125f;
       m = 1.0f / (1.0f + expf(-var));
     }
-    // offset[1] <- offset[1] * mask (Q7) for every tap; the lookup itself reads the centre tap as 0 (Q5)
+    // offset[1] <- offset[1] * mask (Q7) for every tap of level 1 (flat taps 49..97: pass 1 lanes >= 17, pass 2, pass 3
+    // lanes 0..1); with a cumulative-mask buffer the stored offsets stay pristine and the product of all masks so far
+    // is applied instead
     if (prm.apply_mask) {
-      o10 = make_float2(__fmul_rn(o10.x, m), __fmul_rn(o10.y, m));
-      o11 = make_float2(__fmul_rn(o11.x, m), __fmul_rn(o11.y, m));
-    }
-    const float2 o10_store = o10;
-    if (lane == CENTER) o10 = make_float2(0.0f, 0.0f);
-
-    deform_level(box + kOff1, V1, prm.H2[1], prm.W2[1], x1c, y1c, o10, o11, so + TAPS * kOutPitch);
-    deform_level(box + kOff0, prm.lvl[0] + pix * (size_t)(prm.H2[0] * prm.W2[0]), prm.H2[0], prm.W2[0], x0, y0, o00,
-                 o01, so);
-    const float x2c = __fmul_rn(x1c, 0.5f), y2c = __fmul_rn(y1c, 0.5f);
-    uniform_level(box + kOff2, prm.lvl[2] + pix * (size_t)(prm.H2[2] * prm.W2[2]), prm.H2[2], prm.W2[2], x2c, y2c,
-                  so + 2 * TAPS * kOutPitch);
-    uniform_level(box + kOff3, prm.lvl[3] + pix * (size_t)(prm.H2[3] * prm.W2[3]), prm.H2[3], prm.W2[3],
-                  __fmul_rn(x2c, 0.5f), __fmul_rn(y2c, 0.5f), so + 3 * TAPS * kOutPitch);
-
-    // ---------------- in-place side effects on the caller's offsets
-    if (live) {
-      if (prm.apply_mask) {
-        float2* O1 = reinterpret_cast<float2*>(prm.off1) + (size_t)ns * prm.off_edge_stride + (size_t)min(p, P - 1) * TAPS;
-        O1[t0] = o10_store;
-        if (has1) O1[t1] = o11;
+      const float mm = prm.cum_mask != nullptr ? __fmul_rn(cum, m) : m;
+      if (lane >= 17) o[1] = make_float2(__fmul_rn(o[1].x, mm), __fmul_rn(o[1].y, mm));
+      o[2] = make_float2(__fmul_rn(o[2].x, mm), __fmul_rn(o[2].y, mm));
+      o[3] = make_float2(__fmul_rn(o[3].x, mm), __fmul_rn(o[3].y, mm));         // lanes >= 2 hold zeros
+      if (prm.cum_mask != nullptr) {
+        if (lane == 0) prm.cum_mask[(size_t)ns * P + p] = mm;
+      } else {
+        float2* O1 = reinterpret_cast<float2*>(prm.off1) + (size_t)ns * prm.off_edge_stride + (size_t)p * TAPS;
+        if (lane >= 17) O1[lane - 17] = o[1];
+        O1[15 + lane] = o[2];
+        if (lane < 2) O1[47 + lane] = o[3];
       }
-      if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[(size_t)n * P + p] = m;
     }
+    if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[(size_t)n * P + p] = m;
+    // Q5: the centre taps read as 0 (flat taps 24 and 49 + 24 = 73 = pass 2, lane 9)
+    if (lane == CENTER) o[0] = make_float2(0.0f, 0.0f);
+    if (lane == TAPS + CENTER - 64) o[2] = make_float2(0.0f, 0.0f);
+
+#pragma unroll
+    for (int ps = 0; ps < kPasses - 1; ++ps) {
+      const float v = tap(slot, ps, ps < 4 ? o[ps] : make_float2(0.0f, 0.0f), pix);
+      so[(ps * 32 + lane) * kOutPitch] = v;
+    }
+
     __syncwarp();                                               // every lane is done with this slot
-    if (k + kSlots < kPixPerWarp) {
-      const float nx = __shfl_sync(0xffffffffu, cmine.x, k + kSlots), ny = __shfl_sync(0xffffffffu, cmine.y, k + kSlots);
-      if (lane == 0) issue(k + kSlots, nx, ny);
-    }
+    if (k + kRing < kPixPerWarp)
+      issue(k + kRing, __shfl_sync(0xffffffffu, cmine.x, k + kRing), __shfl_sync(0xffffffffu, cmine.y, k + kRing));
   }
 
   __syncthreads();
-  const bool live = (p0 + lane) < P;
-  float* out = prm.out + (size_t)n * CH * P + p0 + lane;
+  const size_t row = (size_t)(prm.out_index != nullptr ? __ldg(prm.out_index + n) : n) * CH * P + p0 + lane;
   const float* srow = s_out + lane;
+  if (HALF) {
+    __half* out = reinterpret_cast<__half*>(prm.out) + row;
 #pragma unroll 4
-  for (int ch = warp; ch < CH; ch += kWarps)
-    if (live) __stcs(out + (size_t)ch * P, srow[ch * kOutPitch]);
+    for (int ch = warp; ch < CH; ch += kWarps) out[(size_t)ch * P] = __float2half_rn(srow[ch * kOutPitch]);
+  } else {
+    float* out = reinterpret_cast<float*>(prm.out) + row;
+#pragma unroll 4
+    for (int ch = warp; ch < CH; ch += kWarps) __stcs(out + (size_t)ch * P, srow[ch * kOutPitch]);
+  }
 }
 
 }  // namespace lgu
@@ -251,13 +302,23 @@ namespace lgu {
 static int launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                const float* coords, const float* off0, float* off1, float* corr, float* mask_out, int E,
                                int H, int W, int num_levels, int radius, int per_corner, int shared_offsets,
-                               int apply_mask, const int32_t* slots, int num_slots, void* stream);
+                               int apply_mask, const int32_t* slots, int num_slots, float* cum_mask,
+                               const int32_t* out_index, int out_half, void* stream);
 }
 extern "C" int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                      const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                      int E, int H, int W, int num_levels, int radius, void* stream) {
   return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, corr, mask_out, E, H, W, num_levels,
-                                  radius, 0, 0, 1, nullptr, E, stream);
+                                  radius, 0, 0, 1, nullptr, E, nullptr, nullptr, 0, stream);
+}
+extern "C" int lgu_corr_lookup_fused_cum(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                         const float* coords, const float* off0, const float* off1, float* cum_mask,
+                                         float* corr, float* mask_out, const int32_t* slots, int num_slots, int E, int H,
+                                         int W, int num_levels, int radius, void* stream) {
+  LGU_REQUIRE(E == 0 || cum_mask != nullptr, "lgu_corr_lookup_fused_cum: null cumulative-mask buffer");
+  LGU_REQUIRE(slots == nullptr || num_slots > 0, "lgu_corr_lookup_fused_cum: bad pool size %d", num_slots);
+  return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, const_cast<float*>(off1), corr, mask_out, E, H, W,
+                                  num_levels, radius, 0, 0, 1, slots, slots != nullptr ? num_slots : E, cum_mask, nullptr, 0, stream);
 }
 extern "C" int lgu_corr_lookup_fused_slots(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                            const float* coords, const float* off0, float* off1, float* corr,
@@ -266,20 +327,29 @@ extern "C" int lgu_corr_lookup_fused_slots(const float* lvl0, const float* lvl1,
   LGU_REQUIRE(E == 0 || slots != nullptr, "lgu_corr_lookup_fused_slots: null slot list");
   LGU_REQUIRE(num_slots > 0, "lgu_corr_lookup_fused_slots: bad pool size %d", num_slots);
   return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, corr, mask_out, E, H, W, num_levels,
-                                  radius, 0, 0, 1, slots, num_slots, stream);
+                                  radius, 0, 0, 1, slots, num_slots, nullptr, nullptr, 0, stream);
 }
 extern "C" int lgu_altcorr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                         const float* coords, const float* off0, float* off1, float* corr,
                                         float* mask_out, int E, int H, int W, int num_levels, int radius,
                                         int shared_offsets, int apply_mask, void* stream) {
   return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, corr, mask_out, E, H, W, num_levels,
-                                  radius, 1, shared_offsets, apply_mask, nullptr, E, stream);
+                                  radius, 1, shared_offsets, apply_mask, nullptr, E, nullptr, nullptr, 0, stream);
+}
+extern "C" int lgu_altcorr_lookup_fused_into(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                             const float* coords, const float* off0, float* off1, void* corr,
+                                             const int32_t* out_index, int out_half, float* mask_out, int E, int H, int W,
+                                             int num_levels, int radius, int shared_offsets, int apply_mask,
+                                             void* stream) {
+  return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, off1, reinterpret_cast<float*>(corr), mask_out, E,
+                                  H, W, num_levels, radius, 1, shared_offsets, apply_mask, nullptr, E, nullptr, out_index,
+                                  out_half, stream);
 }
 static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                     const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                     int E, int H, int W, int num_levels, int radius, int per_corner,
                                     int shared_offsets, int apply_mask, const int32_t* slots, int num_slots,
-                                    void* stream) {
+                                    float* cum_mask, const int32_t* out_index, int out_half, void* stream) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && off0 && off1 && corr, "lgu_corr_lookup_fused: null pointer");
@@ -306,6 +376,8 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
     if (rc) return rc;
   }
   prm.coords = coords; prm.off0 = off0; prm.off1 = off1; prm.out = corr; prm.mask_out = mask_out;
+  prm.cum_mask = cum_mask;
+  prm.out_index = out_index;
   prm.P = P;
   prm.tiles_per_edge = (P + fl::kTile - 1) / fl::kTile;
   const long long nblk = (long long)E * prm.tiles_per_edge;
@@ -314,12 +386,9 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
   prm.apply_mask = apply_mask;
   prm.slots = slots;
   LGU_REQUIRE(!(shared_offsets && apply_mask), "lgu_*_lookup_fused: apply_mask needs per-edge offsets");
-  auto kern = per_corner ? lookup_fused_kernel<true> : lookup_fused_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, flf::kSmemBytes);
-  if (e != cudaSuccess) {
-    set_error("lgu_corr_lookup_fused: cannot opt in to %d B of shared memory: %s", flf::kSmemBytes, cudaGetErrorString(e));
-    return LGU_ERR_LAUNCH;
-  }
-  kern<<<(unsigned)nblk, fl::kThreads, flf::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
+  auto kern = per_corner ? (out_half ? lookup_fused_kernel<true, true> : lookup_fused_kernel<true, false>)
+                         : (out_half ? lookup_fused_kernel<false, true> : lookup_fused_kernel<false, false>);
+  if (int rc = optin_smem(reinterpret_cast<const void*>(kern), flf::kFwdSmemBytes, "lgu_corr_lookup_fused")) return rc;
+  kern<<<(unsigned)nblk, fl::kThreads, flf::kFwdSmemBytes, (cudaStream_t)stream>>>(maps, prm);
   return check_launch("lgu_corr_lookup_fused");
 }

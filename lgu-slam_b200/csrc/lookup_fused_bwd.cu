@@ -646,12 +646,7 @@ static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, co
   auto kern = accumulate ? (fxp ? lookup_fused_bwd_kernel<true, false, true> : lookup_fused_bwd_kernel<true, false, false>)
               : bulk     ? (fxp ? lookup_fused_bwd_kernel<false, true, true> : lookup_fused_bwd_kernel<false, true, false>)
                          : (fxp ? lookup_fused_bwd_kernel<false, false, true> : lookup_fused_bwd_kernel<false, false, false>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, flb::kSmemBytes);
-  if (e != cudaSuccess) {
-    set_error("lgu_corr_lookup_fused_backward: cannot opt in to %d B of shared memory: %s", flb::kSmemBytes,
-              cudaGetErrorString(e));
-    return LGU_ERR_LAUNCH;
-  }
+  if (int rc = optin_smem(reinterpret_cast<const void*>(kern), flb::kSmemBytes, "lgu_corr_lookup_fused_backward")) return rc;
   kern<<<(unsigned)nblk, fl::kThreads, flb::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
   return check_launch("lgu_corr_lookup_fused_backward");
 }

@@ -293,11 +293,11 @@ int launch_level_tma(bool bwd, const float* volume, const float* coords, float* 
   const long long nblk = (long long)E * prm.tiles_per_edge;
   if (nblk >= 2147483647LL) return -1;
   if (bwd) {
-    cudaFuncSetAttribute(lookup_level_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lv::kBwdSmem);
+    if (int rc = optin_smem(reinterpret_cast<const void*>(lookup_level_tma_kernel<true>), lv::kBwdSmem, "lgu_defcorr_index_backward")) return rc;
     lookup_level_tma_kernel<true><<<(unsigned)nblk, fl::kThreads, lv::kBwdSmem, st>>>(map, prm);
     return check_launch("lgu_defcorr_index_backward(tma)");
   }
-  cudaFuncSetAttribute(lookup_level_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lv::kFwdSmem);
+  if (int rc = optin_smem(reinterpret_cast<const void*>(lookup_level_tma_kernel<false>), lv::kFwdSmem, "lgu_defcorr_index_forward")) return rc;
   lookup_level_tma_kernel<false><<<(unsigned)nblk, fl::kThreads, lv::kFwdSmem, st>>>(map, prm);
   return check_launch("lgu_defcorr_index_forward(tma)");
 }

@@ -152,6 +152,11 @@ static inline EncodeTiledFn get_encode_fn() {
 static inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows,
                        uint64_t cols, uint32_t box_rows, uint32_t box_cols,
                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const MapKey key = {{2u, (uint64_t)dev, (uint64_t)reinterpret_cast<uintptr_t>(base), (uint64_t)dt, (uint64_t)elem_bytes,
+                       rows, cols, box_rows, box_cols, (uint64_t)swz, 0, 0}};
+  if (map_cache_get(key, map)) return LGU_OK;
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -168,6 +173,7 @@ static inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem
               (unsigned long long)rows, (unsigned long long)cols);
     return LGU_ERR_LAUNCH;
   }
+  map_cache_put(key, map);
   return LGU_OK;
 }
 
@@ -175,6 +181,11 @@ static inline int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem
 // {32, box_rows, box_chunks} moves box_chunks * 128 CONTIGUOUS bytes per row (128B-swizzled 4 KB sub-tiles in smem).
 static inline int make_map_chunked(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                                    uint32_t box_chunks) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const MapKey key = {{3u, (uint64_t)dev, (uint64_t)reinterpret_cast<uintptr_t>(base), rows, cols, box_rows, box_chunks, 0,
+                       0, 0, 0, 0}};
+  if (map_cache_get(key, map)) return LGU_OK;
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -192,6 +203,7 @@ static inline int make_map_chunked(CUtensorMap* map, const void* base, uint64_t 
               (unsigned long long)rows, (unsigned long long)cols);
     return LGU_ERR_LAUNCH;
   }
+  map_cache_put(key, map);
   return LGU_OK;
 }
 

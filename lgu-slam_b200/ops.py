@@ -261,11 +261,14 @@ def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_lev
     return lv
 
 
-def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False, slots=None):
+def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False, slots=None, cum_mask=None):
     """CorrBlock.__call__'s data path (corr.py:88-109) in one TMA-staged kernel.
     pyramid: 4 tensors [E,H,W,H>>l,W>>l]; coords [E,H,W,2] (x,y; level-0 units); off0, off1 [E,H,W,98] or
     [E,H,W,7,7,2]; off1 is mutated in place (multiplied by this call's uncertainty mask, Q7); the centre taps are
-    read as 0 (Q5) but left untouched in memory.  Returns corr [E,196,H,W] (and the mask [E,H,W] if return_mask)."""
+    read as 0 (Q5) but left untouched in memory.  Returns corr [E,196,H,W] (and the mask [E,H,W] if return_mask).
+    cum_mask [S,H,W] (fp32, initialised to 1 by the caller): off1 is then READ ONLY and stays pristine; the running
+    product of all masks so far lives in cum_mask (updated in place) and is applied in registers -- the same
+    cumulative semantics without writing 392 B per pixel back (lgu_corr_lookup_fused_cum)."""
     if len(pyramid) != 4:
         raise RuntimeError("corr_lookup_fused needs a 4-level pyramid")
     S, H, W = pyramid[0].shape[:3]                    # S = storage slots (== edges without a pool)
@@ -288,8 +291,18 @@ def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False, 
             raise RuntimeError(f"{name} has {o.numel()} elements, expected {S * H * W * rd * rd * 2}")
     corr = torch.empty(E, 4 * rd * rd, H, W, dtype=torch.float32, device=coords.device)
     mask = torch.empty(E, H, W, dtype=torch.float32, device=coords.device) if return_mask else None
+    if cum_mask is not None:
+        _chk(cum_mask, "cum_mask", 3)
+        if tuple(cum_mask.shape) != (S, H, W):
+            raise RuntimeError(f"cum_mask shape {tuple(cum_mask.shape)} != {(S, H, W)}")
     with torch.cuda.device(coords.device):
-        if slots is not None:
+        if cum_mask is not None:
+            st = _lib.lib().lgu_corr_lookup_fused_cum(_p(pyramid[0]), _p(pyramid[1]), _p(pyramid[2]), _p(pyramid[3]),
+                                                      _p(coords), _p(off0), _p(off1), _p(cum_mask), _p(corr),
+                                                      _p(mask) if return_mask else ctypes.c_void_p(0),
+                                                      _p(slots) if slots is not None else ctypes.c_void_p(0),
+                                                      _i(S), _i(E), _i(H), _i(W), _i(4), _i(radius), _stream(coords))
+        elif slots is not None:
             st = _lib.lib().lgu_corr_lookup_fused_slots(_p(pyramid[0]), _p(pyramid[1]), _p(pyramid[2]), _p(pyramid[3]),
                                                         _p(coords), _p(off0), _p(off1), _p(corr),
                                                         _p(mask) if return_mask else ctypes.c_void_p(0), _p(slots),
@@ -457,10 +470,12 @@ def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj):
 
 
 def altcorr_lookup_fused(volumes, coords, off0, off1, radius=3, shared_offsets=False, apply_mask=True,
-                         return_mask=False):
+                         return_mask=False, out=None, out_index=None):
     """corr_lookup_fused with the backend samplers' semantics (per-corner gating, quirk Q4; lowMem_defSample.cu /
     altcorr_kernel.cu).  volumes: 4 tensors [E,H,W,H>>l,W>>l] from build_volume.  shared_offsets: every edge reads
-    offset slab 0 (quirk Q2; off0/off1 then hold >= 1 slab); apply_mask=False: off1 is used as given."""
+    offset slab 0 (quirk Q2; off0/off1 then hold >= 1 slab); apply_mask=False: off1 is used as given.
+    out: destination [E_out,196,H,W], fp32 or fp16 (rounded to nearest), possibly peer memory of another GPU mapped
+    into this process; out_index int32 [E]: row of `out` that receives edge e (default: e).  Returns `out` then."""
     E, H, W = volumes[0].shape[:3]
     for l, t in enumerate(volumes):
         _chk(t, f"volumes[{l}]", 5)
@@ -472,8 +487,26 @@ def altcorr_lookup_fused(volumes, coords, off0, off1, radius=3, shared_offsets=F
         if not (isinstance(o, torch.Tensor) and o.is_cuda and o.is_contiguous() and o.dtype == torch.float32
                 and o.numel() >= need):
             raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor with >= {need} elements")
-    corr = torch.empty(E, 196, H, W, dtype=torch.float32, device=coords.device)
     mask = torch.empty(E, H, W, dtype=torch.float32, device=coords.device) if return_mask else None
+    if out is not None:
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.is_contiguous() and out.dim() == 4
+                and tuple(out.shape[1:]) == (196, H, W) and out.dtype in (torch.float32, torch.float16)):
+            raise RuntimeError("out must be a contiguous CUDA tensor [E_out,196,H,W], fp32 or fp16")
+        if out_index is not None:
+            if not (out_index.is_cuda and out_index.dtype == torch.int32 and out_index.is_contiguous()
+                    and out_index.numel() == E and out_index.device == coords.device):
+                raise RuntimeError("out_index must be a contiguous CUDA int32 vector with one row per edge")
+        elif out.shape[0] < E:
+            raise RuntimeError(f"out has {out.shape[0]} rows, {E} edges")
+        with torch.cuda.device(coords.device):
+            st = _lib.lib().lgu_altcorr_lookup_fused_into(
+                _p(volumes[0]), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]), _p(coords), _p(off0), _p(off1), _p(out),
+                _p(out_index) if out_index is not None else ctypes.c_void_p(0), _i(out.dtype == torch.float16),
+                _p(mask) if return_mask else ctypes.c_void_p(0), _i(E), _i(H), _i(W), _i(4), _i(radius),
+                _i(1 if shared_offsets else 0), _i(1 if apply_mask else 0), _stream(coords))
+        _lib.check(st, "altcorr_lookup_fused (into)")
+        return (out, mask) if return_mask else out
+    corr = torch.empty(E, 196, H, W, dtype=torch.float32, device=coords.device)
     with torch.cuda.device(coords.device):
         st = _lib.lib().lgu_altcorr_lookup_fused(_p(volumes[0]), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]),
                                                  _p(coords), _p(off0), _p(off1), _p(corr),

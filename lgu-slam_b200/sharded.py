@@ -12,7 +12,11 @@ Collectives (only these; the lookups themselves exchange nothing):
      holds the whole buffer and builds its own channels-last pyramid;
   2. per BA step (optional): return of the per-edge outputs [E_local,196,H,W] -- either left sharded
      (`gather=None`; the GRU update can run data-parallel on them), gathered on one rank (`gather="dst"`)
-     or on every rank (`gather="all"`).
+     or on every rank (`gather="all"`).  The fast form of `gather="dst"` is `PeerOutput` + `lookup_into_peer`: the
+     destination rank's output buffer is mapped into every rank (CUDA IPC over NVLink / NVSwitch peer memory) and the
+     lookup kernels STORE THEIR RESULT ROWS STRAIGHT INTO IT (each edge at its original position, optionally as
+     fp16 -- what the consumer, `update_op` under autocast, reads anyway: factor_graph.py:284-286); the transfer is
+     the kernel's own store stream, so it overlaps the compute tile by tile and no collective carries data.
 
 Everything here is host logic on top of `torch.distributed`; the `compute` callable is the AltCorrBlock of
 lgu-slam_b200/corr.py on a GPU box and may be any function with the same signature in CPU (gloo) tests.
@@ -34,6 +38,7 @@ class EdgePlan:
     chunk_owner: List[int]                          # per chunk: owning rank
     rank_chunks: List[List[int]] = field(default_factory=list)      # per rank: its chunk ids, in reference order
     rank_edges: List[torch.Tensor] = field(default_factory=list)    # per rank: edge positions, chunk by chunk
+    total_edges: int = 0                            # length of the edge list (>= visited edges, see reference_chunks)
 
     @property
     def num_edges(self):
@@ -71,7 +76,7 @@ def partition_edges(ii: torch.Tensor, jj: torch.Tensor, world_size: int,
         r = min(range(world_size), key=lambda r: (load[r], r))
         owner[c] = r
         load[r] += chunks[c].numel()
-    plan = EdgePlan(world_size, chunks, owner)
+    plan = EdgePlan(world_size, chunks, owner, total_edges=int(ii.numel()))
     for r in range(world_size):
         mine = [c for c in range(len(chunks)) if owner[c] == r]
         plan.rank_chunks.append(mine)
@@ -101,6 +106,96 @@ def all_gather_frames(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([out[r * tmax:r * tmax + counts[r]] for r in range(world)], dim=0)
 
 
+class PeerOutput:
+    """The gathered output buffer [E, *per_edge_shape] of one backend step, resident on rank `dst` and WRITABLE FROM EVERY
+    RANK: on a GPU box `dst` allocates it and the other ranks map the same memory through CUDA IPC (NVLink / NVSwitch
+    peer access), so a rank's lookup kernels store their result rows straight into the destination GPU's HBM at each
+    edge's original position -- "return per-edge outputs" without a collective on the data path.  On CPU (gloo tests)
+    the buffer is a file under /dev/shm mapped by every rank.  `transport` names what is in use.
+
+    Lifetime: create once (collective), reuse every step, `close()` collectively before the process group goes away."""
+
+    def __init__(self, num_edges, per_edge_shape, dtype, device, dst=0, group=None):
+        self.group, self.dst = group, dst
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device(device)
+        shape = (int(num_edges),) + tuple(int(x) for x in per_edge_shape)
+        self._path = None
+        self._own = None
+        if self.device.type == "cuda":
+            self.transport = "cuda-ipc peer stores (NVLink)" if self.world > 1 else "local"
+            if self.rank == dst:
+                self._own = torch.zeros(shape, dtype=dtype, device=self.device)
+                torch.cuda.synchronize(self.device)
+            self.buffer = self._own
+            if self.world > 1:
+                from torch.multiprocessing.reductions import reduce_tensor
+                box = [reduce_tensor(self._own)[1] if self.rank == dst else None]
+                dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst,
+                                           group=group)
+                if self.rank != dst:
+                    from torch.multiprocessing.reductions import rebuild_cuda_tensor
+                    self.buffer = rebuild_cuda_tensor(*box[0])
+                    self._enable_peer(self.device.index, self.buffer.device.index)
+        else:
+            import os
+            import tempfile
+            self.transport = "shared file mapping (CPU test transport)" if self.world > 1 else "local"
+            box = [None]
+            if self.rank == dst:
+                fd, self._path = tempfile.mkstemp(prefix="lgu_peer_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+                os.close(fd)
+                box = [self._path]
+            if self.world > 1:
+                dist.broadcast_object_list(box, src=dst, group=group)
+            n = 1
+            for x in shape:
+                n *= x
+            if self.rank == dst:
+                self.buffer = torch.from_file(box[0], shared=True, size=n, dtype=dtype).view(shape)
+                self.buffer.zero_()
+            if self.world > 1:
+                dist.barrier(group=group)
+            if self.rank != dst:
+                self.buffer = torch.from_file(box[0], shared=True, size=n, dtype=dtype).view(shape)
+        if self.world > 1:
+            dist.barrier(group=group)                       # the zero-fill on `dst` precedes every remote store
+
+    @staticmethod
+    def _enable_peer(device, peer):
+        """Kernels of `device` dereference pointers into `peer`'s HBM: peer access must be on in this direction."""
+        if device == peer:
+            return
+        if not torch.cuda.can_device_access_peer(device, peer):
+            raise RuntimeError(f"cuda:{device} cannot access cuda:{peer} as a peer (no NVLink / P2P path)")
+        # a device-to-device copy makes torch switch peer access on for the pair (cudaDeviceEnablePeerAccess)
+        a = torch.zeros(1, device=f"cuda:{device}")
+        b = torch.zeros(1, device=f"cuda:{peer}")
+        b.copy_(a)
+        a.copy_(b)
+        torch.cuda.synchronize(device)
+
+    def result(self):
+        """[1, E, ...] on `dst` (call after `ShardedBackendCorr.lookup_into_peer` returned), None elsewhere."""
+        return self.buffer[None] if self.rank == self.dst else None
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self.rank != self.dst:
+            self.buffer = None                              # drop the mapping before the owner frees the memory
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.buffer = self._own = None
+        if self._path is not None:
+            import os
+            try:
+                os.unlink(self._path)
+            except OSError:
+                pass
+
+
 class ShardedBackendCorr:
     """Runs `compute(coords[:, v], ii[v], jj[v])` (AltCorrBlock.__call__, corr.py:238-249) for the chunks this
     rank owns and returns the per-edge outputs sharded or gathered.
@@ -113,6 +208,12 @@ class ShardedBackendCorr:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.plan: Optional[EdgePlan] = None
+        try:
+            import inspect
+            params = inspect.signature(compute).parameters
+            self._writes_in_place = "out" in params and "out_index" in params
+        except (TypeError, ValueError):
+            self._writes_in_place = False
 
     def set_edges(self, ii, jj, frames_per_chunk=FRAMES_PER_CHUNK):
         self.plan = partition_edges(ii, jj, self.world, frames_per_chunk)
@@ -131,7 +232,8 @@ class ShardedBackendCorr:
         """gather="dst" with the transfer hidden behind the compute: every chunk's outputs leave for rank `dst` as
         soon as the chunk is done (point-to-point isend over NVLink / NVSwitch, asynchronous to the next chunk's
         kernels); `dst` posts all receives up front, computes its own chunks into place and scatters the received
-        chunks into the original edge order.  Returns [1,E_visited,CH,H,W] on `dst`, None elsewhere."""
+        chunks into the original edge order.  Returns [1,E,CH,H,W] on `dst` (E = full edge count; never-visited edges
+        are zero), None elsewhere."""
         assert self.plan is not None, "call set_edges(ii, jj) first"
         plan, dev = self.plan, coords.device
         mine = plan.rank_chunks[self.rank]
@@ -153,11 +255,7 @@ class ShardedBackendCorr:
             for r in reqs:
                 r.wait()
             return None
-        full = torch.empty((1, plan.num_edges) + shape, dtype=torch.float32, device=dev)
-        visited = torch.cat(plan.chunk_edges) if plan.chunk_edges else torch.zeros(0, dtype=torch.int64)
-        # position of every visited edge in the compact output (edges the reference loop never visits have none)
-        remap = torch.full((int(visited.max()) + 1 if visited.numel() else 0,), -1, dtype=torch.int64)
-        remap[torch.sort(visited).values] = torch.arange(visited.numel())
+        full = torch.zeros((1, plan.total_edges) + shape, dtype=torch.float32, device=dev)
         recv = []
         for r in range(self.world):
             if r == dst:
@@ -170,11 +268,41 @@ class ShardedBackendCorr:
             if k > 0:
                 vd = v.to(dev)
                 outs[c] = self.compute(coords[:, vd], ii[vd], jj[vd])
-            full[:, remap[v].to(dev)] = outs[c]
+            full[:, v.to(dev)] = outs[c]
         for c, buf, req in recv:
             req.wait()
-            full[:, remap[plan.chunk_edges[c]].to(dev)] = buf[None]
+            full[:, plan.chunk_edges[c].to(dev)] = buf[None]
         return full
+
+    def lookup_into_peer(self, coords, ii, jj, peer: PeerOutput, sync=True):
+        """gather="dst" with NO collective on the data path: every rank runs its chunks with the destination buffer as the
+        kernels' output tensor (`compute(..., out=peer.buffer, out_index=positions)` -- AltCorrBlock's fused lookup stores
+        its 196-channel rows through NVLink peer memory, edge e at row positions[e]); a compute callable without that
+        signature is served by peer-to-peer copies of its result.  One barrier at the end publishes the step
+        (`sync=False` leaves it to the caller, e.g. to overlap several steps).  Returns peer.result()."""
+        assert self.plan is not None, "call set_edges(ii, jj) first"
+        plan, dev = self.plan, coords.device
+        for c in plan.rank_chunks[self.rank]:
+            v = plan.chunk_edges[c]
+            vd = v.to(dev)
+            if self._writes_in_place:
+                self.compute(coords[:, vd], ii[vd], jj[vd], out=peer.buffer, out_index=vd.to(torch.int32))
+            else:                                                  # plain callable: copy its result over
+                res = self.compute(coords[:, vd], ii[vd], jj[vd])[0].to(peer.buffer.dtype)
+                pos = v.tolist()
+                k = 0
+                while k < len(pos):                                # runs of consecutive positions -> one copy each
+                    e = k + 1
+                    while e < len(pos) and pos[e] == pos[e - 1] + 1:
+                        e += 1
+                    peer.buffer[pos[k]:pos[k] + (e - k)].copy_(res[k:e])
+                    k = e
+        if sync:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)                        # this rank's peer stores have landed
+            if self.world > 1:
+                dist.barrier(group=self.group)
+        return peer.result()
 
     def __call__(self, coords, ii, jj, gather="all", dst=0):
         """gather=None: (local outputs, their edge positions).  gather="all": full [1,E,CH,H,W] in the original edge
@@ -207,12 +335,18 @@ class ShardedBackendCorr:
     def _out_shape(self, local, coords):
         # every rank must agree on the per-edge output shape even if it owns no edge: probe it collectively
         shp = torch.tensor(list(local.shape[2:]) if local is not None else [0, 0, 0], device=coords.device)
-        dist.all_reduce(shp, op=dist.ReduceOp.MAX, group=self.group)
+        if self.world > 1:
+            dist.all_reduce(shp, op=dist.ReduceOp.MAX, group=self.group)
         return tuple(int(x) for x in shp.tolist())
 
     def _reorder(self, parts, device):
+        """Per-rank outputs -> [1, E, ...] in the ORIGINAL edge order, E = the full edge count.  Edges the reference's
+        chunk loop never visits (source frame beyond the last loop start, factor_graph.py:272-279) stay zero."""
         order = torch.cat(self.plan.rank_edges).to(device)
-        full = torch.cat([p for p in parts if p is not None and p.shape[1] > 0], dim=1)
-        out = torch.empty_like(full)
+        parts = [p for p in parts if p is not None and p.shape[1] > 0]
+        if not parts:
+            return None
+        full = torch.cat(parts, dim=1)
+        out = torch.zeros((1, self.plan.total_edges) + tuple(full.shape[2:]), dtype=full.dtype, device=device)
         out[:, order] = full
         return out

@@ -372,3 +372,32 @@ def test_pool_build_writes_only_its_slots():
     for l, t in enumerate(pool.levels):
         assert torch.isnan(t[[0, 2, 4]]).all(), f"level {l}: a slot outside the block was written"
         assert torch.isfinite(t[[1, 3]]).all(), f"level {l}: a slot of the block was not fully written"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_altcorrblock_writes_into_a_callers_buffer_at_given_rows(dtype):
+    """The sharded backend's return path (sharded.PeerOutput): AltCorrBlock(out=, out_index=) stores edge e's rows at
+    out[out_index[e]] -- fp32 bit-identical to the returned tensor, fp16 = that tensor rounded to nearest -- and leaves
+    every other row of the buffer untouched."""
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 9)
+    g = inputs.gen(31)
+    T, E = 6, 5
+    fmaps = torch.randn(1, T, 128, 48, 64, generator=g).half().to(dev)
+    ii = torch.tensor([0, 1, 2, 3, 4], device=dev)
+    jj = torch.tensor([1, 2, 3, 4, 5], device=dev)
+    coords = inputs.make_coords(E, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, E, 48, 64, 2).to(dev)
+    rows = torch.tensor([7, 0, 3, 8, 2], dtype=torch.int32, device=dev)
+    with torch.no_grad():
+        blk = corr.AltCorrBlock(ofsMap, ofs_residual, GA, fmaps, materialize=True)
+        want = blk(coords, ii, jj)[0]
+        buf = torch.full((9, 196, 48, 64), -7.0, dtype=dtype, device=dev)
+        ret = blk(coords, ii, jj, out=buf, out_index=rows)
+    assert ret is buf
+    got = buf[rows.long()]
+    if dtype == torch.float32:
+        assert torch.equal(got, want)
+    else:
+        assert torch.equal(got, want.half())
+    untouched = [r for r in range(9) if r not in rows.tolist()]
+    assert (buf[untouched] == -7.0).all()

@@ -245,3 +245,30 @@ def test_fused_backward_accumulate_equals_sum_of_dense_calls(ops, big):
         # out-of-box taps (|offset| >= 4, `big`) go through scalar atomics whose order is not fixed
         tol = 1e-30 if not big else 1e-5 * max(1.0, torch.nan_to_num(want[l]).abs().max().item())
         assert err <= tol, f"level {l}: accumulated gradient differs from the sum of dense calls by {err}"
+
+
+def test_fused_lookup_cumulative_mask_mode_equals_write_back_mode(ops):
+    """lgu_corr_lookup_fused_cum keeps offset[1] pristine and the running product of the masks in a [E,H,W] buffer;
+    three consecutive calls must give what the write-back entry point gives (the reference's cumulative
+    `self.offset[1] *= mask`, Q7): levels 0, 2, 3 bit-identical, level 1 within 1e-5 of the largest value (o*(m1*m2) vs
+    (o*m1)*m2 moves an offset by <= 2 ulp, times the local slope of a white-noise pyramid with |V| up to ~5), and
+    off1 * cum_mask equal to the written-back offsets within 2 ulp of the offset magnitude."""
+    E, dev = 2, "cuda"
+    g = inputs.gen(81)
+    pyr = [torch.randn(E, 48, 64, 48 >> l, 64 >> l, generator=g).to(dev) for l in range(4)]
+    c = _case(E, 82)
+    off0, off1 = c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+    wb = off1.clone()
+    cum = torch.ones(E, 48, 64, device=dev)
+    for step in range(3):
+        coords = (c["coords"] + 0.6 * step * torch.randn(c["coords"].shape, generator=g)).contiguous().to(dev)
+        want, m_w = ops.corr_lookup_fused(pyr, coords, off0, wb, 3, return_mask=True)
+        keep = off1.clone()
+        got, m_c = ops.corr_lookup_fused(pyr, coords, off0, off1, 3, return_mask=True, cum_mask=cum)
+        assert torch.equal(off1, keep), "cum mode must not touch offset[1]"
+        for l in (0, 2, 3):
+            assert torch.equal(got[:, 49 * l:49 * (l + 1)], want[:, 49 * l:49 * (l + 1)]), f"call {step} level {l}"
+        scale = max(1.0, want[:, 49:98].abs().max().item())
+        assert (got[:, 49:98] - want[:, 49:98]).abs().max().item() <= 1e-5 * scale, f"call {step} level 1"
+        assert (m_c - m_w).abs().max().item() <= 1e-6
+        assert ((off1 * cum.view(E, 48, 64, 1)) - wb).abs().max().item() <= 1e-6

@@ -115,7 +115,15 @@ def _worker(rank, world, port, gather, q):
         assert torch.equal(full, fmaps)
         eng = sh.ShardedBackendCorr(_oracle_compute(_levels(full)))
         plan = eng.set_edges(ii, jj)
-        out = eng.lookup_streamed_to(coords, ii, jj, dst=0) if gather == "stream" else eng(coords, ii, jj, gather=gather)
+        if gather == "peer":
+            peer = sh.PeerOutput(ii.numel(), (18, 6, 8), torch.float32, "cpu", dst=0)
+            out = eng.lookup_into_peer(coords, ii, jj, peer)
+            out = out.clone() if out is not None else None
+            peer.close()
+        elif gather == "stream":
+            out = eng.lookup_streamed_to(coords, ii, jj, dst=0)
+        else:
+            out = eng(coords, ii, jj, gather=gather)
         if gather is None:
             local, pos = out
             q.put((rank, "local", local, pos))
@@ -128,7 +136,7 @@ def _worker(rank, world, port, gather, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("gather", ["all", "dst", "stream", None])
+@pytest.mark.parametrize("gather", ["all", "dst", "stream", "peer", None])
 def test_world_size_2_gloo_equals_single_process(gather):
     fmaps, ii, jj, coords = _case()
     sh = _sharded()
@@ -155,7 +163,7 @@ def test_world_size_2_gloo_equals_single_process(gather):
     if gather == "all":
         for _, kind, out, _ in got:
             assert kind == "full" and torch.equal(out, full)
-    elif gather in ("dst", "stream"):
+    elif gather in ("dst", "stream", "peer"):
         assert got[0][1] == "full" and torch.equal(got[0][2], full) and got[1][1] == "none"
     else:
         seen = torch.zeros(ii.numel(), dtype=torch.bool)
@@ -164,3 +172,30 @@ def test_world_size_2_gloo_equals_single_process(gather):
             assert torch.equal(local, full[:, pos])
             seen[pos] = True
         assert seen.all()
+
+
+def test_edges_the_reference_loop_never_visits_stay_zero_in_the_gathered_output():
+    """factor_graph.py:272-279 stops at ceil((jj.max()+1)/8)*8: an edge whose source frame lies beyond that is skipped by
+    the reference loop.  The gathered output keeps the FULL edge count (such rows are zero), in every single-process
+    gather mode, and the streamed / peer variants work without a process group (world = 1)."""
+    sh = _sharded()
+    ii = torch.tensor([0, 1, 9, 2])
+    jj = torch.tensor([1, 0, 3, 3])                       # jj.max() = 3 -> one loop start (0): edge 2 (ii = 9) is skipped
+    H, W = 6, 8
+    coords = torch.rand(1, 4, H, W, 2)
+
+    def compute(c, a, b):
+        return (a.float() * 10 + b.float()).view(1, -1, 1, 1, 1).expand(1, a.numel(), 3, H, W).contiguous()
+
+    eng = sh.ShardedBackendCorr(compute)
+    plan = eng.set_edges(ii, jj)
+    assert plan.total_edges == 4 and plan.num_edges == 3
+    want = compute(coords, ii, jj).clone()
+    want[:, 2] = 0
+    assert torch.equal(eng(coords, ii, jj, gather="all"), want)
+    assert torch.equal(eng.lookup_streamed_to(coords, ii, jj), want)
+    peer = sh.PeerOutput(4, (3, H, W), torch.float32, "cpu")
+    assert torch.equal(eng.lookup_into_peer(coords, ii, jj, peer), want)
+    peer.close()
+    local, pos = eng(coords, ii, jj, gather=None)
+    assert pos.tolist() == [0, 1, 3] and torch.equal(local, want[:, pos])
