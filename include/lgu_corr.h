@@ -218,6 +218,18 @@ LGU_API int lgu_corr_lookup_fused_backward_accumulate(const float* lvl0, const f
                                    float* off0_grad, float* off1_grad,
                                    int E, int H, int W, int num_levels, int radius, void* stream);
 
+/* The same backward for a forward that ran in the cumulative-mask form (lgu_corr_lookup_fused_cum): off1 holds the
+ * PRISTINE level-1 offsets and cum_mask [E,H,W] the running mask product AFTER that forward, so the post-mask offsets
+ * offset[1]_out = off1 * cum_mask are formed in registers (same product, same rounding as the forward) instead of being
+ * read from a materialised tensor.  off1_grad is the gradient with respect to that call's input offsets
+ * (off1 * cum_mask / mask).  accumulate != 0 selects the persistent-accumulator form. */
+LGU_API int lgu_corr_lookup_fused_backward_cum(const float* lvl0, const float* lvl1, const float* coords,
+                                   const float* off0, const float* off1, const float* cum_mask, const float* mask,
+                                   const float* corr_grad, const float* off1_out_grad,
+                                   float* gv0, float* gv1, float* gv2, float* gv3,
+                                   float* off0_grad, float* off1_grad,
+                                   int E, int H, int W, int num_levels, int radius, int accumulate, void* stream);
+
 /* Gaussian-head part of the backward of lgu_build_pyramid (what autograd runs for gaussianMask_cuda.py:84-86
  * followed by 3 x avg_pool2d, corr.py:83-86), straight from the four LEVEL gradients, without a dense pass:
  *   g(q)      = g0[q] + g1[q/2]/4 + g2[q/4]/16 + g3[q/8]/64          (avg_pool2d^T, evaluated at the window taps only)

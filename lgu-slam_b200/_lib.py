@@ -48,7 +48,12 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0          # successful C-ABI calls so far (every one launches at least one of this library's kernels)
+
+
 def check(status, what):
+    global LAUNCHES
+    LAUNCHES += 1
     if status != 0:
         msg = lib().lgu_last_error_string().decode("utf-8", "replace")
         raise LguError(f"{what} failed (status {status}): {msg}")

@@ -245,6 +245,147 @@ build_bwd_gauss_kernel(const float* __restrict__ means, const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Round-2 backward for the reference's only radius (r = 4, a 9 x 9 window).  The round-1 kernels evaluated a
+// full-precision expf, two IEEE divides and ~10 fp64 operations PER TAP and were issue-bound (68 % issue-active at 16 %
+// of the HBM roofline).  The Gaussian is separable, e(i,j) = ex(i) * ey(j), and so is every factor the reference forms
+// from it (gaussianAttn.cu:112-126):
+//     d/dmean_x : 3 V g * [ex(i) ddx(i) / cx] * ey(j)          d/dcov_x : 3 V g * [0.5 ex(i) ddx(i)^2 / cx^2] * ey(j)
+//     d/dmean_y : 3 V g * ex(i) * [ey(j) ddy(j) / cy]          d/dcov_y : 3 V g * ex(i) * [0.5 ey(j) ddy(j)^2 / cy^2]
+// Lanes 0-8 evaluate the 9 COLUMN records, lanes 9-17 the 9 ROW records (one expf each; the fp64 factor of the reference,
+// :120,122, 18 times per pixel instead of 162); records of out-of-range columns / rows are zero, which is the reference's
+// bounds gate.  Lane = tap as before (coalesced 36-byte row segments: a lane = row mapping was measured and is bound by
+// L1 wavefronts, 27 lines per load), the two records of a tap arrive by shuffle, a tap costs 2 multiplies and 4 FMAs,
+// and the four sums are reduced with a value-splitting butterfly (6 shuffles instead of 20).  Differences from the
+// reference's per-tap evaluation are products of correctly rounded factors in another order (a few 1e-7 relative),
+// inside the 1e-5 gradient bar.  FUSED: the upstream gradient and the raw volume are formed per tap from lvl0 and the
+// four level gradients (lgu_build_backward_gauss).
+// The kernel is LATENCY-bound otherwise (two dependent DRAM round trips per pixel -- parameters, then the window -- with
+// ~40 resident warps per SM: measured 86 us at E = 48 whatever the instruction count), so a warp takes NP = 4
+// consecutive pixels per trip: lanes 0..3 fetch the four parameter records together and the 4 x 3 gather passes are all
+// in flight before the first tap is consumed.
+template <bool FUSED, int NP>
+__global__ void __launch_bounds__(kGaWarps * 32)
+gaussian_bwd_sep_kernel(const float* __restrict__ means, const float* __restrict__ covs, const float* __restrict__ den,
+                        const float* __restrict__ vol, const float* __restrict__ g0, const float* __restrict__ g1,
+                        const float* __restrict__ g2, const float* __restrict__ g3, float* __restrict__ means_grad,
+                        float* __restrict__ covs_grad, float* __restrict__ den_grad, long long npix, int H2, int W2) {
+  constexpr int r = 4, rd = 9, taps = 81, kPasses = 3;
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int Q = H2 * W2;
+  // per-lane tap constants of the three passes
+  int ti[kPasses], tj[kPasses];
+#pragma unroll
+  for (int ps = 0; ps < kPasses; ++ps) {
+    const int t = min(ps * 32 + lane, taps - 1);
+    tj[ps] = t / rd;
+    ti[ps] = t - tj[ps] * rd;
+  }
+  const bool is_row = lane >= rd;                               // lanes 9..17 (18..31 compute unused duplicates)
+  const int kidx = (lane < rd ? lane : lane - rd) % rd;
+  for (long long pb = wid * NP; pb < npix; pb += nwarps * NP) {
+    // ---- parameters of the NP pixels: lane q loads pixel pb + q (the tail repeats the last pixel; its store is skipped)
+    const long long pmine = min(pb + (lane < NP ? lane : 0), npix - 1);
+    const float2 m_l = __ldg(reinterpret_cast<const float2*>(means) + pmine);
+    const float2 c_l = __ldg(reinterpret_cast<const float2*>(covs) + pmine);
+    const float d_l = FUSED ? __ldg(den + pmine) : 1.0f;
+    float2 m[NP], c[NP];
+    float dn[NP];
+    int x0[NP], y0[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      m[q] = make_float2(__shfl_sync(0xffffffffu, m_l.x, q), __shfl_sync(0xffffffffu, m_l.y, q));
+      c[q] = make_float2(__shfl_sync(0xffffffffu, c_l.x, q), __shfl_sync(0xffffffffu, c_l.y, q));
+      dn[q] = __shfl_sync(0xffffffffu, d_l, q);
+      x0[q] = tap_coord(floor_to_int(m[q].x), r, 0);
+      y0[q] = tap_coord(floor_to_int(m[q].y), r, 0);
+    }
+    // ---- all gathers of all NP pixels (clamped addresses: the records below zero what the reference's bounds test drops)
+    float v[NP][kPasses], g[NP][kPasses];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const long long pix = min(pb + q, npix - 1);
+#pragma unroll
+      for (int ps = 0; ps < kPasses; ++ps) {
+        const int xc = min(max(tap_coord(x0[q], 0, ti[ps]), 0), W2 - 1), yc = min(max(tap_coord(y0[q], 0, tj[ps]), 0), H2 - 1);
+        const size_t at = (size_t)pix * Q + (size_t)yc * W2 + xc;
+        v[q][ps] = __ldg(vol + at);
+        float gg = g0 != nullptr ? __ldg(g0 + at) : 0.0f;
+        if (FUSED) {                                            // avg_pool2d^T, level by level
+          if (g1 != nullptr) gg = __fadd_rn(gg, __fmul_rn(__ldg(g1 + (size_t)pix * (Q >> 2) + (yc >> 1) * (W2 >> 1) + (xc >> 1)), 0.25f));
+          if (g2 != nullptr) gg = __fadd_rn(gg, __fmul_rn(__ldg(g2 + (size_t)pix * (Q >> 4) + (yc >> 2) * (W2 >> 2) + (xc >> 2)), 0.0625f));
+          if (g3 != nullptr) gg = __fadd_rn(gg, __fmul_rn(__ldg(g3 + (size_t)pix * (Q >> 6) + (yc >> 3) * (W2 >> 3) + (xc >> 3)), 0.015625f));
+        }
+        g[q][ps] = gg;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      // ---- this lane's record: column kidx (lanes 0-8) or row kidx (lanes 9-17)
+      const float mean_a = is_row ? m[q].y : m[q].x, cov_a = is_row ? c[q].y : c[q].x;
+      const int coord = tap_coord(is_row ? y0[q] : x0[q], 0, kidx);
+      const bool inb = (unsigned)coord < (unsigned)(is_row ? H2 : W2);
+      const float rc = __fdiv_rn(1.0f, cov_a);
+      const float dd = __fsub_rn((float)coord, mean_a);
+      const float ev = expf(__fmul_rn(__fmul_rn(__fmul_rn(dd, rc), dd), -0.5f));
+      const float recE = inb ? ev : 0.0f;                                                      // e
+      const float recM = inb ? __fmul_rn(__fmul_rn(dd, ev), rc) : 0.0f;                        // e dd / cov
+      // 0.5 e dd^2 / cov^2 in fp64 like the reference (:120,122), with the correctly rounded fp32 reciprocal of cov^2
+      const float recC = inb ? (float)(((((double)ev * 0.5) * (double)dd) * (double)dd) * (double)__fmul_rn(rc, rc)) : 0.0f;
+      float k3 = 0.0f, rdn = 1.0f;
+      if (FUSED) {
+        rdn = __fdiv_rn(1.0f, dn[q]);
+        k3 = __fmul_rn(3.0f, rdn);                              // lvl0 = V (1 + 3 ex ey / den) inside the window
+      }
+      float gm0 = 0.0f, gm1 = 0.0f, gc0 = 0.0f, gc1 = 0.0f, gd = 0.0f;
+#pragma unroll
+      for (int ps = 0; ps < kPasses; ++ps) {
+        const float cE = __shfl_sync(0xffffffffu, recE, ti[ps]), cM = __shfl_sync(0xffffffffu, recM, ti[ps]);
+        const float cC = __shfl_sync(0xffffffffu, recC, ti[ps]);
+        const float rE = __shfl_sync(0xffffffffu, recE, rd + tj[ps]), rM = __shfl_sync(0xffffffffu, recM, rd + tj[ps]);
+        const float rC = __shfl_sync(0xffffffffu, recC, rd + tj[ps]);
+        const bool live = ps * 32 + lane < taps;
+        float vraw = v[q][ps];
+        if (FUSED) {
+          vraw = __fdividef(v[q][ps], __fmaf_rn(__fmul_rn(k3, cE), rE, 1.0f));   // the raw volume (== v outside the window)
+          if (live) gd = __fmaf_rn(g[q][ps], __fsub_rn(v[q][ps], vraw), gd);
+        }
+        const float w = live ? __fmul_rn(__fmul_rn(vraw, 3.0f), g[q][ps]) : 0.0f;
+        const float wa = __fmul_rn(w, rE), wb = __fmul_rn(w, cE);
+        gm0 = __fmaf_rn(wa, cM, gm0);
+        gc0 = __fmaf_rn(wa, cC, gc0);
+        gm1 = __fmaf_rn(wb, rM, gm1);
+        gc1 = __fmaf_rn(wb, rC, gc1);
+      }
+      // ---- reduce (gm0, gm1, gc0, gc1) over the warp with a value-splitting butterfly: 2 + 1 + 3 shuffles
+      float t;
+      {
+        const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+        const float s0 = hi16 ? gm0 : gc0, s1 = hi16 ? gm1 : gc1;              // what this lane sends
+        const float k0 = hi16 ? gc0 : gm0, k1 = hi16 ? gc1 : gm1;              // what it keeps
+        const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16), a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+        t = (hi8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi8 ? a0 : a1, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);                               // lane 0: gm0, 8: gm1, 16: gc0, 24: gc1
+      }
+      if (FUSED) gd = warp_sum(gd);
+      const float r1 = __shfl_sync(0xffffffffu, t, 8), r2 = __shfl_sync(0xffffffffu, t, 16), r3 = __shfl_sync(0xffffffffu, t, 24);
+      if (lane == 0 && pb + q < npix) {
+        float o0 = t, o1 = r1, o2 = r2, o3 = r3;
+        if (FUSED) {                                            // g / den enters every parameter gradient linearly
+          o0 = __fmul_rn(o0, rdn); o1 = __fmul_rn(o1, rdn); o2 = __fmul_rn(o2, rdn); o3 = __fmul_rn(o3, rdn);
+          den_grad[pb + q] = -__fmul_rn(gd, rdn);
+        }
+        reinterpret_cast<float2*>(means_grad)[pb + q] = make_float2(o0, o1);
+        reinterpret_cast<float2*>(covs_grad)[pb + q] = make_float2(o2, o3);
+      }
+    }
+  }
+}
+
 static inline unsigned grid_for_warps(long long nwarps_needed, int warps_per_cta, int ctas_per_sm) {
   long long want = (nwarps_needed + warps_per_cta - 1) / warps_per_cta;
   long long cap = (long long)kNumSMs * ctas_per_sm;
@@ -284,6 +425,12 @@ extern "C" int lgu_gaussian_mask_backward(const float* means, const float* covs,
               "lgu_gaussian_mask_backward: bad sizes E=%d H1=%d W1=%d H2=%d W2=%d r=%d", E, H1, W1, H2, W2, radius);
   LGU_REQUIRE((long long)H2 * W2 < (1LL << 30), "lgu_gaussian_mask_backward: H2*W2 too large");
   const long long npix = (long long)E * H1 * W1;
+  if (radius == 4) {                                             // the reference's only radius: lane = (pixel, window row)
+    const unsigned grid3 = lgu::grid_for_warps((npix + 3) / 4, lgu::kGaWarps, 8);
+    lgu::gaussian_bwd_sep_kernel<false, 4><<<grid3, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
+        means, covs, nullptr, volume, volume1_grad, nullptr, nullptr, nullptr, means_grad, covs_grad, nullptr, npix, H2, W2);
+    return lgu::check_launch("lgu_gaussian_mask_backward");
+  }
   const unsigned grid = lgu::grid_for_warps(npix, lgu::kGaWarps, 8);
   lgu::gaussian_bwd_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
       means, covs, volume, volume1_grad, means_grad, covs_grad, npix, H2, W2, radius);
@@ -301,6 +448,12 @@ extern "C" int lgu_build_backward_gauss(const float* means, const float* covs, c
               "lgu_build_backward_gauss: bad sizes E=%d H=%d W=%d r=%d (H, W must be multiples of 8)", E, H, W, radius);
   LGU_REQUIRE((long long)H * W < (1LL << 30), "lgu_build_backward_gauss: H*W too large");
   const long long npix = (long long)E * H * W;
+  if (radius == 4) {
+    const unsigned grid3 = lgu::grid_for_warps((npix + 3) / 4, lgu::kGaWarps, 8);
+    lgu::gaussian_bwd_sep_kernel<true, 4><<<grid3, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
+        means, covs, den, lvl0, g0, g1, g2, g3, means_grad, covs_grad, den_grad, npix, H, W);
+    return lgu::check_launch("lgu_build_backward_gauss");
+  }
   const unsigned grid = lgu::grid_for_warps(npix, lgu::kGaWarps, 8);
   lgu::build_bwd_gauss_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
       means, covs, den, lvl0, g0, g1, g2, g3, means_grad, covs_grad, den_grad, npix, H, W, radius);

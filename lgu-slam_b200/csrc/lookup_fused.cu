@@ -35,13 +35,23 @@ namespace lgu {
 // origin, box address and pitch, level extent) comes from a per-warp table in shared memory that the TMA-issuing lanes
 // fill, so the pass body is branch-free and identical for every lane: 2 LDS.128 + ~35 ALU + 4 LDS + 1 STS.
 namespace flf {
-constexpr int kRing = 2;                                            // TMA ring depth (boxes in flight per warp)
+constexpr int kRing = 2;                                             // TMA ring depth (boxes in flight per warp)
 constexpr int kPasses = 7;                                           // ceil(196 / 32)
 constexpr int kRecBytes = 32;                                        // one table record = 2 x 16 B
-constexpr int kRingBytes = fl::kWarps * kRing * fl::kSlotBytes;     // 53,248 B
-constexpr int kSmemTab = fl::kWarps * kRing * fl::LEVELS * kRecBytes;   // 2,048 B
-constexpr int kSmemBars = fl::kWarps * kRing * 8;
-constexpr int kFwdSmemBytes = kRingBytes + fl::kSmemOut + kSmemTab + kSmemBars;
+constexpr int kRingBytes = fl::kWarps * kRing * fl::kSlotBytes;      // 53,248 B
+constexpr int kSmemTab = fl::kWarps * kRing * fl::LEVELS * kRecBytes;    // 2,048 B
+constexpr int kOffBytes = fl::kPixPerWarp * fl::TAPS * 8;            // one level's offset records of a warp's 4 pixels: 1,568 B
+constexpr int kSmemOffs = fl::kWarps * 2 * kOffBytes;                // 25,088 B (levels 0 and 1)
+constexpr int kSmallBytes = 64;                                      // coords (32 B) + cumulative masks (16 B), per warp and tile parity
+constexpr int kSmemSmall = fl::kWarps * 2 * kSmallBytes;             // 1,024 B
+constexpr int kBarsPerWarp = kRing + 3;                              // ring slots, offsets, small[2]
+constexpr int kSmemBars = fl::kWarps * kBarsPerWarp * 8;
+constexpr int kOffOut = kRingBytes;
+constexpr int kOffTab = kOffOut + fl::kSmemOut;
+constexpr int kOffOffs = kOffTab + kSmemTab;
+constexpr int kOffSmall = kOffOffs + kSmemOffs;
+constexpr int kOffBars = kOffSmall + kSmemSmall;
+constexpr int kFwdSmemBytes = kOffBars + kSmemBars;                  // 107,600 B: two CTAs per SM
 }  // namespace flf
 
 struct FusedLookupParams {
@@ -54,7 +64,7 @@ struct FusedLookupParams {
                                // straight into the gathered buffer on another GPU (NVLink peer memory), sharded.py
   float* mask_out;       // [E,P] or null: the sigmoid(var) mask of this call
   float* cum_mask;       // [slots,P] or null: running product of the masks of all calls so far (in/out); off1 stays pristine
-  int P, tiles_per_edge;
+  int P, tiles_per_edge, num_tiles;
   int H2[4], W2[4];
   long long off_edge_stride;   // float2 elements between the offset slabs of consecutive edges (0: every edge reads slab 0, Q2)
   int apply_mask;              // 1: level-1 offsets are scaled by sigmoid(var) of this call (CorrBlock); 0: used as given
@@ -66,15 +76,34 @@ __device__ __forceinline__ float4 flf_lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float2 flf_lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float flf_lds(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void flf_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 // PC: per-corner gating (lowMem / altcorr semantics, Q4) instead of top-left gating (Q3)
 // HALF: the 196-channel rows are stored as fp16 (round-to-nearest) -- what `update_op` reads under autocast
 //       (factor_graph.py:284-286); halves the output stream (and the NVLink traffic of the sharded backend)
+//
+// PERSISTENT CTAs (two per SM) walk the 32-pixel tiles with a stride of the grid.  ncu on the per-tile version
+// (profiles/r02_fused_lookup.md) put ~20 % of the warp time into the per-CTA prologue / epilogue (first coords load,
+// first box round trip, the barrier before the store phase) and 11 % into ONE instruction: the first use of a staged box
+// value, stalled on the long scoreboard it shared with the LDG prefetch of the next pixel's offsets.  Here nothing in the
+// pixel loop is an LDG: a tile's offset records (2 x 1,568 B per warp), coords and cumulative masks arrive by
+// cp.async.bulk on their own mbarriers, the next tile's coords are on chip before the current tile ends, and the ring
+// keeps prefetching boxes ACROSS tile boundaries, so the memory pipeline never drains between tiles.
 template <bool PC, bool HALF>
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupParams prm) {
@@ -82,16 +111,15 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
   using namespace flf;
   extern __shared__ __align__(1024) uint8_t smem[];              // no static shared memory: base is 1024-aligned
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* s_out = reinterpret_cast<float*>(smem + kRingBytes);    // [CH][kOutPitch]
-  const uint32_t box_base = fl_smem_u32(smem) + warp * kRing * kSlotBytes;
-  const uint32_t tab_base = fl_smem_u32(smem) + kRingBytes + kSmemOut + warp * kRing * LEVELS * kRecBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes + kSmemOut + kSmemTab) + warp * kRing;
-
+  float* s_out = reinterpret_cast<float*>(smem + kOffOut);       // [CH][kOutPitch]
+  const uint32_t smem0 = fl_smem_u32(smem);
+  const uint32_t box_base = smem0 + warp * kRing * kSlotBytes;
+  const uint32_t tab_base = smem0 + kOffTab + warp * kRing * LEVELS * kRecBytes;
+  const uint32_t offs_base = smem0 + kOffOffs + warp * 2 * kOffBytes;          // [level 0 | level 1][pixel][tap] float2
+  const uint32_t small_base = smem0 + kOffSmall + warp * 2 * kSmallBytes;      // [parity]{coords[4] float2, cum[4] float}
+  const uint32_t bar_base = smem0 + kOffBars + warp * kBarsPerWarp * 8;        // ring[kRing], offsets, small[2]
+  const uint32_t bar_off = bar_base + kRing * 8, bar_small = bar_base + (kRing + 1) * 8;
   const int P = prm.P;
-  const int n = blockIdx.x / prm.tiles_per_edge;
-  const int p0 = (blockIdx.x - n * prm.tiles_per_edge) * kTile;
-  const int pw = p0 + warp * kPixPerWarp;                       // first pixel of this warp (tiles are always full)
-  const int ns = prm.slots != nullptr ? __ldg(prm.slots + n) : n;   // storage slot of this edge (pyramid, offsets)
 
   // ---- per-lane level record: lanes 0..3 own level `lane` of the warp's table (static half written once)
   const int myl = lane & 3;
@@ -107,19 +135,48 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
   }
   if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < kRing; ++q) fl_mbar_init(bars + q, 1);
+    for (int q = 0; q < kBarsPerWarp; ++q)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_base + q * 8));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
 
-  // coords of the warp's pixels: lane k (< 4) loads pixel k, everyone gets them by shuffle
-  float2 cmine = make_float2(0.0f, 0.0f);
-  if (lane < kPixPerWarp) cmine = __ldg(reinterpret_cast<const float2*>(prm.coords) + (size_t)n * P + pw + lane);
+  // tile -> (edge, first pixel of this warp, storage slot)
+  auto tile_edge = [&](int tile, int& n, int& pw, int& ns) {
+    n = tile / prm.tiles_per_edge;
+    pw = (tile - n * prm.tiles_per_edge) * kTile + warp * kPixPerWarp;
+    ns = prm.slots != nullptr ? __ldg(prm.slots + n) : n;
+  };
+  // lane 0: fetch a tile's coords (+ cumulative masks) / offset records into shared memory
+  auto fetch_small = [&](int n, int pw, int ns, int par) {
+    const uint32_t dst = small_base + par * kSmallBytes, bar = bar_small + par * 8;
+    const uint32_t bytes = prm.cum_mask != nullptr ? 48u : 32u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    flf_bulk_g2s(dst, prm.coords + ((size_t)n * P + pw) * 2, 32, bar);
+    if (prm.cum_mask != nullptr) flf_bulk_g2s(dst + 32, prm.cum_mask + (size_t)ns * P + pw, 16, bar);
+  };
+  auto fetch_offsets = [&](int pw, int ns) {
+    const size_t opix = ((size_t)ns * prm.off_edge_stride + (size_t)pw * TAPS) * 2;     // in floats
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_off), "r"(2u * kOffBytes) : "memory");
+    flf_bulk_g2s(offs_base, prm.off0 + opix, kOffBytes, bar_off);
+    flf_bulk_g2s(offs_base + kOffBytes, prm.off1 + opix, kOffBytes, bar_off);
+  };
+  auto wait = [&](uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FLF_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FLF_DONE_%=;\n\t"
+        "bra FLF_WAIT_%=;\n\t"
+        "FLF_DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+  };
 
-  // Issue the four boxes of pixel k: lane l (< 4) scales the coordinates to level l (coords / 2^l as successive exact
-  // halvings, corr.py:103), derives the box origin and writes the dynamic half of its record; lane 0 launches the copies.
-  auto issue = [&](int k, float cx, float cy) {
-    const int slot = k % kRing;
+  // Issue the four boxes of one pixel into ring slot `slot`: lane l (< 4) scales the coordinates to level l (coords / 2^l
+  // as successive exact halvings, corr.py:103), derives the box origin and writes the dynamic half of its record; lane 0
+  // launches the copies.
+  auto issue = [&](int slot, int pix, float cx, float cy) {
 #pragma unroll
     for (int q = 1; q < LEVELS; ++q)
       if (myl >= q) { cx = __fmul_rn(cx, 0.5f); cy = __fmul_rn(cy, 0.5f); }
@@ -133,24 +190,20 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 #pragma unroll
     for (int l = 0; l < LEVELS; ++l) { xs[l] = __shfl_sync(0xffffffffu, xb, l); ys[l] = __shfl_sync(0xffffffffu, yb, l); }
     if (lane == 0) {
-      const int pix = ns * P + pw + k;
-      const uint32_t dst = box_base + slot * kSlotBytes;
-      fl_mbar_expect_tx(bars + slot, kSlotBytes);
+      const uint32_t dst = box_base + slot * kSlotBytes, bar = bar_base + slot * 8;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kSlotBytes) : "memory");
 #pragma unroll
       for (int l = 0; l < LEVELS; ++l) {
         const int o = l == 0 ? kOff0 : (l == 1 ? kOff1 : (l == 2 ? kOff2 : kOff3));
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
                 dst + o * 4),
-            "l"(&maps.m[l]), "r"(fl_smem_u32(bars + slot)), "r"(xs[l]), "r"(ys[l]), "r"(pix)
+            "l"(&maps.m[l]), "r"(bar), "r"(xs[l]), "r"(ys[l]), "r"(pix)
             : "memory");
       }
     }
     __syncwarp();                                               // table records visible to the whole warp
   };
-#pragma unroll
-  for (int q = 0; q < kRing && q < kPixPerWarp; ++q)
-    issue(q, __shfl_sync(0xffffffffu, cmine.x, q), __shfl_sync(0xffffffffu, cmine.y, q));
 
   // ---- per-lane tap constants of the 7 passes: g = pass*32 + lane -> (level, i - r, j - r); the mask taps (r = 1 on
   // level 1) sit on lanes 4..12 of the last pass, whose lanes 0..3 are taps 45..48 of level 3
@@ -171,19 +224,13 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     dj[ps] = j - r;
   }
   const bool is_mask_lane = lane >= 4 && lane < 13;
-
-  // offsets of the deformable levels: flat taps g < 98 live in passes 0..3 (pass 3: lanes 0, 1 only)
-  float2 onext[4];
-  auto load_offsets = [&](int k) {
-    const size_t opix = (size_t)ns * prm.off_edge_stride + (size_t)(pw + k) * TAPS;
-    const float2* O0 = reinterpret_cast<const float2*>(prm.off0) + opix;
-    const float2* O1 = reinterpret_cast<const float2*>(prm.off1) + opix;
-    onext[0] = O0[lane];
-    onext[1] = lane < 17 ? O0[32 + lane] : O1[lane - 17];
-    onext[2] = O1[15 + lane];
-    onext[3] = lane < 2 ? O1[47 + lane] : make_float2(0.0f, 0.0f);
-  };
-  load_offsets(0);
+  // shared-memory address of this lane's offset record in passes 0..3, relative to the pixel's record pair
+  // (flat taps g < 98: pass 0 = level 0 taps 0..31; pass 1 = level 0 taps 32..48 | level 1 taps 0..14; pass 2 = level 1
+  // taps 15..46; pass 3 = level 1 taps 47, 48 on lanes 0, 1)
+  const uint32_t oaddr0 = offs_base + lane * 8;
+  const uint32_t oaddr1 = lane < 17 ? offs_base + (32 + lane) * 8 : offs_base + kOffBytes + (lane - 17) * 8;
+  const uint32_t oaddr2 = offs_base + kOffBytes + (15 + lane) * 8;
+  const uint32_t oaddr3 = offs_base + kOffBytes + (47 + min(lane, 1)) * 8;
 
   // One bilinear tap of the flat index space against the staged boxes (defCorrSample_kernel.cu:56-86).
   auto tap = [&](int slot, int ps, float2 o, size_t pix) -> float {
@@ -218,81 +265,132 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     return tap_value(t);
   };
 
-#pragma unroll 1
-  for (int k = 0; k < kPixPerWarp; ++k) {
-    const int slot = k % kRing;
-    const int p = pw + k;
-    const size_t pix = (size_t)ns * P + p;                      // slice index in the pyramid storage
-    float2 o[4] = {onext[0], onext[1], onext[2], onext[3]};     // this pixel's offsets (loaded one iteration ahead)
-    if (k + 1 < kPixPerWarp) load_offsets(k + 1);
-    float cum = 1.0f;
-    if (prm.cum_mask != nullptr) cum = __ldg(prm.cum_mask + (size_t)ns * P + p);
-
-    fl_mbar_wait(bars + slot, (k / kRing) & 1);
-    float* so = s_out + warp * kPixPerWarp + k;                 // column of this pixel in the output tile
-
-    // ---------------- last pass first: level-3 taps 45..48 (lanes 0..3) + the r=1 mask taps on level 1 (lanes 4..12,
-    // corrSample_kernel.cu:52-77) -> unbiased variance over the 9 taps (torch.var default, corr.py:96) -> sigmoid
-    float m;
-    {
-      const float v = tap(slot, kPasses - 1, make_float2(0.0f, 0.0f), pix);
-      if (lane < 4) so[((kPasses - 1) * 32 + lane) * kOutPitch] = v;
-      const float vm = is_mask_lane ? v : 0.0f;
-      float s = vm;
+  // ---- prologue of the first tile: parameters, offsets, the first kRing pixels' boxes
+  int tile = blockIdx.x;
+  if (tile >= prm.num_tiles) return;
+  int n, pw, ns;
+  tile_edge(tile, n, pw, ns);
+  if (lane == 0) {
+    fetch_small(n, pw, ns, 0);
+    fetch_offsets(pw, ns);
+  }
+  wait(bar_small, 0);
+  {
+    const float2 c0 = flf_lds64(small_base + (lane & 3) * 8);   // lane q holds pixel q's coords (q < 4)
 #pragma unroll
-      for (int sh = 8; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);    // lanes 0..3, 13..15 contribute 0
-      const float mean = __shfl_sync(0xffffffffu, s, 0) / 9.0f;
-      const float d = is_mask_lane ? (vm - mean) : 0.0f;
-      float ss = d * d;
-#pragma unroll
-      for (int sh = 8; sh > 0; sh >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sh);
-      const float var = __shfl_sync(0xffffffffu, ss, 0) * 0.125f;
-      m = 1.0f / (1.0f + expf(-var));
-    }
-    // offset[1] <- offset[1] * mask (Q7) for every tap of level 1 (flat taps 49..97: pass 1 lanes >= 17, pass 2, pass 3
-    // lanes 0..1); with a cumulative-mask buffer the stored offsets stay pristine and the product of all masks so far
-    // is applied instead
-    if (prm.apply_mask) {
-      const float mm = prm.cum_mask != nullptr ? __fmul_rn(cum, m) : m;
-      if (lane >= 17) o[1] = make_float2(__fmul_rn(o[1].x, mm), __fmul_rn(o[1].y, mm));
-      o[2] = make_float2(__fmul_rn(o[2].x, mm), __fmul_rn(o[2].y, mm));
-      o[3] = make_float2(__fmul_rn(o[3].x, mm), __fmul_rn(o[3].y, mm));         // lanes >= 2 hold zeros
-      if (prm.cum_mask != nullptr) {
-        if (lane == 0) prm.cum_mask[(size_t)ns * P + p] = mm;
-      } else {
-        float2* O1 = reinterpret_cast<float2*>(prm.off1) + (size_t)ns * prm.off_edge_stride + (size_t)p * TAPS;
-        if (lane >= 17) O1[lane - 17] = o[1];
-        O1[15 + lane] = o[2];
-        if (lane < 2) O1[47 + lane] = o[3];
-      }
-    }
-    if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[(size_t)n * P + p] = m;
-    // Q5: the centre taps read as 0 (flat taps 24 and 49 + 24 = 73 = pass 2, lane 9)
-    if (lane == CENTER) o[0] = make_float2(0.0f, 0.0f);
-    if (lane == TAPS + CENTER - 64) o[2] = make_float2(0.0f, 0.0f);
-
-#pragma unroll
-    for (int ps = 0; ps < kPasses - 1; ++ps) {
-      const float v = tap(slot, ps, ps < 4 ? o[ps] : make_float2(0.0f, 0.0f), pix);
-      so[(ps * 32 + lane) * kOutPitch] = v;
-    }
-
-    __syncwarp();                                               // every lane is done with this slot
-    if (k + kRing < kPixPerWarp)
-      issue(k + kRing, __shfl_sync(0xffffffffu, cmine.x, k + kRing), __shfl_sync(0xffffffffu, cmine.y, k + kRing));
+    for (int q = 0; q < kRing; ++q)
+      issue(q, ns * P + pw + q, __shfl_sync(0xffffffffu, c0.x, q), __shfl_sync(0xffffffffu, c0.y, q));
   }
 
-  __syncthreads();
-  const size_t row = (size_t)(prm.out_index != nullptr ? __ldg(prm.out_index + n) : n) * CH * P + p0 + lane;
-  const float* srow = s_out + lane;
-  if (HALF) {
-    __half* out = reinterpret_cast<__half*>(prm.out) + row;
+#pragma unroll 1
+  for (int it = 0; tile < prm.num_tiles; ++it, tile += gridDim.x) {
+    const int par = it & 1;
+    const int ntile = tile + gridDim.x;
+    const bool has_next = ntile < prm.num_tiles;
+    int nn = 0, npw = 0, nns = 0;
+    if (has_next) {
+      tile_edge(ntile, nn, npw, nns);
+      if (lane == 0) fetch_small(nn, npw, nns, par ^ 1);        // next tile's coords / masks: on chip long before they are needed
+    }
+    wait(bar_off, par);                                         // this tile's offset records
+    const uint32_t small = small_base + par * kSmallBytes;
+
+#pragma unroll 1
+    for (int k = 0; k < kPixPerWarp; ++k) {
+      const int slot = k % kRing;                               // kPixPerWarp is a multiple of kRing: slots repeat per tile
+      const int p = pw + k;
+      const size_t pix = (size_t)ns * P + p;                    // slice index in the pyramid storage
+      const uint32_t orec = (uint32_t)k * (TAPS * 8);
+      float2 o[4];
+      o[0] = flf_lds64(oaddr0 + orec);
+      o[1] = flf_lds64(oaddr1 + orec);
+      o[2] = flf_lds64(oaddr2 + orec);
+      o[3] = lane < 2 ? flf_lds64(oaddr3 + orec) : make_float2(0.0f, 0.0f);
+      float cum = 1.0f;
+      if (prm.cum_mask != nullptr) cum = flf_lds(small + 32 + k * 4);
+
+      wait(bar_base + slot * 8, ((it * (kPixPerWarp / kRing)) + k / kRing) & 1);
+      float* so = s_out + warp * kPixPerWarp + k;               // column of this pixel in the output tile
+
+      // ---------------- last pass first: level-3 taps 45..48 (lanes 0..3) + the r=1 mask taps on level 1 (lanes 4..12,
+      // corrSample_kernel.cu:52-77) -> unbiased variance over the 9 taps (torch.var default, corr.py:96) -> sigmoid
+      float m;
+      {
+        const float v = tap(slot, kPasses - 1, make_float2(0.0f, 0.0f), pix);
+        if (lane < 4) so[((kPasses - 1) * 32 + lane) * kOutPitch] = v;
+        const float vm = is_mask_lane ? v : 0.0f;
+        float s = vm;
+#pragma unroll
+        for (int sh = 8; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);    // lanes 0..3, 13..15 contribute 0
+        const float mean = __shfl_sync(0xffffffffu, s, 0) / 9.0f;
+        const float d = is_mask_lane ? (vm - mean) : 0.0f;
+        float ss = d * d;
+#pragma unroll
+        for (int sh = 8; sh > 0; sh >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sh);
+        const float var = __shfl_sync(0xffffffffu, ss, 0) * 0.125f;
+        m = 1.0f / (1.0f + expf(-var));
+      }
+      // offset[1] <- offset[1] * mask (Q7) for every tap of level 1 (flat taps 49..97: pass 1 lanes >= 17, pass 2, pass 3
+      // lanes 0..1); with a cumulative-mask buffer the stored offsets stay pristine and the product of all masks so far
+      // is applied instead
+      if (prm.apply_mask) {
+        const float mm = prm.cum_mask != nullptr ? __fmul_rn(cum, m) : m;
+        if (lane >= 17) o[1] = make_float2(__fmul_rn(o[1].x, mm), __fmul_rn(o[1].y, mm));
+        o[2] = make_float2(__fmul_rn(o[2].x, mm), __fmul_rn(o[2].y, mm));
+        o[3] = make_float2(__fmul_rn(o[3].x, mm), __fmul_rn(o[3].y, mm));       // lanes >= 2 hold zeros
+        if (prm.cum_mask != nullptr) {
+          if (lane == 0) prm.cum_mask[(size_t)ns * P + p] = mm;
+        } else {
+          float2* O1 = reinterpret_cast<float2*>(prm.off1) + (size_t)ns * prm.off_edge_stride + (size_t)p * TAPS;
+          if (lane >= 17) O1[lane - 17] = o[1];
+          O1[15 + lane] = o[2];
+          if (lane < 2) O1[47 + lane] = o[3];
+        }
+      }
+      if (lane == 0 && prm.mask_out != nullptr) prm.mask_out[(size_t)n * P + p] = m;
+      // Q5: the centre taps read as 0 (flat taps 24 and 49 + 24 = 73 = pass 2, lane 9)
+      if (lane == CENTER) o[0] = make_float2(0.0f, 0.0f);
+      if (lane == TAPS + CENTER - 64) o[2] = make_float2(0.0f, 0.0f);
+
+#pragma unroll
+      for (int ps = 0; ps < kPasses - 1; ++ps) {
+        const float v = tap(slot, ps, ps < 4 ? o[ps] : make_float2(0.0f, 0.0f), pix);
+        so[(ps * 32 + lane) * kOutPitch] = v;
+      }
+
+      __syncwarp();                                             // every lane is done with this slot
+      // refill the slot: pixel k + kRing of this tile, or pixel k + kRing - 4 of the NEXT tile (prefetch across tiles)
+      const int kn = k + kRing;
+      if (kn < kPixPerWarp) {
+        const float2 c = flf_lds64(small + (lane & 3) * 8);
+        issue(slot, ns * P + pw + kn, __shfl_sync(0xffffffffu, c.x, kn), __shfl_sync(0xffffffffu, c.y, kn));
+      } else if (has_next) {
+        if (kn == kPixPerWarp) wait(bar_small + (par ^ 1) * 8, ((it + 1) >> 1) & 1);
+        const float2 c = flf_lds64(small_base + (par ^ 1) * kSmallBytes + (lane & 3) * 8);
+        const int q = kn - kPixPerWarp;
+        issue(slot, nns * P + npw + q, __shfl_sync(0xffffffffu, c.x, q), __shfl_sync(0xffffffffu, c.y, q));
+      }
+    }
+    // the warp has consumed this tile's offset records: fetch the next tile's behind the store phase
+    if (has_next && lane == 0) fetch_offsets(npw, nns);
+
+    __syncthreads();
+    {
+      const int p0 = pw - warp * kPixPerWarp;
+      const size_t row = (size_t)(prm.out_index != nullptr ? __ldg(prm.out_index + n) : n) * CH * P + p0 + lane;
+      const float* srow = s_out + lane;
+      if (HALF) {
+        __half* out = reinterpret_cast<__half*>(prm.out) + row;
 #pragma unroll 4
-    for (int ch = warp; ch < CH; ch += kWarps) out[(size_t)ch * P] = __float2half_rn(srow[ch * kOutPitch]);
-  } else {
-    float* out = reinterpret_cast<float*>(prm.out) + row;
+        for (int ch = warp; ch < CH; ch += kWarps) out[(size_t)ch * P] = __float2half_rn(srow[ch * kOutPitch]);
+      } else {
+        float* out = reinterpret_cast<float*>(prm.out) + row;
 #pragma unroll 4
-    for (int ch = warp; ch < CH; ch += kWarps) __stcs(out + (size_t)ch * P, srow[ch * kOutPitch]);
+        for (int ch = warp; ch < CH; ch += kWarps) __stcs(out + (size_t)ch * P, srow[ch * kOutPitch]);
+      }
+    }
+    __syncthreads();                                            // the tile buffer is free for the next tile
+    n = nn; pw = npw; ns = nns;
   }
 }
 
@@ -365,6 +463,10 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
   const float* lv[4] = {lvl0, lvl1, lvl2, lvl3};
   for (int l = 0; l < 4; ++l)
     LGU_REQUIRE((reinterpret_cast<uintptr_t>(lv[l]) & 15) == 0, "lgu_corr_lookup_fused: level %d is not 16-byte aligned", l);
+  // the tile inputs travel by cp.async.bulk: 16-byte aligned sources (always true for whole torch tensors)
+  LGU_REQUIRE(((reinterpret_cast<uintptr_t>(coords) | reinterpret_cast<uintptr_t>(off0) | reinterpret_cast<uintptr_t>(off1) |
+                reinterpret_cast<uintptr_t>(cum_mask)) & 15) == 0,
+              "lgu_corr_lookup_fused: coords / offsets / cum_mask must be 16-byte aligned");
   FusedMaps maps;
   FusedLookupParams prm;
   for (int l = 0; l < 4; ++l) {
@@ -379,9 +481,14 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
   prm.cum_mask = cum_mask;
   prm.out_index = out_index;
   prm.P = P;
-  prm.tiles_per_edge = (P + fl::kTile - 1) / fl::kTile;
-  const long long nblk = (long long)E * prm.tiles_per_edge;
-  LGU_REQUIRE(nblk < 2147483647LL, "lgu_corr_lookup_fused: grid too large (%lld CTAs)", nblk);
+  prm.tiles_per_edge = P / fl::kTile;                         // W % 32 == 0: tiles are always full
+  const long long ntiles = (long long)E * prm.tiles_per_edge;
+  LGU_REQUIRE(ntiles < 2147483647LL, "lgu_corr_lookup_fused: too many tiles (%lld)", ntiles);
+  prm.num_tiles = (int)ntiles;
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long nblk = ntiles < 2LL * sms ? ntiles : 2LL * sms;   // persistent: two CTAs per SM
   prm.off_edge_stride = shared_offsets ? 0 : (long long)P * fl::TAPS;
   prm.apply_mask = apply_mask;
   prm.slots = slots;

@@ -49,6 +49,8 @@ struct FusedLookupBwdParams {
   const float* off0;         // [E,P,49,2]  as used by the forward (centre tap reads as 0)
   const float* off1;         // [E,P,49,2]  post-mask offsets (offset[1]_out of the forward)
   const float* mask;         // [E,P]       m of the forward
+  const float* off1_scale;   // [E,P] or null: off1 holds PRISTINE offsets and offset[1]_out = off1 * off1_scale (the forward's
+                             // cumulative-mask form, lgu_corr_lookup_fused_cum: off1_scale = cum_mask after that call)
   const float* g_out;        // [E,196,P]   upstream gradient of corr
   const float* g_off1_out;   // [E,P,49,2]  upstream gradient of offset[1]_out (later calls), or null
   float* gv[4];              // dense volume gradients [E,P,H2,W2]
@@ -326,6 +328,11 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
     const float2* O0 = reinterpret_cast<const float2*>(prm.off0) + pix * TAPS;
     const float2* O1 = reinterpret_cast<const float2*>(prm.off1) + pix * TAPS;
     a0 = O0[t0]; a1 = O0[t1c]; b0 = O1[t0]; b1 = O1[t1c];
+    if (prm.off1_scale != nullptr) {                              // same product, same rounding as the forward
+      const float sc = __ldg(prm.off1_scale + pix);
+      b0 = make_float2(__fmul_rn(b0.x, sc), __fmul_rn(b0.y, sc));
+      b1 = make_float2(__fmul_rn(b1.x, sc), __fmul_rn(b1.y, sc));
+    }
     u0 = u1 = make_float2(0.0f, 0.0f);
     if (prm.g_off1_out != nullptr) {
       const float2* U = reinterpret_cast<const float2*>(prm.g_off1_out) + pix * TAPS;
@@ -573,7 +580,17 @@ static int launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, const f
                                    const float* off1_out, const float* mask, const float* corr_grad,
                                    const float* off1_out_grad, float* gv0, float* gv1, float* gv2, float* gv3,
                                    float* off0_grad, float* off1_grad, int E, int H, int W, int num_levels, int radius,
-                                   bool accumulate, void* stream);
+                                   bool accumulate, const float* off1_scale, void* stream);
+}
+extern "C" int lgu_corr_lookup_fused_backward_cum(const float* lvl0, const float* lvl1, const float* coords,
+                                                  const float* off0, const float* off1, const float* cum_mask,
+                                                  const float* mask, const float* corr_grad, const float* off1_out_grad,
+                                                  float* gv0, float* gv1, float* gv2, float* gv3, float* off0_grad,
+                                                  float* off1_grad, int E, int H, int W, int num_levels, int radius,
+                                                  int accumulate, void* stream) {
+  LGU_REQUIRE(E == 0 || cum_mask != nullptr, "lgu_corr_lookup_fused_backward_cum: null cumulative-mask buffer");
+  return lgu::launch_lookup_fused_bwd(lvl0, lvl1, coords, off0, off1, mask, corr_grad, off1_out_grad, gv0, gv1, gv2, gv3,
+                                      off0_grad, off1_grad, E, H, W, num_levels, radius, accumulate != 0, cum_mask, stream);
 }
 extern "C" int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lvl1, const float* coords,
                                               const float* off0, const float* off1_out, const float* mask,
@@ -581,7 +598,7 @@ extern "C" int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lv
                                               float* gv1, float* gv2, float* gv3, float* off0_grad, float* off1_grad,
                                               int E, int H, int W, int num_levels, int radius, void* stream) {
   return lgu::launch_lookup_fused_bwd(lvl0, lvl1, coords, off0, off1_out, mask, corr_grad, off1_out_grad, gv0, gv1, gv2,
-                                      gv3, off0_grad, off1_grad, E, H, W, num_levels, radius, false, stream);
+                                      gv3, off0_grad, off1_grad, E, H, W, num_levels, radius, false, nullptr, stream);
 }
 extern "C" int lgu_corr_lookup_fused_backward_accumulate(const float* lvl0, const float* lvl1, const float* coords,
                                                          const float* off0, const float* off1_out, const float* mask,
@@ -590,13 +607,13 @@ extern "C" int lgu_corr_lookup_fused_backward_accumulate(const float* lvl0, cons
                                                          float* off0_grad, float* off1_grad, int E, int H, int W,
                                                          int num_levels, int radius, void* stream) {
   return lgu::launch_lookup_fused_bwd(lvl0, lvl1, coords, off0, off1_out, mask, corr_grad, off1_out_grad, gv0, gv1, gv2,
-                                      gv3, off0_grad, off1_grad, E, H, W, num_levels, radius, true, stream);
+                                      gv3, off0_grad, off1_grad, E, H, W, num_levels, radius, true, nullptr, stream);
 }
 static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, const float* coords, const float* off0,
                                         const float* off1_out, const float* mask, const float* corr_grad,
                                         const float* off1_out_grad, float* gv0, float* gv1, float* gv2, float* gv3,
                                         float* off0_grad, float* off1_grad, int E, int H, int W, int num_levels,
-                                        int radius, bool accumulate, void* stream) {
+                                        int radius, bool accumulate, const float* off1_scale, void* stream) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(lvl0 && lvl1 && coords && off0 && off1_out && mask && corr_grad && gv0 && gv1 && gv2 && gv3 &&
@@ -633,6 +650,7 @@ static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, co
   maps.m[3] = maps.m[0];
   prm.coords = coords; prm.off0 = off0; prm.off1 = off1_out; prm.mask = mask; prm.g_out = corr_grad;
   prm.g_off1_out = off1_out_grad; prm.g_off0 = off0_grad; prm.g_off1 = off1_grad;
+  prm.off1_scale = off1_scale;
   prm.P = P;
   prm.tiles_per_edge = P / fl::kTile;
   const long long nblk = (long long)E * prm.tiles_per_edge;

@@ -317,13 +317,15 @@ def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False, 
 
 
 def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad, off1_out_grad=None,
-                               accumulate_into=None):
+                               accumulate_into=None, cum_mask=None):
     """Backward of corr_lookup_fused in one launch (what autograd runs for corr.py:88-109 in training).
     pyramid: the 4 levels (only levels 0-1 are read); off1_out: off1 after the forward; mask [E,H,W] from the
     forward; corr_grad [E,196,H,W]; off1_out_grad: upstream gradient on the post-mask offsets (later calls) or None.
     Returns (gv0, gv1, gv2, gv3, off0_grad, off1_grad) -- dense level gradients, off1_grad w.r.t. the PRE-mask off1.
     accumulate_into: 4 persistent level-gradient buffers (same shapes as the pyramid, zeroed once by the caller); the
-    launch ADDS this call's gradient into them, touching only the per-pixel footprints, and returns them as gv0..gv3."""
+    launch ADDS this call's gradient into them, touching only the per-pixel footprints, and returns them as gv0..gv3.
+    cum_mask [E,H,W]: the forward ran in the cumulative-mask form -- `off1_out` is then the PRISTINE offset[1] and the
+    post-mask offsets are off1_out * cum_mask (cum_mask as left by that forward), formed in registers."""
     E, H, W = pyramid[0].shape[:3]
     for l, t in enumerate(pyramid):
         _chk(t, f"pyramid[{l}]", 5)
@@ -348,6 +350,18 @@ def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad,
         fn = _lib.lib().lgu_corr_lookup_fused_backward
     g0 = torch.empty(E, H, W, 98, dtype=torch.float32, device=coords.device)
     g1 = torch.empty_like(g0)
+    if cum_mask is not None:
+        _chk(cum_mask, "cum_mask", 3)
+        if tuple(cum_mask.shape) != (E, H, W):
+            raise RuntimeError("cum_mask must be [E,H,W]")
+        with torch.cuda.device(coords.device):
+            st = _lib.lib().lgu_corr_lookup_fused_backward_cum(
+                _p(pyramid[0]), _p(pyramid[1]), _p(coords), _p(off0), _p(off1_out), _p(cum_mask), _p(mask), _p(corr_grad),
+                _p(off1_out_grad) if off1_out_grad is not None else ctypes.c_void_p(0),
+                _p(gv[0]), _p(gv[1]), _p(gv[2]), _p(gv[3]), _p(g0), _p(g1), _i(E), _i(H), _i(W), _i(4), _i(3),
+                _i(1 if accumulate_into is not None else 0), _stream(coords))
+        _lib.check(st, "corr_lookup_fused_backward (cum)")
+        return gv[0], gv[1], gv[2], gv[3], g0, g1
     with torch.cuda.device(coords.device):
         st = fn(
             _p(pyramid[0]), _p(pyramid[1]), _p(coords), _p(off0), _p(off1_out), _p(mask), _p(corr_grad),

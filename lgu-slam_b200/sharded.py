@@ -115,10 +115,11 @@ class PeerOutput:
 
     Lifetime: create once (collective), reuse every step, `close()` collectively before the process group goes away."""
 
-    def __init__(self, num_edges, per_edge_shape, dtype, device, dst=0, group=None):
+    def __init__(self, num_edges, per_edge_shape, dtype, device, dst=0, group=None, single_process=False):
         self.group, self.dst = group, dst
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        alone = single_process or not dist.is_initialized()
+        self.rank = dst if alone else dist.get_rank(group)
+        self.world = 1 if alone else dist.get_world_size(group)
         self.device = torch.device(device)
         shape = (int(num_edges),) + tuple(int(x) for x in per_edge_shape)
         self._path = None
@@ -202,12 +203,16 @@ class ShardedBackendCorr:
 
     compute: callable(coords [1,e,H,W,2], ii [e], jj [e]) -> [1,e,CH,H,W] on `coords.device`."""
 
-    def __init__(self, compute: Callable, group=None):
+    def __init__(self, compute: Callable, group=None, single_process=False):
+        """single_process=True: behave as a one-rank job even inside an initialised process group (every chunk is
+        local, no collective is ever called) -- the 1-GPU arm of a strong-scaling measurement."""
         self.compute = compute
         self.group = group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        alone = single_process or not dist.is_initialized()
+        self.rank = 0 if alone else dist.get_rank(group)
+        self.world = 1 if alone else dist.get_world_size(group)
         self.plan: Optional[EdgePlan] = None
+        self._idx = {}
         try:
             import inspect
             params = inspect.signature(compute).parameters
@@ -217,7 +222,16 @@ class ShardedBackendCorr:
 
     def set_edges(self, ii, jj, frames_per_chunk=FRAMES_PER_CHUNK):
         self.plan = partition_edges(ii, jj, self.world, frames_per_chunk)
+        self._idx = {}
         return self.plan
+
+    def _chunk_index(self, c, dev):
+        """Edge positions of chunk c on `dev` (int64 for indexing, int32 for the kernels), uploaded once per plan."""
+        key = (c, str(dev))
+        if key not in self._idx:
+            vd = self.plan.chunk_edges[c].to(dev)
+            self._idx[key] = (vd, vd.to(torch.int32))
+        return self._idx[key]
 
     def local_lookup(self, coords, ii, jj):
         """This rank's share: outputs [1,E_local,CH,H,W] in the order of plan.rank_edges[rank] (None if it owns none)."""
@@ -274,21 +288,26 @@ class ShardedBackendCorr:
             full[:, plan.chunk_edges[c].to(dev)] = buf[None]
         return full
 
-    def lookup_into_peer(self, coords, ii, jj, peer: PeerOutput, sync=True):
+    def lookup_into_peer(self, coords, ii, jj, peer: PeerOutput, sync=True, coords_are_local=False):
         """gather="dst" with NO collective on the data path: every rank runs its chunks with the destination buffer as the
         kernels' output tensor (`compute(..., out=peer.buffer, out_index=positions)` -- AltCorrBlock's fused lookup stores
         its 196-channel rows through NVLink peer memory, edge e at row positions[e]); a compute callable without that
         signature is served by peer-to-peer copies of its result.  One barrier at the end publishes the step
-        (`sync=False` leaves it to the caller, e.g. to overlap several steps).  Returns peer.result()."""
+        (`sync=False` leaves it to the caller, e.g. to overlap several steps).  Returns peer.result().
+        coords_are_local: `coords` holds only this rank's edges, [1,E_local,...] in the order of plan.rank_edges[rank]
+        (a rank then uploads 1/N of the coordinates per step)."""
         assert self.plan is not None, "call set_edges(ii, jj) first"
         plan, dev = self.plan, coords.device
+        at = 0
         for c in plan.rank_chunks[self.rank]:
             v = plan.chunk_edges[c]
-            vd = v.to(dev)
+            vd, vd32 = self._chunk_index(c, dev)
+            cc = coords[:, at:at + v.numel()] if coords_are_local else coords[:, vd]
+            at += v.numel()
             if self._writes_in_place:
-                self.compute(coords[:, vd], ii[vd], jj[vd], out=peer.buffer, out_index=vd.to(torch.int32))
+                self.compute(cc, ii[vd], jj[vd], out=peer.buffer, out_index=vd32)
             else:                                                  # plain callable: copy its result over
-                res = self.compute(coords[:, vd], ii[vd], jj[vd])[0].to(peer.buffer.dtype)
+                res = self.compute(cc, ii[vd], jj[vd])[0].to(peer.buffer.dtype)
                 pos = v.tolist()
                 k = 0
                 while k < len(pos):                                # runs of consecutive positions -> one copy each

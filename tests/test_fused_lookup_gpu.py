@@ -272,3 +272,25 @@ def test_fused_lookup_cumulative_mask_mode_equals_write_back_mode(ops):
         assert (got[:, 49:98] - want[:, 49:98]).abs().max().item() <= 1e-5 * scale, f"call {step} level 1"
         assert (m_c - m_w).abs().max().item() <= 1e-6
         assert ((off1 * cum.view(E, 48, 64, 1)) - wb).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_fused_backward_cumulative_mask_form_equals_materialised_form(ops, accumulate):
+    """lgu_corr_lookup_fused_backward_cum (pristine offset[1] + the running mask product) against the entry point that
+    reads the materialised post-mask offsets: bit-identical level and offset gradients."""
+    E, dev = 2, "cuda"
+    g = inputs.gen(91)
+    pyr = [torch.randn(E, 48, 64, 48 >> l, 64 >> l, generator=g).to(dev) for l in range(4)]
+    c = _case(E, 92)
+    coords, off0, off1 = c["coords"].to(dev), c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+    cum = torch.ones(E, 48, 64, device=dev)
+    for _ in range(2):                                            # second call: cum_mask = m1 * m2
+        _, mask = ops.corr_lookup_fused(pyr, coords, off0, off1, 3, return_mask=True, cum_mask=cum)
+    g_corr = torch.randn(E, 196, 48, 64, generator=g).to(dev)
+    off1_out = (off1 * cum.unsqueeze(-1)).contiguous()
+    acc_a = [torch.zeros_like(p) for p in pyr] if accumulate else None
+    acc_b = [torch.zeros_like(p) for p in pyr] if accumulate else None
+    want = ops.corr_lookup_fused_backward(pyr, coords, off0, off1_out, mask, g_corr, accumulate_into=acc_a)
+    got = ops.corr_lookup_fused_backward(pyr, coords, off0, off1, mask, g_corr, accumulate_into=acc_b, cum_mask=cum)
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert torch.equal(a, b), f"output {k}"
