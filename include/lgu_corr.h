@@ -289,6 +289,19 @@ LGU_API int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, const
 LGU_API int lgu_pack_fmaps(const void* fmaps, int src_is_half, void* hi, void* lo,
                    int T, int C, int P, void* stream);
 
+/* --------------------------------------------------------------------------
+ * Peer-visible device memory for the edge-sharded backend (no reference counterpart: the reference is single-GPU).
+ * lgu_peer_alloc: cudaMalloc on the current device + its CUDA IPC handle (64 bytes) for the other ranks of the box;
+ * lgu_peer_open:  map that allocation into the calling process WITH THE CALLER'S DEVICE CURRENT (peer access over
+ *                 NVLink / NVSwitch is switched on for that device), so its kernels can store straight into the owner's
+ *                 HBM (lgu_altcorr_lookup_fused_into with out = the mapped pointer);
+ * lgu_peer_close / lgu_peer_free: unmap / release.
+ * ------------------------------------------------------------------------ */
+LGU_API int lgu_peer_alloc(long long bytes, void** ptr, void* handle64);
+LGU_API int lgu_peer_open(const void* handle64, void** ptr);
+LGU_API int lgu_peer_close(void* ptr);
+LGU_API int lgu_peer_free(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

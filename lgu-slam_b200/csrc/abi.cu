@@ -91,6 +91,57 @@ void map_cache_put(const MapKey& key, const void* map128) {
 }  // namespace lgu
 
 extern "C" {
+// ---- peer-visible device memory (the gathered output buffer of the sharded backend, lgu-slam_b200/sharded.py) ---------
+int lgu_peer_alloc(long long bytes, void** ptr, void* handle64) {
+  LGU_REQUIRE(bytes > 0 && ptr != nullptr && handle64 != nullptr, "lgu_peer_alloc: bad arguments");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);                 // a plain cudaMalloc allocation: exportable by CUDA IPC
+  if (e != cudaSuccess) {
+    lgu::set_error("lgu_peer_alloc: cudaMalloc(%lld) failed: %s", bytes, cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    lgu::set_error("lgu_peer_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return LGU_OK;
+}
+int lgu_peer_open(const void* handle64, void** ptr) {
+  LGU_REQUIRE(handle64 != nullptr && ptr != nullptr, "lgu_peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  // opened with the CALLER's device current: the mapping (and peer access to the owning GPU) belongs to the device whose
+  // kernels will store through it
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    lgu::set_error("lgu_peer_open: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  return LGU_OK;
+}
+int lgu_peer_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) {
+    lgu::set_error("lgu_peer_close: %s", cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  return LGU_OK;
+}
+int lgu_peer_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) {
+    lgu::set_error("lgu_peer_free: %s", cudaGetErrorString(e));
+    return LGU_ERR_LAUNCH;
+  }
+  return LGU_OK;
+}
+
 int lgu_abi_version(void) { return 1; }
 const char* lgu_build_info(void) {
   return "lgu_corr sm_100a, nvcc " LGU_STR(__CUDACC_VER_MAJOR__) "." LGU_STR(__CUDACC_VER_MINOR__) ", built " __DATE__;

@@ -126,19 +126,25 @@ class PeerOutput:
         self._own = None
         if self.device.type == "cuda":
             self.transport = "cuda-ipc peer stores (NVLink)" if self.world > 1 else "local"
-            if self.rank == dst:
-                self._own = torch.zeros(shape, dtype=dtype, device=self.device)
-                torch.cuda.synchronize(self.device)
-            self.buffer = self._own
-            if self.world > 1:
-                from torch.multiprocessing.reductions import reduce_tensor
-                box = [reduce_tensor(self._own)[1] if self.rank == dst else None]
-                dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst,
-                                           group=group)
-                if self.rank != dst:
-                    from torch.multiprocessing.reductions import rebuild_cuda_tensor
-                    self.buffer = rebuild_cuda_tensor(*box[0])
-                    self._enable_peer(self.device.index, self.buffer.device.index)
+            self._ptr, self._opened = None, False
+            nbytes = torch.empty(0, dtype=dtype).element_size()
+            for x in shape:
+                nbytes *= x
+            box = [None]
+            with torch.cuda.device(self.device):
+                if self.rank == dst:
+                    self._ptr, handle = self._native_alloc(nbytes)
+                    box = [handle]
+                if self.world > 1:
+                    dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst,
+                                               group=group)
+                    if self.rank != dst:
+                        self._ptr = self._native_open(box[0])     # mapped with THIS rank's device current
+                        self._opened = True
+                self.buffer = self._wrap(self._ptr, shape, dtype)
+                if self.rank == dst:
+                    self.buffer.zero_()
+                    torch.cuda.synchronize(self.device)
         else:
             import os
             import tempfile
@@ -163,19 +169,35 @@ class PeerOutput:
         if self.world > 1:
             dist.barrier(group=group)                       # the zero-fill on `dst` precedes every remote store
 
+    # ---- raw device memory through the C ABI (lgu_peer_*): a plain cudaMalloc allocation + its CUDA IPC handle
     @staticmethod
-    def _enable_peer(device, peer):
-        """Kernels of `device` dereference pointers into `peer`'s HBM: peer access must be on in this direction."""
-        if device == peer:
-            return
-        if not torch.cuda.can_device_access_peer(device, peer):
-            raise RuntimeError(f"cuda:{device} cannot access cuda:{peer} as a peer (no NVLink / P2P path)")
-        # a device-to-device copy makes torch switch peer access on for the pair (cudaDeviceEnablePeerAccess)
-        a = torch.zeros(1, device=f"cuda:{device}")
-        b = torch.zeros(1, device=f"cuda:{peer}")
-        b.copy_(a)
-        a.copy_(b)
-        torch.cuda.synchronize(device)
+    def _lib():
+        import ctypes
+        from . import _lib
+        return _lib, ctypes
+
+    @classmethod
+    def _native_alloc(cls, nbytes):
+        _lib, ctypes = cls._lib()
+        ptr, handle = ctypes.c_void_p(0), ctypes.create_string_buffer(64)
+        _lib.check(_lib.lib().lgu_peer_alloc(ctypes.c_longlong(nbytes), ctypes.byref(ptr), handle), "peer_alloc")
+        return ptr.value, handle.raw
+
+    @classmethod
+    def _native_open(cls, handle):
+        _lib, ctypes = cls._lib()
+        ptr = ctypes.c_void_p(0)
+        _lib.check(_lib.lib().lgu_peer_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr)), "peer_open")
+        return ptr.value
+
+    @staticmethod
+    def _wrap(ptr, shape, dtype):
+        """A torch tensor aliasing raw device memory (CUDA array interface, zero copy)."""
+        typestr = {torch.float32: "<f4", torch.float16: "<f2"}[dtype]
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(_Mem(), device="cuda")
 
     def result(self):
         """[1, E, ...] on `dst` (call after `ShardedBackendCorr.lookup_into_peer` returned), None elsewhere."""
@@ -184,11 +206,22 @@ class PeerOutput:
     def close(self):
         if self.world > 1:
             dist.barrier(group=self.group)
-        if self.rank != self.dst:
-            self.buffer = None                              # drop the mapping before the owner frees the memory
+        ptr = getattr(self, "_ptr", None)
+        self.buffer = None
+        if self.device.type == "cuda" and ptr is not None:
+            _lib, ctypes = self._lib()
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                if self._opened:
+                    _lib.lib().lgu_peer_close(ctypes.c_void_p(ptr))   # drop the mapping before the owner frees the memory
+            self._ptr = None
         if self.world > 1:
             dist.barrier(group=self.group)
-        self.buffer = self._own = None
+        if self.device.type == "cuda" and ptr is not None and not self._opened:
+            _lib, ctypes = self._lib()
+            with torch.cuda.device(self.device):
+                _lib.lib().lgu_peer_free(ctypes.c_void_p(ptr))
+        self._own = None
         if self._path is not None:
             import os
             try:
