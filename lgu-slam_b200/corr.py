@@ -702,8 +702,9 @@ class AltCorrBlock:
         t = torch.cat(((f1 * 4.0).permute(0, 3, 1, 2), (f2 * 4.0).permute(0, 3, 1, 2)), dim=1).float()
         return _generate_offsets(self.ofsMap, self.ofs_residual, t)
 
-    def _corr_materialized(self, coords, ii, jj, out=None, out_index=None):
+    def _corr_materialized(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None):
         B, N, H, W, S, _ = coords.shape
+        step = min(self.MAX_EDGES_PER_PASS, int(pass_edges)) if pass_edges else self.MAX_EDGES_PER_PASS
         assert B == 1 and S == 1, "the materialised path serves the reference's only call shape (B = S = 1)"
         planes = self._level_planes()
         c = coords.reshape(N, H, W, 2).float().contiguous()
@@ -731,8 +732,8 @@ class AltCorrBlock:
             mask0 = torch.sigmoid(torch.var(m0.permute(0, 1, 3, 4, 2).reshape(1, H, W, 9), dim=3))
             slab0 = (off0[:1].contiguous(), (off1[:1] * mask0.view(1, H, W, 1)).contiguous())
         outs, masks, new_off1 = [], [], []
-        for s in range(0, N, self.MAX_EDGES_PER_PASS):
-            e = slice(s, min(N, s + self.MAX_EDGES_PER_PASS))
+        for s in range(0, N, step):
+            e = slice(s, min(N, s + step))
             vols = ent["vols"].get(s) if ent is not None else None
             if vols is None:
                 vols = [ops.build_volume(planes[0][0], planes[0][1], planes[l][0], planes[l][1], ii32[e], jj32[e])
@@ -756,6 +757,8 @@ class AltCorrBlock:
             outs.append(o)
             masks.append(m)
             del vols
+            if pass_hook is not None:                             # rows e.start .. e.stop of this call are enqueued
+                pass_hook(e.start, e.stop)
         # the attribute the reference leaves behind: offset[1] * mask (corr.py:206)
         if self.strict_ref:
             if n_off == N:
@@ -769,11 +772,11 @@ class AltCorrBlock:
         res = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
         return res.view(B, N, -1, H, W, 1)
 
-    def corr_fn(self, coords, ii, jj, out=None, out_index=None):
+    def corr_fn(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None):
         B, N, H, W, S, _ = coords.shape
         rd = 2 * self.radius + 1
         if self.materialize and B == 1 and S == 1:
-            return self._corr_materialized(coords, ii, jj, out, out_index)
+            return self._corr_materialized(coords, ii, jj, out, out_index, pass_edges, pass_hook)
         if out is not None:
             raise RuntimeError("out= needs the materialised path (4 levels, r = 3, C = 128, B = S = 1)")
         f1 = self.pyramid[0][:, ii]
@@ -802,14 +805,16 @@ class AltCorrBlock:
             out.append(corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2))
         return torch.cat(out, dim=2)
 
-    def __call__(self, coords, ii, jj, out=None, out_index=None):
+    def __call__(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None):
         """corr.py:238-249.  out / out_index (materialised path only): write edge e's [196,H,W] result into row
         out_index[e] of `out` ([E_out,196,H,W], fp32 or fp16 -- possibly another GPU's memory, see sharded.PeerOutput)
-        instead of returning a new tensor; `out` is returned."""
+        instead of returning a new tensor; `out` is returned.  pass_edges / pass_hook: the chunk is processed in passes of
+        at most pass_edges edges (volumes + lookup per pass) and pass_hook(first, last) is called after each pass's
+        launches are enqueued -- the sharded backend ships finished rows while the next pass computes."""
         squeeze = coords.dim() == 5
         if squeeze:
             coords = coords.unsqueeze(dim=-2)
-        corr = self.corr_fn(coords, ii, jj, out, out_index)
+        corr = self.corr_fn(coords, ii, jj, out, out_index, pass_edges, pass_hook)
         if out is not None:
             return out
         if squeeze:

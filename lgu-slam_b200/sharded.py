@@ -115,8 +115,20 @@ class PeerOutput:
 
     Lifetime: create once (collective), reuse every step, `close()` collectively before the process group goes away."""
 
-    def __init__(self, num_edges, per_edge_shape, dtype, device, dst=0, group=None, single_process=False):
+    def __init__(self, num_edges, per_edge_shape, dtype, device, dst=0, group=None, single_process=False, plan=None):
+        """plan (an EdgePlan): rows are laid out CHUNK-MAJOR -- chunk c of the reference loop occupies the contiguous rows
+        chunk_rows[c] .. chunk_rows[c] + len(chunk c), which is how the consumer walks them (factor_graph.py:272-279
+        runs update_op chunk by chunk) and lets a rank ship a whole chunk with one peer-to-peer copy; `row_of_edge`
+        maps an edge position to its row (-1: never visited).  Without a plan, row = edge position."""
         self.group, self.dst = group, dst
+        self.chunk_rows, self.row_of_edge = None, None
+        if plan is not None:
+            self.chunk_rows, at = [], 0
+            self.row_of_edge = torch.full((int(num_edges),), -1, dtype=torch.int64)
+            for v in plan.chunk_edges:
+                self.chunk_rows.append(at)
+                self.row_of_edge[v] = torch.arange(at, at + v.numel())
+                at += int(v.numel())
         alone = single_process or not dist.is_initialized()
         self.rank = dst if alone else dist.get_rank(group)
         self.world = 1 if alone else dist.get_world_size(group)
@@ -250,8 +262,9 @@ class ShardedBackendCorr:
             import inspect
             params = inspect.signature(compute).parameters
             self._writes_in_place = "out" in params and "out_index" in params
+            self._has_pass_hook = "pass_hook" in params and "pass_edges" in params
         except (TypeError, ValueError):
-            self._writes_in_place = False
+            self._writes_in_place = self._has_pass_hook = False
 
     def set_edges(self, ii, jj, frames_per_chunk=FRAMES_PER_CHUNK):
         self.plan = partition_edges(ii, jj, self.world, frames_per_chunk)
@@ -321,40 +334,105 @@ class ShardedBackendCorr:
             full[:, plan.chunk_edges[c].to(dev)] = buf[None]
         return full
 
-    def lookup_into_peer(self, coords, ii, jj, peer: PeerOutput, sync=True, coords_are_local=False):
-        """gather="dst" with NO collective on the data path: every rank runs its chunks with the destination buffer as the
-        kernels' output tensor (`compute(..., out=peer.buffer, out_index=positions)` -- AltCorrBlock's fused lookup stores
-        its 196-channel rows through NVLink peer memory, edge e at row positions[e]); a compute callable without that
-        signature is served by peer-to-peer copies of its result.  One barrier at the end publishes the step
-        (`sync=False` leaves it to the caller, e.g. to overlap several steps).  Returns peer.result().
+    # via="copy": whole chunks are shipped behind the NEXT chunk's compute; the rank's LAST chunk has nothing to hide behind,
+    # so it runs in passes of SHIP_EDGES edges and only its last pass's rows are exposed (37 edges x 24 row tiles = 6 full
+    # waves of the 148-CTA volume build)
+    SHIP_EDGES = 37
+
+    def lookup_into_peer(self, coords, ii, jj, peer: PeerOutput, sync=True, coords_are_local=False, via="store"):
+        """gather="dst" with NO collective on the data path.  via="store": every rank runs its chunks with the destination
+        buffer as the kernels' output tensor (`compute(..., out=peer.buffer, out_index=rows)` -- AltCorrBlock's fused
+        lookup stores its 196-channel rows through NVLink peer memory).  via="copy": the chunk is computed into a local
+        staging buffer and shipped by an asynchronous peer-to-peer copy on a side stream (the copy engines move it while
+        the SMs build the next chunk's volumes; measured at 8 GPUs the direct stores of all ranks' lookups collide on the
+        destination's NVLink ingress, see profiles/r02_backend_scaling.md); with a chunk-major PeerOutput that is one
+        copy per chunk.  A compute callable without out= support is served by copies of its result.  One barrier at the end
+        publishes the step (`sync=False` leaves it to the caller).  Returns peer.result().
         coords_are_local: `coords` holds only this rank's edges, [1,E_local,...] in the order of plan.rank_edges[rank]
         (a rank then uploads 1/N of the coordinates per step)."""
         assert self.plan is not None, "call set_edges(ii, jj) first"
         plan, dev = self.plan, coords.device
+        staged = via == "copy" and dev.type == "cuda" and self._writes_in_place and self.rank != peer.dst
+        if staged:
+            self._ensure_staging(peer, dev)
+            cur = torch.cuda.current_stream(dev)
         at = 0
-        for c in plan.rank_chunks[self.rank]:
+        for k, c in enumerate(plan.rank_chunks[self.rank]):
             v = plan.chunk_edges[c]
+            nv = int(v.numel())
             vd, vd32 = self._chunk_index(c, dev)
-            cc = coords[:, at:at + v.numel()] if coords_are_local else coords[:, vd]
-            at += v.numel()
-            if self._writes_in_place:
-                self.compute(cc, ii[vd], jj[vd], out=peer.buffer, out_index=vd32)
+            cc = coords[:, at:at + nv] if coords_are_local else coords[:, vd]
+            at += nv
+            if peer.chunk_rows is not None:                        # chunk-major destination: contiguous rows
+                r0 = peer.chunk_rows[c]
+                rows = None
+            else:
+                r0, rows = None, vd32
+            if staged:
+                b = k & 1
+                cur.wait_event(self._stage_free[b])                # the previous shipment of this staging buffer has left
+                stage = self._stage[b]
+
+                def ship(first, last, b=b, stage=stage, r0=r0, v=v):
+                    done = torch.cuda.Event()
+                    done.record(cur)
+                    with torch.cuda.stream(self._copy_stream):
+                        self._copy_stream.wait_event(done)
+                        if r0 is not None:
+                            peer.buffer[r0 + first:r0 + last].copy_(stage[first:last], non_blocking=True)
+                        else:
+                            for a, n_run, src in self._runs(v[first:last]):
+                                peer.buffer[a:a + n_run].copy_(stage[first + src:first + src + n_run], non_blocking=True)
+
+                if self._has_pass_hook and k == len(plan.rank_chunks[self.rank]) - 1:     # ship pass by pass
+                    self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None, pass_edges=self.SHIP_EDGES, pass_hook=ship)
+                else:
+                    self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None)
+                    ship(0, nv)
+                with torch.cuda.stream(self._copy_stream):
+                    self._stage_free[b].record(self._copy_stream)
+            elif self._writes_in_place:
+                if rows is None:
+                    rows = torch.arange(r0, r0 + nv, dtype=torch.int32, device=dev)
+                self.compute(cc, ii[vd], jj[vd], out=peer.buffer, out_index=rows)
             else:                                                  # plain callable: copy its result over
                 res = self.compute(cc, ii[vd], jj[vd])[0].to(peer.buffer.dtype)
-                pos = v.tolist()
-                k = 0
-                while k < len(pos):                                # runs of consecutive positions -> one copy each
-                    e = k + 1
-                    while e < len(pos) and pos[e] == pos[e - 1] + 1:
-                        e += 1
-                    peer.buffer[pos[k]:pos[k] + (e - k)].copy_(res[k:e])
-                    k = e
+                if r0 is not None:
+                    peer.buffer[r0:r0 + nv].copy_(res)
+                else:
+                    for a, n_run, src in self._runs(v):
+                        peer.buffer[a:a + n_run].copy_(res[src:src + n_run])
+        if staged:
+            self._copy_stream.synchronize()
         if sync:
             if dev.type == "cuda":
                 torch.cuda.synchronize(dev)                        # this rank's peer stores have landed
             if self.world > 1:
                 dist.barrier(group=self.group)
         return peer.result()
+
+    @staticmethod
+    def _runs(v):
+        """Runs of consecutive edge positions: (first position, length, offset in the chunk)."""
+        pos = v.tolist()
+        k = 0
+        while k < len(pos):
+            e = k + 1
+            while e < len(pos) and pos[e] == pos[e - 1] + 1:
+                e += 1
+            yield pos[k], e - k, k
+            k = e
+
+    def _ensure_staging(self, peer, dev):
+        need = max((int(self.plan.chunk_edges[c].numel()) for c in self.plan.rank_chunks[self.rank]), default=0)
+        shape = (max(need, 1),) + tuple(peer.buffer.shape[1:])
+        st = getattr(self, "_stage", None)
+        if st is None or st[0].shape != shape or st[0].dtype != peer.buffer.dtype or st[0].device != dev:
+            self._stage = [torch.empty(shape, dtype=peer.buffer.dtype, device=dev) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            for e in self._stage_free:
+                e.record(torch.cuda.current_stream(dev))
 
     def __call__(self, coords, ii, jj, gather="all", dst=0):
         """gather=None: (local outputs, their edge positions).  gather="all": full [1,E,CH,H,W] in the original edge

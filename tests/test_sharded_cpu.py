@@ -115,9 +115,13 @@ def _worker(rank, world, port, gather, q):
         assert torch.equal(full, fmaps)
         eng = sh.ShardedBackendCorr(_oracle_compute(_levels(full)))
         plan = eng.set_edges(ii, jj)
-        if gather == "peer":
-            peer = sh.PeerOutput(ii.numel(), (18, 6, 8), torch.float32, "cpu", dst=0)
+        if gather in ("peer", "peer_chunk"):
+            peer = sh.PeerOutput(ii.numel(), (18, 6, 8), torch.float32, "cpu", dst=0,
+                                 plan=plan if gather == "peer_chunk" else None)
             out = eng.lookup_into_peer(coords, ii, jj, peer)
+            if out is not None and gather == "peer_chunk":          # chunk-major rows -> original edge order
+                assert sorted(peer.row_of_edge.tolist()) == list(range(ii.numel()))
+                out = out[:, peer.row_of_edge]
             out = out.clone() if out is not None else None
             peer.close()
         elif gather == "stream":
@@ -136,7 +140,7 @@ def _worker(rank, world, port, gather, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("gather", ["all", "dst", "stream", "peer", None])
+@pytest.mark.parametrize("gather", ["all", "dst", "stream", "peer", "peer_chunk", None])
 def test_world_size_2_gloo_equals_single_process(gather):
     fmaps, ii, jj, coords = _case()
     sh = _sharded()
@@ -163,7 +167,7 @@ def test_world_size_2_gloo_equals_single_process(gather):
     if gather == "all":
         for _, kind, out, _ in got:
             assert kind == "full" and torch.equal(out, full)
-    elif gather in ("dst", "stream", "peer"):
+    elif gather in ("dst", "stream", "peer", "peer_chunk"):
         assert got[0][1] == "full" and torch.equal(got[0][2], full) and got[1][1] == "none"
     else:
         seen = torch.zeros(ii.numel(), dtype=torch.bool)

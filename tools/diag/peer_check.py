@@ -22,16 +22,21 @@ full = sh.all_gather_frames(fm[rank * per:(rank + 1) * per].to(dev))
 assert torch.equal(full.cpu(), fm)
 with torch.no_grad():
     blk = corr.AltCorrBlock(ofs, ofr, GA, full.view(1, T, C, H, W), materialize=True)
-    def compute(c, i, j, out=None, out_index=None): return blk(c, i, j, out=out, out_index=out_index)
+    def compute(c, i, j, out=None, out_index=None, pass_edges=None, pass_hook=None):
+        return blk(c, i, j, out=out, out_index=out_index, pass_edges=pass_edges, pass_hook=pass_hook)
     eng = sh.ShardedBackendCorr(compute); plan = eng.set_edges(ii, jj)
-    for dtype in (torch.float32, torch.float16):
-        peer = sh.PeerOutput(E, (196, H, W), dtype, dev, dst=0)
-        res = eng.lookup_into_peer(coords, ii.to(dev), jj.to(dev), peer)
+    for dtype, via, chunked in ((torch.float32, "store", False), (torch.float16, "store", False), (torch.float16, "copy", True),
+                                (torch.float16, "copy", False)):
+        eng.SHIP_EDGES = 8
+        peer = sh.PeerOutput(E, (196, H, W), dtype, dev, dst=0, plan=plan if chunked else None)
+        res = eng.lookup_into_peer(coords, ii.to(dev), jj.to(dev), peer, via=via)
+        if rank == 0 and chunked:
+            res = res[:, peer.row_of_edge.to(dev)]
         if rank == 0:
             one = sh.ShardedBackendCorr(compute, single_process=True); one.set_edges(ii, jj)
             own = sh.PeerOutput(E, (196, H, W), dtype, dev, single_process=True)
             want = one.lookup_into_peer(coords, ii.to(dev), jj.to(dev), own)
-            print("peer", dtype, "counts", plan.counts(), "equal:", torch.equal(res, want), "nonzero frac", (res != 0).float().mean().item(), flush=True)
+            print("peer", dtype, via, chunked, "counts", plan.counts(), "equal:", torch.equal(res, want), "nonzero frac", (res != 0).float().mean().item(), flush=True)
             assert torch.equal(res, want)
             own.close()
         peer.close()
