@@ -106,6 +106,21 @@ LGU_API int lgu_lowmem_defsample_forward(const float* fmap1, const float* fmap2,
                                  int B, int N, int H1, int W1, int H2, int W2, int C, int radius,
                                  int strict_ref, void* stream);
 
+/* lowMem_defSample on TENSOR CORES, same operator contract: with `workspace` (device memory, 256-byte aligned, at least
+ * lgu_lowmem_workspace_bytes(...) bytes, contents undefined on entry and exit) the call splits the maps into fp16 hi/lo
+ * planes, builds this level's [B,P,Q] volume on tcgen05 (lgu_build_volume) and samples it with the TMA-staged lookup in
+ * per-corner-gating mode.  lgu_lowmem_workspace_bytes returns 0 for shapes the path does not cover (needs N == 1, C == 128,
+ * radius 3 -- 1 for altcorr --, H1*W1 % 128 == 0, W2 % 4 == 0); the *_ws entry points then (and with workspace == NULL) run
+ * the on-the-fly SIMT kernel.  Results equal the on-the-fly kernel up to fp32 summation order (<= 1e-5). */
+LGU_API long long lgu_lowmem_workspace_bytes(int B, int N, int H1, int W1, int H2, int W2, int C, int radius);
+LGU_API int lgu_lowmem_defsample_forward_ws(const float* fmap1, const float* fmap2, const float* coords,
+                                    float* offset, float* corr,
+                                    int B, int N, int H1, int W1, int H2, int W2, int C, int radius,
+                                    int strict_ref, void* workspace, long long workspace_bytes, void* stream);
+LGU_API int lgu_altcorr_forward_ws(const float* fmap1, const float* fmap2, const float* coords, float* corr,
+                           int B, int N, int H1, int W1, int H2, int W2, int C, int radius,
+                           void* workspace, long long workspace_bytes, void* stream);
+
 /* altcorr_forward             (src/droid.cpp:193-203, src/altcorr_kernel.cu:27-149,290-319)
  * The second boundary the backend path crosses (droid_slam/modules/corr.py:202).
  * corr [B,N,rd*rd,H1,W1], channel = iy + rd*ix. */

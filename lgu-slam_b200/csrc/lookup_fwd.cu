@@ -166,13 +166,23 @@ lookup_fwd_kernel(const float* __restrict__ volume, const float* __restrict__ co
 // idle.  One THREAD per pixel instead: its 4 x 4 footprint is loaded once (16 bounds-checked loads, zero outside),
 // the 9 taps are blended from registers, and consecutive threads store consecutive pixels of each tap plane
 // (coalesced).  Index logic as corrSample_kernel.cu:52-77 (top-left gating, Q3).
+// PC: altcorr_forward's semantics on a materialised volume (src/altcorr_kernel.cu:27-149: dot products at integer
+// positions, each gated on its own, bilinearly splatted = a per-corner-gated bilinear tap, quirk Q4), coords interleaved
+// [E,P,2] as that operator receives them.
+template <bool PC>
 __global__ void __launch_bounds__(128)
 lookup_fwd_r1_kernel(const float* __restrict__ volume, const float* __restrict__ coords, float* __restrict__ corr,
                      int P, int H2, int W2, long long npix) {
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
   const int n = (int)(pix / P), p = (int)(pix - (long long)n * P);
-  const float x0 = __ldg(coords + (size_t)n * 2 * P + p), y0 = __ldg(coords + (size_t)n * 2 * P + P + p);
+  float x0, y0;
+  if (PC) {
+    const float2 c = __ldg(reinterpret_cast<const float2*>(coords) + pix);
+    x0 = c.x; y0 = c.y;
+  } else {
+    x0 = __ldg(coords + (size_t)n * 2 * P + p); y0 = __ldg(coords + (size_t)n * 2 * P + P + p);
+  }
   const float dx = __fsub_rn(x0, floorf(x0)), dy = __fsub_rn(y0, floorf(y0));
   const int fx = floor_to_int(x0), fy = floor_to_int(y0);
   const float* V = volume + (size_t)pix * H2 * W2;
@@ -185,15 +195,21 @@ lookup_fwd_r1_kernel(const float* __restrict__ volume, const float* __restrict__
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b)
-      q[a][b] = in_bounds(ys[a], xs[b], H2, W2) ? __ldg(V + (size_t)ys[a] * W2 + xs[b]) : 0.0f;
+      q[a][b] = in_bounds(ys[a], xs[b], H2, W2) ? __ldg(V + (long long)ys[a] * W2 + xs[b]) : 0.0f;
   float* out = corr + (size_t)n * 9 * P + p;
 #pragma unroll
   for (int i = 0; i < 3; ++i)          // x tap
 #pragma unroll
     for (int j = 0; j < 3; ++j) {      // y tap
-      const bool gate = in_bounds(ys[j], xs[i], H2, W2);      // out-of-bounds x2 / y2 corners already read as 0
+      const bool gate = PC ? true : in_bounds(ys[j], xs[i], H2, W2);      // out-of-bounds corners already read as 0
       out[(size_t)(i * 3 + j) * P] = gate ? blend4(q[j][i], q[j][i + 1], q[j + 1][i], q[j + 1][i + 1], dx, dy) : 0.0f;
     }
+}
+
+int launch_r1_pc(const float* volume, const float* coords, float* corr, int B, int P, int H2, int W2, cudaStream_t st) {
+  const long long npix = (long long)B * P;
+  lookup_fwd_r1_kernel<true><<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(volume, coords, corr, P, H2, W2, npix);
+  return check_launch("lgu_altcorr_forward(volume)");
 }
 
 // Any radius (slow path, rarely used): same mapping, direct strided stores.
@@ -234,7 +250,7 @@ static int launch_lookup_fwd(const float* volume, const float* coords, float* of
     case 1:
       if (!DEFORM) {
         const long long npix = (long long)E * P;
-        lookup_fwd_r1_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(volume, coords, corr, P, H2, W2, npix);
+        lookup_fwd_r1_kernel<false><<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(volume, coords, corr, P, H2, W2, npix);
         break;
       }
       lookup_fwd_kernel<1, DEFORM><<<grid, block, 0, st>>>(volume, coords, offset, corr, P, W1, H2, W2, tiles);

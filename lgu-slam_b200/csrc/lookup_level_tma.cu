@@ -25,7 +25,8 @@ constexpr int kBwdSmem = kLvBoxes + kWarps * kBoxFloats * 4 + kWarps * kSlots * 
 
 struct LevelParams {
   const float* volume;
-  const float* coords;      // [E,2,P]
+  const float* coords;      // [E,2,P]  (PC: [E,P,2], x and y interleaved, as lowMem_defSample receives them)
+  long long off_edge_stride;   // PC: float2 elements between the offset slabs of consecutive edges (0: all edges read slab 0, Q2)
   float* offset;            // [E,P,49,2]  centre tap zeroed in place (Q5)
   float* corr;              // fwd: out [E,49,P]
   const float* corr_grad;   // bwd: [E,49,P]
@@ -38,7 +39,10 @@ struct LevelMap {
   CUtensorMap m;
 };
 
-template <bool BWD>
+// PC (forward only): lowMem_defSample's semantics on a materialised volume -- every bilinear corner gated on its own
+// (quirk Q4; the zero-filled box provides exactly that), fractions x - floor(x) (lowMem_defSample.cu:87-88), interleaved
+// coords, offset slab indexing with a stride (0 = the reference's offset[b*n] with N = 1, quirk Q2).
+template <bool BWD, bool PC = false>
 __global__ void __launch_bounds__(fl::kThreads, BWD ? 3 : 4)
 lookup_level_tma_kernel(const __grid_constant__ LevelMap map, const LevelParams prm) {
   using namespace lv;
@@ -66,8 +70,13 @@ lookup_level_tma_kernel(const __grid_constant__ LevelMap map, const LevelParams 
   float cxm = 0.0f, cym = 0.0f;                                 // lane k (< 4) holds pixel k's coords
   if (lane < kPixPerWarp) {
     const int p = min(pw + lane, P - 1);
-    cxm = __ldg(prm.coords + (size_t)n * 2 * P + p);
-    cym = __ldg(prm.coords + (size_t)n * 2 * P + P + p);
+    if (PC) {
+      const float2 c = __ldg(reinterpret_cast<const float2*>(prm.coords) + (size_t)n * P + p);
+      cxm = c.x; cym = c.y;
+    } else {
+      cxm = __ldg(prm.coords + (size_t)n * 2 * P + p);
+      cym = __ldg(prm.coords + (size_t)n * 2 * P + P + p);
+    }
   }
   auto issue = [&](int k, float cx, float cy) {                 // lane 0 only
     const int slot = k & 1;
@@ -118,8 +127,9 @@ lookup_level_tma_kernel(const __grid_constant__ LevelMap map, const LevelParams 
     }
   }
   float2 a0, a1;
+  const size_t oslab = PC ? (size_t)n * prm.off_edge_stride : (size_t)n * P * TAPS;
   auto load_offsets = [&](int k) {
-    const float2* O = reinterpret_cast<const float2*>(prm.offset) + ((size_t)n * P + min(pw + k, P - 1)) * TAPS;
+    const float2* O = reinterpret_cast<const float2*>(prm.offset) + oslab + (size_t)min(pw + k, P - 1) * TAPS;
     a0 = O[t0];
     a1 = O[t1c];
   };
@@ -146,18 +156,20 @@ lookup_level_tma_kernel(const __grid_constant__ LevelMap map, const LevelParams 
     {
       const float px = __fadd_rn(oa.x, x0), py = __fadd_rn(oa.y, y0);          // defCorrSample_kernel.cu:56-61
       const int fx = floor_to_int(px), fy = floor_to_int(py);
-      ta.dx = __fsub_rn(px, (float)fx); ta.dy = __fsub_rn(py, (float)fy);
-      tap_fetch<kBW01, kBH01>(ta, bx, xb, yb, fx, fy, i0, j0, R, H2, W2);
+      ta.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);
+      ta.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
+      tap_fetch<kBW01, kBH01, PC>(ta, bx, xb, yb, fx, fy, i0, j0, R, H2, W2);
     }
     {
       const float px = __fadd_rn(ob.x, x0), py = __fadd_rn(ob.y, y0);
       const int fx = floor_to_int(px), fy = floor_to_int(py);
-      tb.dx = __fsub_rn(px, (float)fx); tb.dy = __fsub_rn(py, (float)fy);
-      tap_fetch<kBW01, kBH01>(tb, bx, xb, yb, fx, fy, i1, j1, R, H2, W2);
+      tb.dx = PC ? __fsub_rn(px, floorf(px)) : __fsub_rn(px, (float)fx);
+      tb.dy = PC ? __fsub_rn(py, floorf(py)) : __fsub_rn(py, (float)fy);
+      tap_fetch<kBW01, kBH01, PC>(tb, bx, xb, yb, fx, fy, i1, j1, R, H2, W2);
     }
     if (__any_sync(0xffffffffu, ta.miss || tb.miss)) {          // |offset| >= 4 (or a far out-of-range pixel)
-      tap_patch_from_global(ta, V, H2, W2);
-      tap_patch_from_global(tb, V, H2, W2);
+      tap_patch_from_global<PC>(ta, V, H2, W2);
+      tap_patch_from_global<PC>(tb, V, H2, W2);
     }
     if (!BWD) {
       s_tile[t0 * kOutPitchL + pl] = tap_value(ta);
@@ -259,7 +271,7 @@ lookup_level_tma_kernel(const __grid_constant__ LevelMap map, const LevelParams 
     }
     // Q5: the centre offset tap is zeroed in the caller's tensor (after every load of this record)
     if (live && lane == CENTER)
-      reinterpret_cast<float2*>(prm.offset)[pix * TAPS + CENTER] = make_float2(0.0f, 0.0f);
+      reinterpret_cast<float2*>(prm.offset)[oslab + (size_t)min(p, P - 1) * TAPS + CENTER] = make_float2(0.0f, 0.0f);
     __syncwarp();
     if (k + 2 < kPixPerWarp) {
       const float nx = __shfl_sync(0xffffffffu, cxm, k + 2), ny = __shfl_sync(0xffffffffu, cym, k + 2);
@@ -287,7 +299,7 @@ int launch_level_tma(bool bwd, const float* volume, const float* coords, float* 
   if (rc) return rc;
   LevelParams prm;
   prm.volume = volume; prm.coords = coords; prm.offset = offset; prm.corr = corr; prm.corr_grad = corr_grad;
-  prm.volume_grad = volume_grad; prm.offset_grad = offset_grad;
+  prm.volume_grad = volume_grad; prm.offset_grad = offset_grad; prm.off_edge_stride = 0;
   prm.P = (int)P; prm.H2 = H2; prm.W2 = W2;
   prm.tiles_per_edge = (int)((P + fl::kTile - 1) / fl::kTile);
   const long long nblk = (long long)E * prm.tiles_per_edge;
@@ -300,6 +312,27 @@ int launch_level_tma(bool bwd, const float* volume, const float* coords, float* 
   if (int rc = optin_smem(reinterpret_cast<const void*>(lookup_level_tma_kernel<false>), lv::kFwdSmem, "lgu_defcorr_index_forward")) return rc;
   lookup_level_tma_kernel<false><<<(unsigned)nblk, fl::kThreads, lv::kFwdSmem, st>>>(map, prm);
   return check_launch("lgu_defcorr_index_forward(tma)");
+}
+
+// lowMem_defSample's sampling step on a materialised volume [B, P, H2*W2] (radius 3): see lowmem.cu
+int launch_level_tma_pc(const float* volume, const float* coords, float* offset, float* corr, int B, int H1, int W1, int H2,
+                        int W2, long long off_edge_stride, cudaStream_t st) {
+  const long long P = (long long)H1 * W1;
+  LGU_REQUIRE((W2 & 3) == 0 && (reinterpret_cast<uintptr_t>(volume) & 15) == 0 && B * P < 2147483647LL,
+              "lowMem sampler: volume must be 16-byte aligned with W2 %% 4 == 0");
+  LevelMap map;
+  int rc = make_slice_map(&map.m, volume, B * P, H2, W2, fl::kBW01, fl::kBH01);
+  if (rc) return rc;
+  LevelParams prm;
+  prm.volume = volume; prm.coords = coords; prm.offset = offset; prm.corr = corr; prm.corr_grad = nullptr;
+  prm.volume_grad = nullptr; prm.offset_grad = nullptr; prm.off_edge_stride = off_edge_stride;
+  prm.P = (int)P; prm.H2 = H2; prm.W2 = W2;
+  prm.tiles_per_edge = (int)((P + fl::kTile - 1) / fl::kTile);
+  const long long nblk = (long long)B * prm.tiles_per_edge;
+  LGU_REQUIRE(nblk < 2147483647LL, "lowMem sampler: grid too large");
+  if (int rc2 = optin_smem(reinterpret_cast<const void*>(lookup_level_tma_kernel<false, true>), lv::kFwdSmem, "lgu_lowmem_defsample_forward")) return rc2;
+  lookup_level_tma_kernel<false, true><<<(unsigned)nblk, fl::kThreads, lv::kFwdSmem, st>>>(map, prm);
+  return check_launch("lgu_lowmem_defsample_forward(volume)");
 }
 
 }  // namespace lgu

@@ -13,9 +13,77 @@
 // tile leaves through the same shared-memory transpose as lookup_fwd.cu (128-byte rows).
 // Index logic: every corner gated separately (quirk Q4), [ix][iy] output order (Q1),
 // offset slab b*n in strict_ref mode (Q2), centre offset tap zeroed in place (Q5).
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace lgu {
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core path behind the SAME operator names (round 2).  The reference samples on the fly because 12-24 GB GPUs
+// cannot hold a chunk's all-pairs volumes; per call that costs 1.2 GB/edge of L2 gathers (4 x 128 scalar channel loads
+// per tap per pixel).  With a caller-supplied workspace the operator instead
+//   1. splits the fp32 channels-last maps into fp16 hi / lo planes (exact for the backend's fp16 frame buffer; for
+//      general fp32 maps the 3-MMA split keeps |error| <= ~2^-21 relative per product),
+//   2. builds the [B, P, Q] volume of THIS level on tcgen05 (lgu_build_volume, fp32 accumulation in TMEM),
+//   3. samples it with the TMA-staged single-level lookup in per-corner-gating mode (quirk Q4, lookup_level_tma.cu;
+//      r = 1 for altcorr_forward).
+// "Dot-then-interpolate" is algebraically the reference's "interpolate-then-dot" (both gate every corner on its own);
+// the results differ by fp32 summation order only (<= 1e-5, tests/test_ref_gpu.py).  Shapes the path does not cover
+// (C != 128, N != 1, H1*W1 % 128 != 0, W2 % 4 != 0, other radii) run the SIMT kernel below.
+int launch_level_tma_pc(const float* volume, const float* coords, float* offset, float* corr, int B, int H1, int W1, int H2,
+                        int W2, long long off_edge_stride, cudaStream_t st);                       // lookup_level_tma.cu
+int launch_r1_pc(const float* volume, const float* coords, float* corr, int B, int P, int H2, int W2, cudaStream_t st);
+
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, long long n4,
+                    int32_t* __restrict__ idx, int nidx) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nidx) idx[t] = (int32_t)t;
+  for (long long q = t; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + q);
+    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+    const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+    const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+    reinterpret_cast<__half2*>(hi)[2 * q] = __halves2half2(h0, h1);
+    reinterpret_cast<__half2*>(hi)[2 * q + 1] = __halves2half2(h2, h3);
+    reinterpret_cast<__half2*>(lo)[2 * q] = __halves2half2(l0, l1);
+    reinterpret_cast<__half2*>(lo)[2 * q + 1] = __halves2half2(l2, l3);
+  }
+}
+
+struct LowMemWs {
+  size_t f1_hi, f1_lo, f2_hi, f2_lo, idx, volume, total;
+};
+static inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+// 0 total: the tensor-core path does not apply to this shape
+static LowMemWs lowmem_ws_layout(int B, int N, int H1, int W1, int H2, int W2, int C, int radius) {
+  LowMemWs w = {0, 0, 0, 0, 0, 0, 0};
+  const long long P = (long long)H1 * W1, Q = (long long)H2 * W2;
+  if (N != 1 || C != 128 || (radius != 3 && radius != 1) || (P % 128) != 0 || (W2 % 4) != 0 || B <= 0 ||
+      (long long)B * P >= 2147483647LL)
+    return w;
+  size_t at = 0;
+  w.f1_hi = at; at = up256(at + (size_t)B * P * C * 2);
+  w.f1_lo = at; at = up256(at + (size_t)B * P * C * 2);
+  w.f2_hi = at; at = up256(at + (size_t)B * Q * C * 2);
+  w.f2_lo = at; at = up256(at + (size_t)B * Q * C * 2);
+  w.idx = at;   at = up256(at + (size_t)B * 4);
+  w.volume = at; at = up256(at + (size_t)B * P * Q * 4);
+  w.total = at;
+  return w;
+}
+
+static int lowmem_volume(const float* fmap1, const float* fmap2, int B, int P, int Q, int C, const LowMemWs& w, char* ws,
+                         cudaStream_t st) {
+  auto hi1 = reinterpret_cast<__half*>(ws + w.f1_hi), lo1 = reinterpret_cast<__half*>(ws + w.f1_lo);
+  auto hi2 = reinterpret_cast<__half*>(ws + w.f2_hi), lo2 = reinterpret_cast<__half*>(ws + w.f2_lo);
+  auto idx = reinterpret_cast<int32_t*>(ws + w.idx);
+  const long long n1 = (long long)B * P * C / 4, n2 = (long long)B * Q * C / 4;
+  split_planes_kernel<<<(unsigned)((n1 + 255) / 256 < 4096 ? (n1 + 255) / 256 : 4096), 256, 0, st>>>(fmap1, hi1, lo1, n1, idx, B);
+  split_planes_kernel<<<(unsigned)((n2 + 255) / 256 < 4096 ? (n2 + 255) / 256 : 4096), 256, 0, st>>>(fmap2, hi2, lo2, n2, idx, 0);
+  if (int rc = check_launch("lowMem: operand split")) return rc;
+  return lgu_build_volume(hi1, lo1, hi2, lo2, idx, idx, reinterpret_cast<float*>(ws + w.volume), B, B, B, P, Q, C, 2, st);
+}
 
 constexpr int kLmWarps = 8;
 constexpr int kLmThreads = kLmWarps * 32;
@@ -196,6 +264,51 @@ static int launch_lowmem(const LowMemArgs& a0, cudaStream_t st, const char* name
 }
 
 }  // namespace lgu
+
+extern "C" long long lgu_lowmem_workspace_bytes(int B, int N, int H1, int W1, int H2, int W2, int C, int radius) {
+  return (long long)lgu::lowmem_ws_layout(B, N, H1, W1, H2, W2, C, radius).total;
+}
+
+extern "C" int lgu_lowmem_defsample_forward_ws(const float* fmap1, const float* fmap2, const float* coords, float* offset,
+                                               float* corr, int B, int N, int H1, int W1, int H2, int W2, int C, int radius,
+                                               int strict_ref, void* workspace, long long workspace_bytes, void* stream) {
+  if (B == 0) return LGU_OK;
+  const lgu::LowMemWs w = lgu::lowmem_ws_layout(B, N, H1, W1, H2, W2, C, radius);
+  if (w.total == 0 || radius != 3 || workspace == nullptr)       // shape outside the tensor-core path: the SIMT kernel
+    return lgu_lowmem_defsample_forward(fmap1, fmap2, coords, offset, corr, B, N, H1, W1, H2, W2, C, radius, strict_ref, stream);
+  LGU_REQUIRE(fmap1 && fmap2 && coords && offset && corr, "lgu_lowmem_defsample_forward_ws: null pointer");
+  LGU_REQUIRE((size_t)workspace_bytes >= w.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "lgu_lowmem_defsample_forward_ws: workspace of %lld B (256-byte aligned) needed, got %lld", (long long)w.total,
+              workspace_bytes);
+  LGU_REQUIRE(((reinterpret_cast<uintptr_t>(fmap1) | reinterpret_cast<uintptr_t>(fmap2)) & 15) == 0,
+              "lgu_lowmem_defsample_forward_ws: feature maps must be 16-byte aligned");
+  const int P = H1 * W1, Q = H2 * W2;
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (int rc = lgu::lowmem_volume(fmap1, fmap2, B, P, Q, C, w, ws, (cudaStream_t)stream)) return rc;
+  // offset slabs: the reference reads offset[b*n] with n == 0 (quirk Q2: every edge uses slab 0); fixed mode: offset[b]
+  const long long stride = strict_ref ? 0 : (long long)P * 49;
+  return lgu::launch_level_tma_pc(reinterpret_cast<const float*>(ws + w.volume), coords, offset, corr, B, H1, W1, H2, W2,
+                                  stride, (cudaStream_t)stream);
+}
+
+extern "C" int lgu_altcorr_forward_ws(const float* fmap1, const float* fmap2, const float* coords, float* corr, int B, int N,
+                                      int H1, int W1, int H2, int W2, int C, int radius, void* workspace,
+                                      long long workspace_bytes, void* stream) {
+  if (B == 0) return LGU_OK;
+  const lgu::LowMemWs w = lgu::lowmem_ws_layout(B, N, H1, W1, H2, W2, C, radius);
+  if (w.total == 0 || radius != 1 || workspace == nullptr)
+    return lgu_altcorr_forward(fmap1, fmap2, coords, corr, B, N, H1, W1, H2, W2, C, radius, stream);
+  LGU_REQUIRE(fmap1 && fmap2 && coords && corr, "lgu_altcorr_forward_ws: null pointer");
+  LGU_REQUIRE((size_t)workspace_bytes >= w.total && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "lgu_altcorr_forward_ws: workspace of %lld B (256-byte aligned) needed, got %lld", (long long)w.total,
+              workspace_bytes);
+  LGU_REQUIRE(((reinterpret_cast<uintptr_t>(fmap1) | reinterpret_cast<uintptr_t>(fmap2)) & 15) == 0,
+              "lgu_altcorr_forward_ws: feature maps must be 16-byte aligned");
+  const int P = H1 * W1, Q = H2 * W2;
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (int rc = lgu::lowmem_volume(fmap1, fmap2, B, P, Q, C, w, ws, (cudaStream_t)stream)) return rc;
+  return lgu::launch_r1_pc(reinterpret_cast<const float*>(ws + w.volume), coords, corr, B, P, H2, W2, (cudaStream_t)stream);
+}
 
 extern "C" int lgu_lowmem_defsample_forward(const float* fmap1, const float* fmap2, const float* coords,
                                             float* offset, float* corr, int B, int N, int H1, int W1, int H2, int W2,

@@ -137,10 +137,47 @@ def gaussianMask_backward(means, covs, volume, volume1_grad, radius):
     return [gm, gc]
 
 
-def lowMem_defSample(fmap1, fmap2, coords, offset, radius, strict_ref=True):
+# Workspace of the tensor-core lowMem / altcorr path: one grow-only byte buffer per device, reused by every call (the
+# C ABI allocates nothing).  A call whose volume would not fit LOWMEM_WORKSPACE_CAP is processed in sub-batches of edges.
+LOWMEM_WORKSPACE_CAP = 32 << 30
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    buf = _workspaces.get(device)
+    if buf is None or buf.numel() < nbytes:
+        _workspaces[device] = None                      # release the old buffer before growing
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[device] = buf
+    return buf
+
+
+def release_workspace():
+    """Drop the cached tensor-core workspaces (they are re-created on demand)."""
+    _workspaces.clear()
+
+
+def _ws_bytes(B, N, H1, W1, H2, W2, C, radius):
+    L = _lib.lib()
+    L.lgu_lowmem_workspace_bytes.restype = ctypes.c_longlong
+    return int(L.lgu_lowmem_workspace_bytes(_i(B), _i(N), _i(H1), _i(W1), _i(H2), _i(W2), _i(C), _i(radius)))
+
+
+def _sub_batches(B, per_call_bytes_fn):
+    """Split B edges into runs whose workspace fits LOWMEM_WORKSPACE_CAP (usually one run)."""
+    step = B
+    while step > 1 and per_call_bytes_fn(step) > LOWMEM_WORKSPACE_CAP:
+        step = (step + 1) // 2
+    return [(s0, min(B, s0 + step)) for s0 in range(0, B, step)]
+
+
+def lowMem_defSample(fmap1, fmap2, coords, offset, radius, strict_ref=True, tensor_cores=True):
     """droid.cpp:124-136.  fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C], coords [B,N,H1,W1,2],
     offset [slabs,H1,W1,rd,rd,2] (mutated) -> [corr [B,N,rd,rd,H1,W1]].
-    strict_ref=True keeps the reference's offset[b*n] slab indexing (quirk Q2)."""
+    strict_ref=True keeps the reference's offset[b*n] slab indexing (quirk Q2).
+    tensor_cores (default): for the reference's call shape (N = 1, C = 128, r = 3, H1*W1 % 128 == 0, W2 % 4 == 0) this
+    level's [B,P,Q] volume is built on tcgen05 into a cached workspace and sampled with the TMA-staged lookup
+    (lgu_lowmem_defsample_forward_ws); other shapes, or tensor_cores=False, run the on-the-fly SIMT kernel."""
     _chk(fmap1, "fmap1", 4); _chk(fmap2, "fmap2", 4); _chk(coords, "coords", 5); _chk(offset, "offset", 6)
     B, H1, W1, C = fmap1.shape
     B2, H2, W2, C2 = fmap2.shape
@@ -152,6 +189,19 @@ def lowMem_defSample(fmap1, fmap2, coords, offset, radius, strict_ref=True):
     if tuple(offset.shape[1:]) != (H1, W1, rd, rd, 2) or offset.shape[0] < need:
         raise RuntimeError(f"offset shape {tuple(offset.shape)} incompatible with {(need, H1, W1, rd, rd, 2)}")
     corr = torch.empty(B, N, rd, rd, H1, W1, dtype=fmap1.dtype, device=fmap1.device)
+    if tensor_cores and B > 0 and _ws_bytes(B, N, H1, W1, H2, W2, C, radius) > 0:
+        runs = _sub_batches(B, lambda b: _ws_bytes(b, N, H1, W1, H2, W2, C, radius))
+        with torch.cuda.device(fmap1.device):
+            for b0, b1 in runs:
+                nb = _ws_bytes(b1 - b0, N, H1, W1, H2, W2, C, radius)
+                ws = _workspace(fmap1.device, nb)
+                off = offset if strict_ref else offset[b0:]          # strict: every run reads slab 0 of the call (Q2)
+                st = _lib.lib().lgu_lowmem_defsample_forward_ws(
+                    _p(fmap1[b0:b1]), _p(fmap2[b0:b1]), _p(coords[b0:b1]), _p(off), _p(corr[b0:b1]), _i(b1 - b0), _i(N),
+                    _i(H1), _i(W1), _i(H2), _i(W2), _i(C), _i(radius), _i(1 if strict_ref else 0), _p(ws),
+                    ctypes.c_longlong(ws.numel()), _stream(fmap1))
+                _lib.check(st, "lowMem_defSample (tensor cores)")
+        return [corr]
     with torch.cuda.device(fmap1.device):
         st = _lib.lib().lgu_lowmem_defsample_forward(_p(fmap1), _p(fmap2), _p(coords), _p(offset), _p(corr), _i(B),
                                                      _i(N), _i(H1), _i(W1), _i(H2), _i(W2), _i(C), _i(radius),
@@ -160,8 +210,10 @@ def lowMem_defSample(fmap1, fmap2, coords, offset, radius, strict_ref=True):
     return [corr]
 
 
-def altcorr_forward(fmap1, fmap2, coords, radius):
-    """droid_backends.altcorr_forward (src/droid.cpp:193-203) -> [corr [B,N,rd*rd,H1,W1]]."""
+def altcorr_forward(fmap1, fmap2, coords, radius, tensor_cores=True):
+    """droid_backends.altcorr_forward (src/droid.cpp:193-203) -> [corr [B,N,rd*rd,H1,W1]].
+    tensor_cores (default): for N = 1, C = 128, r = 1 (the reference's only call, corr.py:202) the volume is built on
+    tcgen05 and sampled with per-corner gating (lgu_altcorr_forward_ws); otherwise the on-the-fly SIMT kernel."""
     _chk(fmap1, "fmap1", 4); _chk(fmap2, "fmap2", 4); _chk(coords, "coords", 5)
     B, H1, W1, C = fmap1.shape
     B2, H2, W2, C2 = fmap2.shape
@@ -170,6 +222,16 @@ def altcorr_forward(fmap1, fmap2, coords, radius):
     if B2 != B or C2 != C or Bc != B or (Hc, Wc, two) != (H1, W1, 2):
         raise RuntimeError("altcorr_forward: inconsistent fmap/coords shapes")
     corr = torch.empty(B, N, rd * rd, H1, W1, dtype=fmap1.dtype, device=fmap1.device)
+    if tensor_cores and B > 0 and _ws_bytes(B, N, H1, W1, H2, W2, C, radius) > 0:
+        runs = _sub_batches(B, lambda b: _ws_bytes(b, N, H1, W1, H2, W2, C, radius))
+        with torch.cuda.device(fmap1.device):
+            for b0, b1 in runs:
+                ws = _workspace(fmap1.device, _ws_bytes(b1 - b0, N, H1, W1, H2, W2, C, radius))
+                st = _lib.lib().lgu_altcorr_forward_ws(
+                    _p(fmap1[b0:b1]), _p(fmap2[b0:b1]), _p(coords[b0:b1]), _p(corr[b0:b1]), _i(b1 - b0), _i(N), _i(H1),
+                    _i(W1), _i(H2), _i(W2), _i(C), _i(radius), _p(ws), ctypes.c_longlong(ws.numel()), _stream(fmap1))
+                _lib.check(st, "altcorr_forward (tensor cores)")
+        return [corr]
     with torch.cuda.device(fmap1.device):
         st = _lib.lib().lgu_altcorr_forward(_p(fmap1), _p(fmap2), _p(coords), _p(corr), _i(B), _i(N), _i(H1), _i(W1),
                                             _i(H2), _i(W2), _i(C), _i(radius), _stream(fmap1))

@@ -177,3 +177,23 @@ def test_full_size_properties(ops):
     rhs = (vol.double() * gv.double()).sum().item()
     assert abs(lhs - rhs) <= 1e-6 * (out.double().abs() * grad.double().abs()).sum().item()
     assert (gv != 0).sum().item() <= E * H * W * 49 * 4
+
+
+@pytest.mark.parametrize("H2,W2,strict", [(48, 64, True), (24, 32, False), (6, 8, True)])
+def test_lowmem_tensor_core_path_equals_on_the_fly_kernel(ops, H2, W2, strict):
+    """lowMem_defSample behind the reference's operator name runs on tensor cores for the reference's call shape (volume
+    on tcgen05 into a workspace + TMA-staged per-corner-gated lookup); it must agree with the on-the-fly SIMT kernel
+    (itself <= 1e-5 from the compiled reference) within fp32 summation order, produce the same zero pattern, and leave
+    the same in-place side effect on the offset slabs (quirks Q2, Q5).  General fp32 maps (not fp16-representable)."""
+    c = inputs.lowmem_case(5, 1, 48, 64, H2, W2, 128, 3, seed=77, probes=True, half_exact=False)
+    f1, f2, co = cu(c["fmap1"]), cu(c["fmap2"]), cu(c["coords"])
+    o_a, o_b = cu(c["offset"]), cu(c["offset"])
+    a, = ops.lowMem_defSample(f1, f2, co, o_a, 3, strict_ref=strict)
+    b, = ops.lowMem_defSample(f1, f2, co, o_b, 3, strict_ref=strict, tensor_cores=False)
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    assert (torch.nan_to_num(a) - torch.nan_to_num(b)).abs().max().item() <= 1e-5
+    assert torch.equal(o_a, o_b)
+    m_a, = ops.altcorr_forward(f1, f2, co, 1)
+    m_b, = ops.altcorr_forward(f1, f2, co, 1, tensor_cores=False)
+    assert torch.equal(torch.isnan(m_a), torch.isnan(m_b))
+    assert (torch.nan_to_num(m_a) - torch.nan_to_num(m_b)).abs().max().item() <= 1e-5
