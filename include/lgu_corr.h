@@ -143,7 +143,8 @@ LGU_API int lgu_altcorr_forward(const float* fmap1, const float* fmap2, const fl
  *         |error| <= ~2^-21 relative per product (fp32-valued inputs, the training path).
  * fmaps_lo  residual plane (x - fp16(x)) for precision 2, else NULL.
  * ii, jj  [E] int32 frame index of the source / target map of each edge.
- * means,covs [E,H,W,2], den [E,H,W] (= 6.28*sqrt(cov_x*cov_y), formed by the caller), or NULL.
+ * means,covs [E,H,W,2] or NULL; den [E,H,W] (= 6.28*sqrt(cov_x*cov_y), gaussianMask_cuda.py:77,85) or NULL: the kernel
+ * then forms it from covs in its prologue with the same fp32 roundings.
  * lvl0..lvl3 [E,H,W,H>>l,W>>l] outputs (lvl1..3 may be NULL to skip pooling). */
 LGU_API int lgu_build_pyramid(const void* fmaps_hi, const void* fmaps_lo, const int32_t* ii, const int32_t* jj,
                       const float* means, const float* covs, const float* den,
@@ -303,6 +304,19 @@ LGU_API int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, const
  * hi [T,P,C] (and lo [T,P,C] = fp16(x/4 - hi) when lo != NULL), pre-scaled by 1/4 (corr.py:148-149). */
 LGU_API int lgu_pack_fmaps(const void* fmaps, int src_is_half, void* hi, void* lo,
                    int T, int C, int P, void* stream);
+
+/* --------------------------------------------------------------------------
+ * Offset heads' glue  (droid_slam/modules/corr.py:117-135 / 217-235, per_Corr_Normalization :44-51) in two launches
+ * instead of ~14 torch kernels:
+ *   off0[e,y,x,c] = 4 tanh( (c0[e,c,y,x] - mean0_e) / sqrt(var0_e + eps) )
+ *   off1[e,y,x,c] = ( 4 tanh( (c1[e,c,y/2,x/2] - mean1_e) / sqrt(var1_e + eps) ) + off0[e,y,x,c] ) / 2
+ * c0 [E,CH,H,W] = ofsMap(t), c1 [E,CH,H/2,W/2] = ofs_residual(avg_pool2d(t, 2)) (the conv outputs; the nearest-neighbour
+ * upsampling of c1 is done by indexing, its statistics equal the low-resolution ones), mean/var per edge over
+ * (CH,H,W), biased variance, eps = 1e-5.  off0, off1 [E,H,W,CH]: the channels-last layout the lookups read.
+ * stats [E,4] fp32 receives (mean0, rstd0, mean1, rstd1).  Forward only (inference paths); CH <= 128, W % 32 == 0, H even.
+ * ------------------------------------------------------------------------ */
+LGU_API int lgu_offset_heads(const float* c0, const float* c1, float* off0, float* off1, float* stats,
+                     int E, int CH, int H, int W, float eps, void* stream);
 
 /* --------------------------------------------------------------------------
  * Peer-visible device memory for the edge-sharded backend (no reference counterpart: the reference is single-GPU).

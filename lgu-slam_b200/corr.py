@@ -291,7 +291,15 @@ def _generate_offsets(ofsMap, ofs_residual, t):
     """t [E,256,h,w] -> 4 per-level offset tensors [E,h,w,98]; levels 2 and 3 are zeros."""
     _, _, h, w = t.shape
     o0 = ofsMap(t)
-    o1 = F.interpolate(ofs_residual(F.avg_pool2d(t, kernel_size=2, stride=2)), (h, w))
+    r1 = ofs_residual(F.avg_pool2d(t, kernel_size=2, stride=2))
+    if (not torch.is_grad_enabled() or not (o0.requires_grad or r1.requires_grad)) and o0.is_cuda and w % 32 == 0 \
+            and h % 2 == 0 and o0.shape[1] <= 128 and o0.dtype == torch.float32:
+        # inference: normalise -> 4 tanh -> level-1 average -> upsample -> NHWC in two launches (lgu_offset_heads) instead of
+        # ~14 torch kernels; the records come out contiguous [E,h,w,98] (the reference holds permuted views here, so its
+        # stored centre taps survive the first per-operator call; they are read as 0 either way, quirk Q5)
+        off0, off1 = ops.offset_heads(o0.detach().contiguous(), r1.detach().contiguous())
+        return [off0, off1, torch.zeros_like(off0), torch.zeros_like(off0)]
+    o1 = F.interpolate(r1, (h, w))
     o0 = torch.tanh(per_Corr_Normalization(o0, [1, 2, 3])) * 4
     o1 = (torch.tanh(per_Corr_Normalization(o1, [1, 2, 3])) * 4 + o0) / 2
     # [E,h,w,98] as PERMUTED VIEWS, like the reference (corr.py:129-134): `.contiguous()` at the samplers then copies,
@@ -555,9 +563,9 @@ class PooledCorrBlock:
             frames = torch.cat((f1, f2), dim=0).contiguous()
             hi, lo = ops.pack_fmaps(frames, split=frames.dtype == torch.float32)
             ar = torch.arange(2 * E, dtype=torch.int32, device=frames.device)
-            den = (6.28 * torch.sqrt(det)).view(E, h, w).float().contiguous()
+            # den = 6.28 * sqrt(det) is formed in the build kernel's prologue (same fp32 roundings)
             ops.build_pyramid(hi, lo, ar[:E].contiguous(), ar[E:].contiguous(), h, w, means=mean.float().contiguous(),
-                              covs=cov.contiguous(), den=den, num_levels=num_levels, gauss_radius=GAUSS_RADIUS,
+                              covs=cov.contiguous(), den=None, num_levels=num_levels, gauss_radius=GAUSS_RADIUS,
                               round_half=autocast_rounding, out=pool.levels, out_slots=sl)
         self.mean_n = mean.view(E, h, w, 2)
         self.theta = 2 * det.view(E, h, w)

@@ -345,7 +345,8 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
         const float2 m = __ldg(reinterpret_cast<const float2*>(prm.means) + ipix);
         const float2 c = __ldg(reinterpret_cast<const float2*>(prm.covs) + ipix);
         mx = m.x; my = m.y; c1 = c.x; c2 = c.y;
-        den = __ldg(prm.den + ipix);
+        // den == NULL: the 6.28 * sqrt(cov_x * cov_y) of gaussianMask_cuda.py:77,85 is formed here (same fp32 roundings)
+        den = prm.den != nullptr ? __ldg(prm.den + ipix) : __fmul_rn(6.28f, __fsqrt_rn(__fmul_rn(c1, c2)));
         bx = (unsigned)floor_to_int(mx) - (unsigned)gr;
         by = (unsigned)floor_to_int(my) - (unsigned)gr;
       }
@@ -644,7 +645,7 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   LGU_REQUIRE(precision == 1 || precision == 2, "lgu_build_pyramid: precision must be 1 or 2");
   LGU_REQUIRE(precision == 1 || fmaps_lo != nullptr, "lgu_build_pyramid: precision 2 needs the lo plane");
   LGU_REQUIRE(T > 0 && E > 0 && gauss_radius >= 0 && gauss_radius <= 15, "lgu_build_pyramid: bad sizes");
-  LGU_REQUIRE(gauss_radius == 0 || (means && covs && den), "lgu_build_pyramid: Gaussian parameters missing");
+  LGU_REQUIRE(gauss_radius == 0 || (means && covs), "lgu_build_pyramid: Gaussian parameters missing");
   if (!(W == 64 && H > 0 && (H % 8) == 0 && C == 128)) {
     set_error("lgu_build_pyramid: only W=64, H%%8==0, C=128 grids are implemented (got H=%d W=%d C=%d)", H, W, C);
     return LGU_ERR_UNSUPPORTED;

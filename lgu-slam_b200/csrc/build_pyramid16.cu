@@ -204,7 +204,8 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         const float2 m = __ldg(reinterpret_cast<const float2*>(prm.means) + ipix);
         const float2 c = __ldg(reinterpret_cast<const float2*>(prm.covs) + ipix);
         mx = m.x; my = m.y; c1 = c.x; c2 = c.y;
-        den = __ldg(prm.den + ipix);
+        // den == NULL: the 6.28 * sqrt(cov_x * cov_y) of gaussianMask_cuda.py:77,85 is formed here (same fp32 roundings)
+        den = prm.den != nullptr ? __ldg(prm.den + ipix) : __fmul_rn(6.28f, __fsqrt_rn(__fmul_rn(c1, c2)));
         bx = (unsigned)floor_to_int(mx) - (unsigned)gr;
         by = (unsigned)floor_to_int(my) - (unsigned)gr;
       }

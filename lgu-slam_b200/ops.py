@@ -242,6 +242,25 @@ def altcorr_forward(fmap1, fmap2, coords, radius, tensor_cores=True):
 # ----------------------------------------------------------------------------------------------
 # Fused ops (no single reference operator; they replace sequences of the reference's Python glue)
 # ----------------------------------------------------------------------------------------------
+def offset_heads(c0, c1, eps=1e-5):
+    """The offset heads' glue (corr.py:117-135 / 217-235) in two launches: c0 [E,CH,H,W] = ofsMap(t), c1 [E,CH,H/2,W/2] =
+    ofs_residual(avg_pool2d(t, 2)) -> (off0, off1) [E,H,W,CH], channels-last and contiguous:
+    off0 = 4 tanh(norm(c0)), off1 = (4 tanh(norm(upsample(c1))) + off0) / 2, norm = per-edge standardisation over
+    (CH,H,W) with biased variance + eps (per_Corr_Normalization, corr.py:44-51).  Forward only."""
+    _chk(c0, "c0", 4); _chk(c1, "c1", 4)
+    E, CH, H, W = c0.shape
+    if tuple(c1.shape) != (E, CH, H // 2, W // 2):
+        raise RuntimeError(f"c1 shape {tuple(c1.shape)} != {(E, CH, H // 2, W // 2)}")
+    off0 = torch.empty(E, H, W, CH, dtype=torch.float32, device=c0.device)
+    off1 = torch.empty_like(off0)
+    stats = torch.empty(E, 4, dtype=torch.float32, device=c0.device)
+    with torch.cuda.device(c0.device):
+        st = _lib.lib().lgu_offset_heads(_p(c0), _p(c1), _p(off0), _p(off1), _p(stats), _i(E), _i(CH), _i(H), _i(W),
+                                         ctypes.c_float(eps), _stream(c0))
+    _lib.check(st, "offset_heads")
+    return off0, off1
+
+
 def pack_fmaps(fmaps, split=False):
     """fmaps [T,C,H,W] (fp32 or fp16 CUDA, as the encoders emit) -> channels-last fp16 planes for the
     tcgen05 build: hi [T,H*W,C] = fp16(x/4) and, if split, lo = fp16(x/4 - hi) (else None).
@@ -286,9 +305,13 @@ def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_lev
         raise RuntimeError("ii and jj must have the same length")
     use_gauss = gauss_radius > 0 and means is not None
     if use_gauss:
-        _chk(means, "means", 4); _chk(covs, "covs", 4); _chk(den, "den", 3)
-        if tuple(means.shape) != (E, H, W, 2) or tuple(covs.shape) != (E, H, W, 2) or tuple(den.shape) != (E, H, W):
-            raise RuntimeError("means/covs must be [E,H,W,2] and den [E,H,W]")
+        _chk(means, "means", 4); _chk(covs, "covs", 4)
+        if tuple(means.shape) != (E, H, W, 2) or tuple(covs.shape) != (E, H, W, 2):
+            raise RuntimeError("means/covs must be [E,H,W,2]")
+        if den is not None:                      # None: the kernel forms 6.28*sqrt(cov_x*cov_y) in its prologue
+            _chk(den, "den", 3)
+            if tuple(den.shape) != (E, H, W):
+                raise RuntimeError("den must be [E,H,W]")
     if not 1 <= num_levels <= 4:
         raise RuntimeError("num_levels must be in 1..4")
     null = ctypes.c_void_p(0)
@@ -306,8 +329,8 @@ def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_lev
         with torch.cuda.device(hi.device):
             st = _lib.lib().lgu_build_pyramid_slots(
                 _p(hi), _p(lo) if precision == 2 else null, _p(ii), _p(jj), _p(means) if use_gauss else null,
-                _p(covs) if use_gauss else null, _p(den) if use_gauss else null, ptr[0], ptr[1], ptr[2], ptr[3],
-                _p(out_slots), _i(S), _i(T), _i(E), _i(H), _i(W), _i(C), _i(gauss_radius if use_gauss else 0),
+                _p(covs) if use_gauss else null, _p(den) if (use_gauss and den is not None) else null, ptr[0], ptr[1], ptr[2],
+                ptr[3], _p(out_slots), _i(S), _i(T), _i(E), _i(H), _i(W), _i(C), _i(gauss_radius if use_gauss else 0),
                 _i(precision), _i(1 if round_half else 0), _stream(hi))
         _lib.check(st, "build_pyramid (slots)")
         return lv
@@ -316,7 +339,7 @@ def build_pyramid(hi, lo, ii, jj, H, W, means=None, covs=None, den=None, num_lev
     with torch.cuda.device(hi.device):
         st = _lib.lib().lgu_build_pyramid(_p(hi), _p(lo) if precision == 2 else null, _p(ii), _p(jj),
                                           _p(means) if use_gauss else null, _p(covs) if use_gauss else null,
-                                          _p(den) if use_gauss else null, ptr[0], ptr[1], ptr[2], ptr[3],
+                                          _p(den) if (use_gauss and den is not None) else null, ptr[0], ptr[1], ptr[2], ptr[3],
                                           _i(T), _i(E), _i(H), _i(W), _i(C), _i(gauss_radius if use_gauss else 0),
                                           _i(precision), _i(1 if round_half else 0), _stream(hi))
     _lib.check(st, "build_pyramid")

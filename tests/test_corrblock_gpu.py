@@ -401,3 +401,38 @@ def test_altcorrblock_writes_into_a_callers_buffer_at_given_rows(dtype):
         assert torch.equal(got, want.half())
     untouched = [r for r in range(9) if r not in rows.tolist()]
     assert (buf[untouched] == -7.0).all()
+
+
+def test_offset_heads_kernel_matches_the_reference_chain(ops):
+    """lgu_offset_heads (2 launches) against the reference's chain (corr.py:117-135 with per_Corr_Normalization :44-51),
+    evaluated by torch in fp32: offsets agree within 1e-5 (|offset| <= 4; statistics are accumulated in fp64 here and by
+    Welford in torch), layout [E,H,W,98] contiguous."""
+    dev = "cuda"
+    g = inputs.gen(41)
+    E, CH, H, W = 3, 98, 48, 64
+    c0 = (torch.randn(E, CH, H, W, generator=g) * 1.7 + 0.3).to(dev)
+    c1 = (torch.randn(E, CH, H // 2, W // 2, generator=g) * 0.6 - 0.2).to(dev)
+
+    def norm(x):
+        mean = x.mean(dim=[1, 2, 3], keepdim=True)
+        std = torch.sqrt(x.var(dim=[1, 2, 3], unbiased=False, keepdim=True) + 1e-5)
+        return (x - mean) / std
+    w0 = torch.tanh(norm(c0)) * 4
+    w1 = (torch.tanh(norm(torch.nn.functional.interpolate(c1, (H, W)))) * 4 + w0) / 2
+    off0, off1 = ops.offset_heads(c0, c1)
+    assert off0.shape == (E, H, W, CH) and off0.is_contiguous() and off1.is_contiguous()
+    assert (off0 - w0.permute(0, 2, 3, 1)).abs().max().item() <= 1e-5
+    assert (off1 - w1.permute(0, 2, 3, 1)).abs().max().item() <= 1e-5
+
+
+def test_build_forms_the_gaussian_denominator_itself(ops):
+    """den = NULL: the build kernel computes 6.28 * sqrt(cov_x * cov_y) in its prologue -- bit-identical pyramids."""
+    dev = "cuda"
+    c = inputs.frontend_case(E=3, T=4, seed=43)
+    hi, _ = ops.pack_fmaps(c["fmaps"].half().to(dev))
+    ii, jj, means, covs = c["ii"].to(dev), c["jj"].to(dev), c["means"].to(dev), c["covs"].to(dev)
+    den = (6.28 * torch.sqrt(covs[..., 0] * covs[..., 1])).contiguous()
+    a = ops.build_pyramid(hi, None, ii, jj, 48, 64, means=means, covs=covs, den=den, gauss_radius=4)
+    b = ops.build_pyramid(hi, None, ii, jj, 48, 64, means=means, covs=covs, den=None, gauss_radius=4)
+    for l in range(4):
+        assert torch.equal(a[l], b[l]), f"level {l}"
