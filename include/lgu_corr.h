@@ -178,6 +178,19 @@ LGU_API int lgu_corr_lookup_fused_cum(const float* lvl0, const float* lvl1, cons
                               float* corr, float* mask_out, const int32_t* slots, int num_slots,
                               int E, int H, int W, int num_levels, int radius, void* stream);
 
+/* The fused lookup with its CONSUMER's first layer folded in: UpdateModule.corr_encoder[0:2] =
+ * Conv2d(196, 128, 1) + ReLU (droid_net.py:74-76, applied at :115) is evaluated on the 196 x 32 tile while it is still in
+ * shared memory -- TF32 tensor-core MMAs with a 3-term hi/lo split, fp32 accumulation: <= 1e-5 of F.conv2d in fp32 --
+ * and enc [E,128,H,W] (fp32, or fp16 with out_half) is written; corr [E,196,H,W] is written too unless NULL (then the
+ * 784 B/pixel tensor never exists).  wfrag = lgu_pack_conv1x1(weight [128,196]) (6400 x 2 float4), bias [128] or NULL.
+ * Everything else as lgu_corr_lookup_fused_cum (off1 pristine, cum_mask in/out, optional slots). */
+LGU_API int lgu_pack_conv1x1(const float* weight, float* wfrag, int out_channels, int in_channels, void* stream);
+LGU_API int lgu_corr_lookup_fused_enc(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                              const float* coords, const float* off0, const float* off1, float* cum_mask,
+                              float* corr, void* enc, const float* wfrag, const float* bias, int relu, int out_half,
+                              float* mask_out, const int32_t* slots, int num_slots,
+                              int E, int H, int W, int num_levels, int radius, void* stream);
+
 /* The same fused lookup with the BACKEND path's semantics (AltCorrBlock.corr_fn, corr.py:174-215, whose samplers
  * are lowMem_defSample.cu:27-134 and src/altcorr_kernel.cu:27-149): every bilinear corner is gated on its own
  * (quirk Q4) and fractions are x - floor(x).  lvl_l here is the volume of level 0 source maps against the level-l

@@ -471,6 +471,38 @@ class CorrBlock:
             out.append(corr.view(batch, num, -1, ht, wd))
         return torch.cat(out, dim=2), self.mean_n, self.theta
 
+    @torch.no_grad()
+    def lookup_encoded(self, coords, corr_encoder, keep_corr=False, enc_half=False):
+        """__call__ with the consumer's first layer folded into the lookup kernel (inference): corr_encoder is
+        UpdateModule.corr_encoder (droid_net.py:74-78) or its first conv; returns (enc, mean_n, theta) with
+        enc = relu(conv1x1(corr)) [b,n,128,h,w] -- feed it to corr_encoder[2:] -- or (corr, enc, mean_n, theta) with
+        keep_corr=True.  The 196-channel tensor is not written unless asked for."""
+        conv = corr_encoder[0] if isinstance(corr_encoder, nn.Sequential) else corr_encoder
+        if not (isinstance(conv, nn.Conv2d) and conv.kernel_size == (1, 1) and conv.in_channels == 196
+                and conv.out_channels == 128):
+            raise RuntimeError("lookup_encoded needs the 196 -> 128 1x1 corr_encoder conv")
+        batch, num, ht, wd, _ = coords.shape
+        E = batch * num
+        if not self._can_fuse_lookup(coords):
+            raise RuntimeError("lookup_encoded needs the fused lookup (4 levels, r = 3, W % 32 == 0, H % 8 == 0)")
+        key = (id(conv), conv.weight._version, conv.weight.data_ptr())
+        if getattr(self, "_enc_key", None) != key:
+            self._enc_key, self._enc_frag = key, ops.pack_conv1x1(conv.weight.float())
+        if not isinstance(self.offset, _Offsets):
+            self.offset = _Offsets(self.offset)
+        if not (self.offset[0].is_contiguous() and self.offset[0].dtype == torch.float32):
+            self.offset[0] = self.offset[0].float().contiguous()
+        pyr = [t if t.is_contiguous() else t.contiguous() for t in self.corr_pyramid]
+        c = coords.detach().reshape(E, ht, wd, 2).float().contiguous()
+        base, cum = self.offset.factored()
+        bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+        corr, enc = ops.corr_lookup_fused_enc(pyr, c, self.offset[0], base, cum, self._enc_frag, bias, relu=True,
+                                              keep_corr=keep_corr, enc_half=enc_half)
+        enc = enc.view(batch, num, 128, ht, wd)
+        if keep_corr:
+            return corr.view(batch, num, -1, ht, wd), enc, self.mean_n, self.theta
+        return enc, self.mean_n, self.theta
+
     def cat(self, other):
         for i in range(self.num_levels):
             self.corr_pyramid[i] = torch.cat([self.corr_pyramid[i], other.corr_pyramid[i]], 0)

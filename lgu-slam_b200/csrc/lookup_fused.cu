@@ -69,6 +69,12 @@ struct FusedLookupParams {
   long long off_edge_stride;   // float2 elements between the offset slabs of consecutive edges (0: every edge reads slab 0, Q2)
   int apply_mask;              // 1: level-1 offsets are scaled by sigmoid(var) of this call (CorrBlock); 0: used as given
   const int32_t* slots;        // [E] or null: edge n lives in pyramid / offset slot slots[n] (edge-slot pool)
+  // CONV: the consumer's first layer, UpdateModule.corr_encoder[0:2] = Conv2d(196, 128, 1) + ReLU (droid_net.py:74-76,115),
+  // evaluated on the staged 196 x 32 tile before it leaves the SM
+  const float4* conv_w;        // [8 warps][25 k-steps][32 lanes][2] float4: mma fragments (a0..a3) of W_hi then W_lo (lgu_pack_conv1x1)
+  const float* conv_b;         // [128] or null
+  void* enc;                   // [E_out,128,P] fp32 (fp16 with HALF); rows follow out_index like `out`
+  int conv_relu;
 };
 
 __device__ __forceinline__ float4 flf_lds128(uint32_t addr) {
@@ -104,7 +110,20 @@ __device__ __forceinline__ void flf_bulk_g2s(uint32_t dst, const void* src, uint
 // pixel loop is an LDG: a tile's offset records (2 x 1,568 B per warp), coords and cumulative masks arrive by
 // cp.async.bulk on their own mbarriers, the next tile's coords are on chip before the current tile ends, and the ring
 // keeps prefetching boxes ACROSS tile boundaries, so the memory pipeline never drains between tiles.
-template <bool PC, bool HALF>
+// m16n8k8 TF32 tensor-core MMA on register fragments (D += A * B, fp32 accumulate)
+__device__ __forceinline__ void flf_mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t flf_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+template <bool PC, bool HALF, bool CONV = false>
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupParams prm) {
   using namespace fl;
@@ -375,7 +394,61 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     if (has_next && lane == 0) fetch_offsets(npw, nns);
 
     __syncthreads();
-    {
+    if (CONV) {
+      // ---- corr_encoder[0:2] on the staged tile: enc[oc, pixel] = relu(b[oc] + sum_k W[oc, k] * corr[k, pixel]).
+      // Warp w owns output channels 16 w .. 16 w + 15 for all 32 pixels: 4 n-tiles x 25 k-steps of m16n8k8 TF32 MMAs on
+      // register fragments, 3-term split (W = W_hi + W_lo pre-split by lgu_pack_conv1x1, corr = hi + lo split here;
+      // lo*lo dropped: ~2^-22 relative per product, fp32 accumulation) -> <= 1e-5 of F.conv2d in fp32 for O(1..10) values.
+      // (tcgen05 would want W_hi / W_lo in tensor memory -- 392 of the 512 columns an SM shares between its two resident
+      // CTAs -- and UMMA-layout copies of the tile next to a 107 KB TMA ring: neither fits, and 3.7 GFLOP-equivalent per
+      // 48-edge lookup is far from the legacy tensor path's limit.)
+      constexpr int KS = (CH + 7) / 8;                          // 25 k-steps; rows 196..199 are zero
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f; }
+      const float4* wf = prm.conv_w + ((size_t)warp * KS * 32 + lane) * 2;
+      const int kq = lane & 3, nq = lane >> 2;
+#pragma unroll 1
+      for (int ks = 0; ks < KS; ++ks) {
+        const float4 whi = __ldg(wf + (size_t)ks * 64), wlo = __ldg(wf + (size_t)ks * 64 + 1);
+        const uint32_t ahi[4] = {__float_as_uint(whi.x), __float_as_uint(whi.y), __float_as_uint(whi.z), __float_as_uint(whi.w)};
+        const uint32_t alo[4] = {__float_as_uint(wlo.x), __float_as_uint(wlo.y), __float_as_uint(wlo.z), __float_as_uint(wlo.w)};
+        const int k0 = ks * 8 + kq, k1 = k0 + 4;
+        const bool v0 = k0 < CH, v1 = k1 < CH;
+        const float* r0 = s_out + (v0 ? k0 : 0) * kOutPitch + nq;
+        const float* r1 = s_out + (v1 ? k1 : 0) * kOutPitch + nq;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float x0 = v0 ? r0[nt * 8] : 0.0f, x1 = v1 ? r1[nt * 8] : 0.0f;
+          const uint32_t h0 = flf_tf32(x0), h1 = flf_tf32(x1);
+          const uint32_t l0 = flf_tf32(x0 - __uint_as_float(h0)), l1 = flf_tf32(x1 - __uint_as_float(h1));
+          flf_mma_tf32(acc[nt], alo, h0, h1);                   // small terms first
+          flf_mma_tf32(acc[nt], ahi, l0, l1);
+          flf_mma_tf32(acc[nt], ahi, h0, h1);
+        }
+      }
+      // C fragment: rows oc0 + nq (c0, c1) and oc0 + nq + 8 (c2, c3), pixels nt * 8 + 2 kq + {0, 1}
+      const int p0 = pw - warp * kPixPerWarp;
+      const int oc_a = warp * 16 + nq, oc_b = oc_a + 8;
+      const float ba = prm.conv_b != nullptr ? __ldg(prm.conv_b + oc_a) : 0.0f;
+      const float bb = prm.conv_b != nullptr ? __ldg(prm.conv_b + oc_b) : 0.0f;
+      const size_t erow = (size_t)(prm.out_index != nullptr ? __ldg(prm.out_index + n) : n) * 128 * P + p0 + 2 * kq;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float e0 = acc[nt][0] + ba, e1 = acc[nt][1] + ba, e2 = acc[nt][2] + bb, e3 = acc[nt][3] + bb;
+        if (prm.conv_relu) { e0 = fmaxf(e0, 0.0f); e1 = fmaxf(e1, 0.0f); e2 = fmaxf(e2, 0.0f); e3 = fmaxf(e3, 0.0f); }
+        if (HALF) {
+          __half* enc = reinterpret_cast<__half*>(prm.enc) + erow + nt * 8;
+          *reinterpret_cast<__half2*>(enc + (size_t)oc_a * P) = __floats2half2_rn(e0, e1);
+          *reinterpret_cast<__half2*>(enc + (size_t)oc_b * P) = __floats2half2_rn(e2, e3);
+        } else {
+          float* enc = reinterpret_cast<float*>(prm.enc) + erow + nt * 8;
+          *reinterpret_cast<float2*>(enc + (size_t)oc_a * P) = make_float2(e0, e1);
+          *reinterpret_cast<float2*>(enc + (size_t)oc_b * P) = make_float2(e2, e3);
+        }
+      }
+    }
+    if (!CONV || prm.out != nullptr) {
       const int p0 = pw - warp * kPixPerWarp;
       const size_t row = (size_t)(prm.out_index != nullptr ? __ldg(prm.out_index + n) : n) * CH * P + p0 + lane;
       const float* srow = s_out + lane;
@@ -397,11 +470,57 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 }  // namespace lgu
 
 namespace lgu {
+struct ConvArgs {
+  const float4* w;
+  const float* b;
+  void* enc;
+  int relu;
+};
 static int launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                const float* coords, const float* off0, float* off1, float* corr, float* mask_out, int E,
                                int H, int W, int num_levels, int radius, int per_corner, int shared_offsets,
                                int apply_mask, const int32_t* slots, int num_slots, float* cum_mask,
-                               const int32_t* out_index, int out_half, void* stream);
+                               const int32_t* out_index, int out_half, void* stream, const ConvArgs* conv = nullptr);
+
+// W [128, K] (K <= 200) -> the m16n8k8 A fragments the CONV epilogue reads: [8 warps][25 k-steps][32 lanes]{hi(a0..a3), lo(a0..a3)}
+__global__ void pack_conv1x1_kernel(const float* __restrict__ W, float4* __restrict__ frag, int K) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 8 * 25 * 32) return;
+  const int lane = t & 31, ks = (t >> 5) % 25, w = t / (25 * 32);
+  const int r0 = w * 16 + (lane >> 2), r1 = r0 + 8, c0 = ks * 8 + (lane & 3), c1 = c0 + 4;
+  const float a[4] = {c0 < K ? W[(size_t)r0 * K + c0] : 0.0f, c0 < K ? W[(size_t)r1 * K + c0] : 0.0f,
+                      c1 < K ? W[(size_t)r0 * K + c1] : 0.0f, c1 < K ? W[(size_t)r1 * K + c1] : 0.0f};
+  float hi[4], lo[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    hi[q] = __uint_as_float(flf_tf32(a[q]));
+    lo[q] = __uint_as_float(flf_tf32(a[q] - hi[q]));
+  }
+  frag[(size_t)t * 2] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  frag[(size_t)t * 2 + 1] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+}
+extern "C" int lgu_pack_conv1x1(const float* weight, float* wfrag, int out_channels, int in_channels, void* stream) {
+  LGU_REQUIRE(weight && wfrag, "lgu_pack_conv1x1: null pointer");
+  LGU_REQUIRE(out_channels == 128 && in_channels == 196, "lgu_pack_conv1x1: only the 196 -> 128 corr_encoder is implemented");
+  lgu::pack_conv1x1_kernel<<<(8 * 25 * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      weight, reinterpret_cast<float4*>(wfrag), in_channels);
+  return lgu::check_launch("lgu_pack_conv1x1");
+}
+extern "C" int lgu_corr_lookup_fused_enc(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                         const float* coords, const float* off0, const float* off1, float* cum_mask,
+                                         float* corr, void* enc, const float* wfrag, const float* bias, int relu,
+                                         int out_half, float* mask_out, const int32_t* slots, int num_slots, int E, int H,
+                                         int W, int num_levels, int radius, void* stream) {
+  LGU_REQUIRE(E == 0 || (cum_mask != nullptr && enc != nullptr && wfrag != nullptr), "lgu_corr_lookup_fused_enc: null pointer");
+  LGU_REQUIRE(slots == nullptr || num_slots > 0, "lgu_corr_lookup_fused_enc: bad pool size %d", num_slots);
+  LGU_REQUIRE((reinterpret_cast<uintptr_t>(wfrag) & 15) == 0 && (reinterpret_cast<uintptr_t>(enc) & 7) == 0,
+              "lgu_corr_lookup_fused_enc: wfrag must be 16-byte and enc 8-byte aligned");
+  LGU_REQUIRE(!(out_half && corr != nullptr), "lgu_corr_lookup_fused_enc: fp16 output applies to enc only (pass corr = NULL)");
+  const lgu::ConvArgs conv = {reinterpret_cast<const float4*>(wfrag), bias, enc, relu};
+  return lgu::launch_lookup_fused(lvl0, lvl1, lvl2, lvl3, coords, off0, const_cast<float*>(off1), corr, mask_out, E, H, W,
+                                  num_levels, radius, 0, 0, 1, slots, slots != nullptr ? num_slots : E, cum_mask, nullptr,
+                                  out_half, stream, &conv);
 }
 extern "C" int lgu_corr_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                      const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
@@ -447,10 +566,11 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
                                     const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                     int E, int H, int W, int num_levels, int radius, int per_corner,
                                     int shared_offsets, int apply_mask, const int32_t* slots, int num_slots,
-                                    float* cum_mask, const int32_t* out_index, int out_half, void* stream) {
+                                    float* cum_mask, const int32_t* out_index, int out_half, void* stream,
+                                    const ConvArgs* conv) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
-  LGU_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && off0 && off1 && corr, "lgu_corr_lookup_fused: null pointer");
+  LGU_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && off0 && off1 && (corr || conv), "lgu_corr_lookup_fused: null pointer");
   LGU_REQUIRE(E > 0 && H > 0 && W > 0, "lgu_corr_lookup_fused: bad sizes E=%d H=%d W=%d", E, H, W);
   if (num_levels != 4 || radius != 3 || (W % 32) != 0 || (H % 8) != 0) {
     set_error("lgu_corr_lookup_fused: only num_levels=4, radius=3, W%%32==0, H%%8==0 are implemented "
@@ -480,6 +600,8 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
   prm.coords = coords; prm.off0 = off0; prm.off1 = off1; prm.out = corr; prm.mask_out = mask_out;
   prm.cum_mask = cum_mask;
   prm.out_index = out_index;
+  prm.conv_w = conv ? conv->w : nullptr; prm.conv_b = conv ? conv->b : nullptr; prm.enc = conv ? conv->enc : nullptr;
+  prm.conv_relu = conv ? conv->relu : 0;
   prm.P = P;
   prm.tiles_per_edge = P / fl::kTile;                         // W % 32 == 0: tiles are always full
   const long long ntiles = (long long)E * prm.tiles_per_edge;
@@ -495,6 +617,10 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
   LGU_REQUIRE(!(shared_offsets && apply_mask), "lgu_*_lookup_fused: apply_mask needs per-edge offsets");
   auto kern = per_corner ? (out_half ? lookup_fused_kernel<true, true> : lookup_fused_kernel<true, false>)
                          : (out_half ? lookup_fused_kernel<false, true> : lookup_fused_kernel<false, false>);
+  if (conv != nullptr) {
+    LGU_REQUIRE(!per_corner, "lgu_corr_lookup_fused_enc: the fused encoder is implemented for the CorrBlock lookup");
+    kern = out_half ? lookup_fused_kernel<false, true, true> : lookup_fused_kernel<false, false, true>;
+  }
   if (int rc = optin_smem(reinterpret_cast<const void*>(kern), flf::kFwdSmemBytes, "lgu_corr_lookup_fused")) return rc;
   kern<<<(unsigned)nblk, fl::kThreads, flf::kFwdSmemBytes, (cudaStream_t)stream>>>(maps, prm);
   return check_launch("lgu_corr_lookup_fused");

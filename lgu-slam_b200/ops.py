@@ -401,6 +401,61 @@ def corr_lookup_fused(pyramid, coords, off0, off1, radius=3, return_mask=False, 
     return (corr, mask) if return_mask else corr
 
 
+def pack_conv1x1(weight):
+    """corr_encoder[0].weight [128,196] (or [128,196,1,1]) -> the tensor-core operand fragments of the fused encoder
+    epilogue (TF32 hi/lo split, m16n8k8 A-fragment order): a float32 tensor of 8*25*32*8 elements."""
+    if not (isinstance(weight, torch.Tensor) and weight.is_cuda and weight.dtype == torch.float32):
+        raise RuntimeError("weight must be a CUDA fp32 tensor")
+    w = weight.detach().reshape(weight.shape[0], -1).contiguous()
+    if tuple(w.shape) != (128, 196):
+        raise RuntimeError(f"only the 196 -> 128 corr_encoder is implemented, got weight {tuple(weight.shape)}")
+    frag = torch.empty(8 * 25 * 32 * 8, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        st = _lib.lib().lgu_pack_conv1x1(_p(w), _p(frag), _i(128), _i(196), _stream(w))
+    _lib.check(st, "pack_conv1x1")
+    return frag
+
+
+def corr_lookup_fused_enc(pyramid, coords, off0, off1, cum_mask, wfrag, bias=None, relu=True, keep_corr=False,
+                          enc_half=False, slots=None):
+    """corr_lookup_fused (cumulative-mask form) with the consumer's first layer folded in: UpdateModule.corr_encoder[0:2] =
+    Conv2d(196,128,1) + ReLU (droid_net.py:74-76,115) evaluated on the staged tile with TF32 tensor-core MMAs (3-term
+    split, <= 1e-5 of F.conv2d in fp32).  Returns (corr [E,196,H,W] or None, enc [E,128,H,W] fp32 / fp16).
+    keep_corr=False: the 196-channel tensor is never written.  wfrag from pack_conv1x1; bias [128] or None."""
+    if len(pyramid) != 4:
+        raise RuntimeError("corr_lookup_fused_enc needs a 4-level pyramid")
+    S, H, W = pyramid[0].shape[:3]
+    for l, t in enumerate(pyramid):
+        _chk(t, f"pyramid[{l}]", 5)
+        if tuple(t.shape) != (S, H, W, H >> l, W >> l):
+            raise RuntimeError(f"pyramid[{l}] shape {tuple(t.shape)} != {(S, H, W, H >> l, W >> l)}")
+    _chk(coords, "coords", 4); _chk(cum_mask, "cum_mask", 3)
+    E = coords.shape[0] if slots is not None else S
+    if tuple(coords.shape) != (E, H, W, 2) or tuple(cum_mask.shape) != (S, H, W):
+        raise RuntimeError("corr_lookup_fused_enc: inconsistent coords / cum_mask shapes")
+    for name, o in (("off0", off0), ("off1", off1)):
+        if not (isinstance(o, torch.Tensor) and o.is_cuda and o.is_contiguous() and o.dtype == torch.float32
+                and o.numel() == S * H * W * 98):
+            raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor with {S * H * W * 98} elements")
+    if not (wfrag.is_cuda and wfrag.dtype == torch.float32 and wfrag.numel() == 8 * 25 * 32 * 8 and wfrag.is_contiguous()):
+        raise RuntimeError("wfrag must come from pack_conv1x1")
+    if bias is not None and not (bias.is_cuda and bias.dtype == torch.float32 and bias.numel() == 128 and bias.is_contiguous()):
+        raise RuntimeError("bias must be a contiguous CUDA fp32 vector of 128")
+    if keep_corr and enc_half:
+        raise RuntimeError("enc_half needs keep_corr=False")
+    corr = torch.empty(E, 196, H, W, dtype=torch.float32, device=coords.device) if keep_corr else None
+    enc = torch.empty(E, 128, H, W, dtype=torch.float16 if enc_half else torch.float32, device=coords.device)
+    null = ctypes.c_void_p(0)
+    with torch.cuda.device(coords.device):
+        st = _lib.lib().lgu_corr_lookup_fused_enc(
+            _p(pyramid[0]), _p(pyramid[1]), _p(pyramid[2]), _p(pyramid[3]), _p(coords), _p(off0), _p(off1), _p(cum_mask),
+            _p(corr) if keep_corr else null, _p(enc), _p(wfrag), _p(bias) if bias is not None else null,
+            _i(1 if relu else 0), _i(1 if enc_half else 0), null, _p(slots) if slots is not None else null, _i(S), _i(E),
+            _i(H), _i(W), _i(4), _i(3), _stream(coords))
+    _lib.check(st, "corr_lookup_fused_enc")
+    return corr, enc
+
+
 def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad, off1_out_grad=None,
                                accumulate_into=None, cum_mask=None):
     """Backward of corr_lookup_fused in one launch (what autograd runs for corr.py:88-109 in training).

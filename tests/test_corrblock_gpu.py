@@ -436,3 +436,33 @@ def test_build_forms_the_gaussian_denominator_itself(ops):
     b = ops.build_pyramid(hi, None, ii, jj, 48, 64, means=means, covs=covs, den=None, gauss_radius=4)
     for l in range(4):
         assert torch.equal(a[l], b[l]), f"level {l}"
+
+
+def test_corrblock_lookup_encoded_matches_call_plus_corr_encoder():
+    """CorrBlock.lookup_encoded (the fused lookup with UpdateModule.corr_encoder[0:2] folded in) == relu(conv1x1(__call__)),
+    and both keep the block's cumulative offset state in step."""
+    dev = "cuda"
+    corr, ofsMap, ofs_residual, GA = _modules(dev, 10)
+    g = inputs.gen(51)
+    f1 = torch.randn(1, 3, 128, 48, 64, generator=g).half().to(dev)
+    f2 = torch.randn(1, 3, 128, 48, 64, generator=g).half().to(dev)
+    coords = [inputs.make_coords(3, 48, 64, 48, 64, g).permute(0, 2, 3, 1).contiguous().view(1, 3, 48, 64, 2).to(dev) for _ in range(2)]
+    torch.manual_seed(6)
+    enc_net = nn.Sequential(nn.Conv2d(196, 128, 1), nn.ReLU(inplace=True), nn.Conv2d(128, 128, 3, padding=1), nn.ReLU(inplace=True)).to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            a = corr.CorrBlock(ofsMap, ofs_residual, GA, f1, f2)
+            b = corr.CorrBlock(ofsMap, ofs_residual, GA, f1, f2)
+            for c in coords:
+                out, _, _ = a(c)
+                want = torch.relu(enc_net[0](out.view(3, 196, 48, 64)))
+                kept, enc, mean_n, theta = b.lookup_encoded(c, enc_net, keep_corr=True)
+                assert torch.equal(kept, out) and enc.shape == (1, 3, 128, 48, 64)
+                err = (enc.view(3, 128, 48, 64) - want).abs().max().item()
+                assert err <= 2e-5 * max(1.0, want.abs().max().item()), err       # both sides are fp32 evaluations here
+            enc_only, _, _ = b.lookup_encoded(coords[0], enc_net[0])
+            assert enc_only.shape == (1, 3, 128, 48, 64)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev

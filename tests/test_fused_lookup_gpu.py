@@ -294,3 +294,45 @@ def test_fused_backward_cumulative_mask_form_equals_materialised_form(ops, accum
     got = ops.corr_lookup_fused_backward(pyr, coords, off0, off1, mask, g_corr, accumulate_into=acc_b, cum_mask=cum)
     for k, (a, b) in enumerate(zip(got, want)):
         assert torch.equal(a, b), f"output {k}"
+
+
+@pytest.mark.parametrize("keep_corr,half", [(True, False), (False, False), (False, True)])
+def test_fused_lookup_with_corr_encoder_epilogue(ops, keep_corr, half):
+    """UpdateModule.corr_encoder[0:2] (Conv2d(196,128,1) + ReLU, droid_net.py:74-76,115) folded into the
+    lookup kernel.  corr (when kept) is bit-identical to the plain fused lookup; enc agrees with F.conv2d + relu evaluated
+    in fp32 (TF32 off) on that corr within 1e-5 * max(1, max|enc|); the fp16 output is that value rounded to nearest
+    (compared at 1 fp16 ulp)."""
+    dev = "cuda"
+    E = 3
+    g = inputs.gen(101)
+    pyr = [torch.randn(E, 48, 64, 48 >> l, 64 >> l, generator=g).to(dev) for l in range(4)]
+    c = _case(E, 102)
+    coords, off0, off1 = c["coords"].to(dev), c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+    torch.manual_seed(5)
+    conv = torch.nn.Conv2d(196, 128, 1).to(dev)
+    with torch.no_grad():
+        conv.weight.mul_(3.0)                                    # O(1) outputs, live low-order bits
+    cum_a, cum_b = torch.ones(E, 48, 64, device=dev), torch.ones(E, 48, 64, device=dev)
+    want_corr = ops.corr_lookup_fused(pyr, coords, off0, off1, 3, cum_mask=cum_a)
+    frag = ops.pack_conv1x1(conv.weight)
+    corr, enc = ops.corr_lookup_fused_enc(pyr, coords, off0, off1, cum_b, frag, conv.bias.detach().contiguous(), relu=True,
+                                          keep_corr=keep_corr, enc_half=half)
+    assert torch.equal(cum_a, cum_b)
+    if keep_corr:
+        assert torch.equal(corr, want_corr)
+    else:
+        assert corr is None
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = torch.relu(torch.nn.functional.conv2d(want_corr.double(), conv.weight.double(), conv.bias.double()))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    assert enc.shape == (E, 128, 48, 64) and enc.dtype == (torch.float16 if half else torch.float32)
+    scale = max(1.0, want.abs().max().item())
+    err = (enc.double() - want).abs().max().item()
+    if half:
+        assert err <= 2.0 ** -10 * scale, f"fp16 enc: {err} (scale {scale})"
+    else:
+        assert err <= 1e-5 * scale, f"enc: {err} (scale {scale})"

@@ -12,10 +12,19 @@ pyr = [torch.randn(E, H, W, H >> l, W >> l, device=dev, generator=g) for l in ra
 o1 = fc["offsets"][1].to(dev); o0 = fc["offsets"][0].to(dev); co = fc["coords"].to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 modes = ["writeback"] + (["cum"] if hasattr(lgu_slam_b200._lib.lib(), "lgu_corr_lookup_fused_cum") else [])
+if hasattr(lgu_slam_b200._lib.lib(), "lgu_corr_lookup_fused_enc"):
+    modes += ["enc+corr", "enc", "enc_fp16", "cum+cudnn_conv"]
+    conv = torch.nn.Conv2d(196, 128, 1).to(dev)
+    frag = ops.pack_conv1x1(conv.weight); bias = conv.bias.detach().contiguous()
 for mode in modes:
     cum = torch.ones(E, H, W, device=dev)
     def f(o):
         if mode == "cum": ops.corr_lookup_fused(pyr, co, o0, o, 3, cum_mask=cum)
+        elif mode == "enc+corr": ops.corr_lookup_fused_enc(pyr, co, o0, o, cum, frag, bias, keep_corr=True)
+        elif mode == "enc": ops.corr_lookup_fused_enc(pyr, co, o0, o, cum, frag, bias)
+        elif mode == "enc_fp16": ops.corr_lookup_fused_enc(pyr, co, o0, o, cum, frag, bias, enc_half=True)
+        elif mode == "cum+cudnn_conv":
+            with torch.no_grad(): torch.relu_(conv(ops.corr_lookup_fused(pyr, co, o0, o, 3, cum_mask=cum)))
         else: ops.corr_lookup_fused(pyr, co, o0, o, 3)
     for _ in range(3): f(o1.clone())
     torch.cuda.synchronize(); ts = []
