@@ -194,13 +194,13 @@ class Workload:
         n0 = self.lib.LAUNCHES
         mark("start")
         hi, _ = ops.pack_fmaps(d["fmaps"])
+        self.cum.fill_(1.0)                                        # state of a freshly built block: no mask applied yet
         mark("pack")
         pyr = ops.build_pyramid(hi, None, d["ii"], d["jj"], H, W, means=d["means"], covs=d["covs"], den=d["den"],
                                 num_levels=LEVELS, gauss_radius=GR, precision=1)
         mark("build")
         # ---- CorrBlock.__call__ (corr.py:88-109): one fused TMA-staged launch (mask lookup + 4 deformable levels); the
         # block's cumulative offset[1] mask (Q7) lives in a per-pixel buffer, offset[1] itself stays pristine
-        self.cum.fill_(1.0)                                        # a freshly built block: no mask applied yet
         corr, mask = ops.corr_lookup_fused(pyr, d["coords"], d["off0"], d["off1"], R, return_mask=True, cum_mask=self.cum)
         mark("lookup_fwd")
         # ---- its backward (what autograd runs for corr.py:88-109): one launch, dense gradients of all 4 levels; the

@@ -2,7 +2,7 @@
 # One GPU-box visit: parity tests, bench (ours + CPU arm), ncu launch list of the bench command.
 # Usage (from the dev container):  gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag]'
 set -u
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
