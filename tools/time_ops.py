@@ -163,6 +163,9 @@ def reference_cuda():
         return torch.cat([ref.defCorr_index_forward(pyr[l], cl[l], o[l], 3)[0].view(E, 49, H, W) for l in range(4)], 1)
     o1 = off[1].reshape(E, H, W, 98).clone()
     both("CorrBlock.__call__ data path", ref_call, lambda: ops.corr_lookup_fused(pyr, coords, off[0].view(E, H, W, 98), o1, 3))
+    cum = torch.ones(E, H, W, device=dev)
+    both("CorrBlock.__call__ data path (cumulative-mask form)", ref_call,
+         lambda: ops.corr_lookup_fused(pyr, coords, off[0].view(E, H, W, 98), o1, 3, cum_mask=cum))
     def ref_bwd():
         for l in range(4):
             ref.defCorr_index_backward(pyr[l], cl[l], off[l], grad, 3)
