@@ -484,8 +484,8 @@ class BackendWorkload:
     def engine(self, single):
         key = "single" if single else "sharded"
         if key not in self.plans:
-            def compute(c, i, j, out=None, out_index=None, pass_edges=None, pass_hook=None):
-                return self.blk(c, i, j, out=out, out_index=out_index, pass_edges=pass_edges, pass_hook=pass_hook)
+            def compute(c, i, j, out=None, out_index=None, pass_edges=None, pass_hook=None, key=None):
+                return self.blk(c, i, j, out=out, out_index=out_index, pass_edges=pass_edges, pass_hook=pass_hook, key=key)
             eng = self.sh.ShardedBackendCorr(compute, single_process=single)
             plan = eng.set_edges(self.ii, self.jj)
             mine = plan.rank_edges[eng.rank]
@@ -528,7 +528,7 @@ class BackendWorkload:
                 vd, _ = eng._chunk_index(ch, self.dev)
                 n = vd.numel()
                 idx = torch.arange(at, at + n, dtype=torch.int32, device=self.dev)
-                self.blk(c[:, at:at + n], self.ii_d[vd], self.jj_d[vd], out=peer, out_index=idx)
+                self.blk(c[:, at:at + n], self.ii_d[vd], self.jj_d[vd], out=peer, out_index=idx, key=("chunk", ch))
                 at += n
             torch.cuda.synchronize(self.dev)
             return peer

@@ -742,7 +742,7 @@ class AltCorrBlock:
         t = torch.cat(((f1 * 4.0).permute(0, 3, 1, 2), (f2 * 4.0).permute(0, 3, 1, 2)), dim=1).float()
         return _generate_offsets(self.ofsMap, self.ofs_residual, t)
 
-    def _corr_materialized(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None):
+    def _corr_materialized(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None, key=None):
         B, N, H, W, S, _ = coords.shape
         step = min(self.MAX_EDGES_PER_PASS, int(pass_edges)) if pass_edges else self.MAX_EDGES_PER_PASS
         assert B == 1 and S == 1, "the materialised path serves the reference's only call shape (B = S = 1)"
@@ -751,7 +751,9 @@ class AltCorrBlock:
         ii32, jj32 = ii.to(torch.int32).contiguous(), jj.to(torch.int32).contiguous()
         ent = None
         if self.cache:
-            key = (tuple(ii.tolist()), tuple(jj.tolist()))
+            # cache key of the chunk: the caller's (e.g. the sharded engine's chunk id) if given -- reading the edge list
+            # back from the device costs a host synchronisation per chunk
+            key = key if key is not None else (tuple(ii.tolist()), tuple(jj.tolist()))
             ent = self._cache.get(key)
             if ent is None:
                 # strict_ref: only slab 0 is ever read (Q2) -> generate just that slab
@@ -812,11 +814,11 @@ class AltCorrBlock:
         res = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
         return res.view(B, N, -1, H, W, 1)
 
-    def corr_fn(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None):
+    def corr_fn(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None, key=None):
         B, N, H, W, S, _ = coords.shape
         rd = 2 * self.radius + 1
         if self.materialize and B == 1 and S == 1:
-            return self._corr_materialized(coords, ii, jj, out, out_index, pass_edges, pass_hook)
+            return self._corr_materialized(coords, ii, jj, out, out_index, pass_edges, pass_hook, key)
         if out is not None:
             raise RuntimeError("out= needs the materialised path (4 levels, r = 3, C = 128, B = S = 1)")
         f1 = self.pyramid[0][:, ii]
@@ -845,16 +847,17 @@ class AltCorrBlock:
             out.append(corr.view(B, N, S, -1, H, W).permute(0, 1, 3, 4, 5, 2))
         return torch.cat(out, dim=2)
 
-    def __call__(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None):
+    def __call__(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None, key=None):
         """corr.py:238-249.  out / out_index (materialised path only): write edge e's [196,H,W] result into row
         out_index[e] of `out` ([E_out,196,H,W], fp32 or fp16 -- possibly another GPU's memory, see sharded.PeerOutput)
         instead of returning a new tensor; `out` is returned.  pass_edges / pass_hook: the chunk is processed in passes of
         at most pass_edges edges (volumes + lookup per pass) and pass_hook(first, last) is called after each pass's
-        launches are enqueued -- the sharded backend ships finished rows while the next pass computes."""
+        launches are enqueued -- the sharded backend ships finished rows while the next pass computes.  key: hashable
+        identity of this chunk for cache=True (default: the edge lists themselves, read back from the device)."""
         squeeze = coords.dim() == 5
         if squeeze:
             coords = coords.unsqueeze(dim=-2)
-        corr = self.corr_fn(coords, ii, jj, out, out_index, pass_edges, pass_hook)
+        corr = self.corr_fn(coords, ii, jj, out, out_index, pass_edges, pass_hook, key)
         if out is not None:
             return out
         if squeeze:

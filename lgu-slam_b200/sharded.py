@@ -263,8 +263,9 @@ class ShardedBackendCorr:
             params = inspect.signature(compute).parameters
             self._writes_in_place = "out" in params and "out_index" in params
             self._has_pass_hook = "pass_hook" in params and "pass_edges" in params
+            self._takes_key = "key" in params
         except (TypeError, ValueError):
-            self._writes_in_place = self._has_pass_hook = False
+            self._writes_in_place = self._has_pass_hook = self._takes_key = False
 
     def set_edges(self, ii, jj, frames_per_chunk=FRAMES_PER_CHUNK):
         self.plan = partition_edges(ii, jj, self.world, frames_per_chunk)
@@ -384,17 +385,20 @@ class ShardedBackendCorr:
                             for a, n_run, src in self._runs(v[first:last]):
                                 peer.buffer[a:a + n_run].copy_(stage[first + src:first + src + n_run], non_blocking=True)
 
+                kw = {"key": ("chunk", c)} if self._takes_key else {}
                 if self._has_pass_hook and k == len(plan.rank_chunks[self.rank]) - 1:     # ship pass by pass
-                    self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None, pass_edges=self.SHIP_EDGES, pass_hook=ship)
+                    self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None, pass_edges=self.SHIP_EDGES, pass_hook=ship,
+                                 **kw)
                 else:
-                    self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None)
+                    self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None, **kw)
                     ship(0, nv)
                 with torch.cuda.stream(self._copy_stream):
                     self._stage_free[b].record(self._copy_stream)
             elif self._writes_in_place:
                 if rows is None:
                     rows = torch.arange(r0, r0 + nv, dtype=torch.int32, device=dev)
-                self.compute(cc, ii[vd], jj[vd], out=peer.buffer, out_index=rows)
+                self.compute(cc, ii[vd], jj[vd], out=peer.buffer, out_index=rows,
+                             **({"key": ("chunk", c)} if self._takes_key else {}))
             else:                                                  # plain callable: copy its result over
                 res = self.compute(cc, ii[vd], jj[vd])[0].to(peer.buffer.dtype)
                 if r0 is not None:
