@@ -38,9 +38,22 @@ constexpr int kAccFloats = kSlotFloats;                          // 832 floats: 
 constexpr int kWarpFloats = kSlots * kInSlotFloats + kAccFloats; // 2112 floats = 8448 B
 constexpr int kSmemWarp = kWarps * kWarpFloats * 4;              // 67,584 B
 constexpr int kGWarpFloats = CH * kPixPerWarp;                   // per-warp upstream-gradient rows: 196 x 4 pixels
-constexpr int kSmemG = kWarps * kGWarpFloats * 4;                // 25,088 B
+constexpr int kGWarpStride = (kGWarpFloats * 4 + 127) / 128 * 32;    // 800 floats: the TMA destination is 128-byte aligned
+constexpr int kSmemG = kWarps * kGWarpStride * 4;                // 25,600 B
+constexpr int kPairBytes = 2 * TAPS * 8;                         // one level's offset records of a PIXEL PAIR: 784 B
+constexpr int kSmemOffs = kWarps * 2 * kPairBytes;               // 12,544 B (levels 0 and 1, single-buffered)
+constexpr int kSmallBytes = 64;                                  // per warp and tile parity: coords[4] float2 | mask[4] | scale[4]
+constexpr int kSmemSmall = kWarps * 2 * kSmallBytes;             // 1,024 B
+constexpr int kBarsPerWarp = kSlots + 4;                         // box ring[2], offset pair, upstream strip, small[2]
+constexpr int kSmemBars = kWarps * kBarsPerWarp * 8;
 using fl::kZeroBytes;                                            // CTA-shared zero source of the bulk zero-fill
-constexpr int kSmemBytes = kSmemWarp + kSmemG + kWarps * kSlots * 8 + kZeroBytes;
+constexpr int kOffG = kSmemWarp;
+constexpr int kOffOffs = kOffG + kSmemG;
+constexpr int kOffSmall = kOffOffs + kSmemOffs;
+constexpr int kOffBars = kOffSmall + kSmemSmall;
+constexpr int kOffZero = kOffBars + kSmemBars;
+constexpr int kSmemBytes = kOffZero + kZeroBytes;                // 115,456 B: two CTAs per SM
+static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM");
 }  // namespace flb
 
 struct FusedLookupBwdParams {
@@ -56,7 +69,7 @@ struct FusedLookupBwdParams {
   float* gv[4];              // dense volume gradients [E,P,H2,W2]
   float* g_off0;             // [E,P,49,2]
   float* g_off1;             // [E,P,49,2]  gradient of offset[1]_in
-  int P, tiles_per_edge;
+  int P, tiles_per_edge, num_tiles;
   int H2[4], W2[4];
 };
 
@@ -242,6 +255,14 @@ __device__ __forceinline__ void add_box(float* __restrict__ G, float* acc, int x
   }
 }
 
+// Round 2: PERSISTENT CTAs (two per SM) walk the tiles, and nothing a pixel needs is fetched by LDG inside the pixel loop
+// (ncu's source view of the per-tile version: 28 % of all samples were long-scoreboard stalls -- the first use of the
+// prefetched offset records, the cp.async loop of the upstream-gradient strip, the coords load of every CTA's prologue --
+// and 5 % sat at the CTA-end barrier).  Per tile and warp: the 196 x 4 upstream-gradient strip is ONE TMA box, the offset
+// records travel as pixel PAIRS by cp.async.bulk (a pair is 16-byte aligned; the single pair buffer is refilled as soon
+// as the second pixel of a pair has read its records), coords / mask / cumulative-mask scale arrive as 64 bytes per tile
+// one tile ahead, and the box ring keeps prefetching across tile boundaries.  The strip of the next tile is requested as
+// soon as the last pixel of the current one has moved its eight gradient values to registers.
 template <bool ACC, bool BULK, bool FXP>
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupBwdParams prm) {
@@ -251,35 +272,75 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
   float* wmem = reinterpret_cast<float*>(smem) + warp * kWarpFloats;
   float* inbox = wmem;                                           // [slot][lvl0 | lvl1]
   float* acc = wmem + kSlots * kInSlotFloats;                    // acc0 | acc1 | acc2 | acc3 (offsets kOff0..3)
-  float* s_g = reinterpret_cast<float*>(smem + kSmemWarp) + warp * kGWarpFloats;   // this warp's [CH][4 pixels]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemWarp + kSmemG) + warp * kSlots;
-  uint8_t* zero_smem = smem + kSmemWarp + kSmemG + kWarps * kSlots * 8;
+  float* s_g = reinterpret_cast<float*>(smem + kOffG) + warp * kGWarpStride;       // this warp's [CH][4 pixels]
+  const uint32_t smem0 = fl_smem_u32(smem);
+  const uint32_t offs_base = smem0 + kOffOffs + warp * 2 * kPairBytes;              // [level 0 | level 1][2 pixels][49] float2
+  const uint32_t small_base = smem0 + kOffSmall + warp * 2 * kSmallBytes;
+  const uint32_t bar_base = smem0 + kOffBars + warp * kBarsPerWarp * 8;
+  const uint32_t bar_off = bar_base + kSlots * 8, bar_strip = bar_base + (kSlots + 1) * 8, bar_small = bar_base + (kSlots + 2) * 8;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars) + warp * kBarsPerWarp;
+  uint8_t* zero_smem = smem + kOffZero;
   if (BULK && !ACC) {
     for (int q = threadIdx.x; q < kZeroBytes / 16; q += kThreads)
       reinterpret_cast<float4*>(zero_smem)[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
   }
-
   const int P = prm.P;
-  const int n = blockIdx.x / prm.tiles_per_edge;
-  const int p0 = (blockIdx.x - n * prm.tiles_per_edge) * kTile;
-  const int pw = p0 + warp * kPixPerWarp;
-
   if (lane == 0) {
-    fl_mbar_init(bars + 0, 1);
-    fl_mbar_init(bars + 1, 1);
+#pragma unroll
+    for (int q = 0; q < kBarsPerWarp; ++q) fl_mbar_init(bars + q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int q = lane; q < kAccFloats; q += 32) acc[q] = 0.0f;
   __syncwarp();
 
-  float2 cmine = make_float2(0.0f, 0.0f);
-  if (lane < kPixPerWarp)
-    cmine = __ldg(reinterpret_cast<const float2*>(prm.coords) + (size_t)n * P + min(pw + lane, P - 1));
-
-  auto issue = [&](int k, float cx, float cy) {                 // lane 0 only
-    const int slot = k & 1;
-    const int pix = n * P + min(pw + k, P - 1);
+  auto bulk_g2s = [&](uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  auto expect = [&](uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  };
+  auto wait = [&](uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FLB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FLB_DONE_%=;\n\t"
+        "bra FLB_WAIT_%=;\n\t"
+        "FLB_DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+  };
+  auto tile_edge = [&](int tile, int& n, int& pw) {
+    n = tile / prm.tiles_per_edge;
+    pw = (tile - n * prm.tiles_per_edge) * kTile + warp * kPixPerWarp;
+  };
+  // lane 0 only: per-tile inputs
+  auto fetch_small = [&](int n, int pw, int par) {
+    const uint32_t dst = small_base + par * kSmallBytes, bar = bar_small + par * 8;
+    expect(bar, prm.off1_scale != nullptr ? 64u : 48u);
+    bulk_g2s(dst, prm.coords + ((size_t)n * P + pw) * 2, 32, bar);
+    bulk_g2s(dst + 32, prm.mask + (size_t)n * P + pw, 16, bar);
+    if (prm.off1_scale != nullptr) bulk_g2s(dst + 48, prm.off1_scale + (size_t)n * P + pw, 16, bar);
+  };
+  auto fetch_pair = [&](int n, int pfirst) {                    // offset records of pixels pfirst, pfirst + 1 (pfirst even)
+    const size_t at = ((size_t)n * P + pfirst) * TAPS * 2;
+    expect(bar_off, 2u * kPairBytes);
+    bulk_g2s(offs_base, prm.off0 + at, kPairBytes, bar_off);
+    bulk_g2s(offs_base + kPairBytes, prm.off1 + at, kPairBytes, bar_off);
+  };
+  auto fetch_strip = [&](int n, int pw) {                       // g_out[n, 0..195, pw..pw+3] -> s_g, one TMA box
+    expect(bar_strip, (uint32_t)(kGWarpFloats * 4));
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            fl_smem_u32(s_g)),
+        "l"(&maps.m[2]), "r"(bar_strip), "r"(pw), "r"(n * CH)
+        : "memory");
+  };
+  auto issue = [&](int slot, int pix, float cx, float cy) {     // lane 0 only: the two input boxes of one pixel
     float* dst = inbox + slot * kInSlotFloats;
     fl_mbar_expect_tx(bars + slot, kInSlotBytes);
     float sx = cx, sy = cy;
@@ -291,32 +352,16 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       sy = __fmul_rn(sy, 0.5f);
     }
   };
-  {
-    const float c0x = __shfl_sync(0xffffffffu, cmine.x, 0), c0y = __shfl_sync(0xffffffffu, cmine.y, 0);
-    const float c1x = __shfl_sync(0xffffffffu, cmine.x, 1), c1y = __shfl_sync(0xffffffffu, cmine.y, 1);
-    if (lane == 0) {
-      issue(0, c0x, c0y);
-      issue(1, c1x, c1y);
-    }
-  }
-
-  // upstream gradients of this warp's 4 pixels: 196 rows of 16 bytes, fetched with cp.async straight into the warp's
-  // own shared-memory strip (no CTA-wide tile, no __syncthreads: a CTA no longer starts with an exposed DRAM round
-  // trip, the rows land while the first TMA boxes are in flight); clear the accumulators
-  {
-    const float* g = prm.g_out + (size_t)n * CH * P + pw;
-    // (kept rolled: unrolling the 7 LDGSTS with private address registers was measured slower, 670 vs 655 us at E = 48)
-#pragma unroll 1
-    for (int q = 0; q < (CH + 31) / 32; ++q) {
-      const int ch = q * 32 + lane;
-      if (ch < CH) {
-        const uint32_t dst = fl_smem_u32(s_g + ch * kPixPerWarp);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + (size_t)ch * P) : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int q = lane; q < kAccFloats; q += 32) acc[q] = 0.0f;
-  }
+  auto lds64 = [&](uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+  };
+  auto lds32 = [&](uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+  };
 
   const int t0 = lane, t1 = lane + 32;
   const int i0 = t0 / RD, j0 = t0 - i0 * RD;
@@ -326,45 +371,92 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
   constexpr int CENTER = R * RD + R;
   const int mi = min(lane, 8) / 3, mj = min(lane, 8) - mi * 3;
 
-  float2 a0, a1, b0, b1, u0, u1;                                // off0 / off1 / upstream g_off1_out of taps t0, t1
-  float mk, sc1;
-  auto load_offsets = [&](int k) {
-    const size_t pix = (size_t)n * P + min(pw + k, P - 1);
-    const float2* O0 = reinterpret_cast<const float2*>(prm.off0) + pix * TAPS;
-    const float2* O1 = reinterpret_cast<const float2*>(prm.off1) + pix * TAPS;
-    a0 = O0[t0]; a1 = O0[t1c]; b0 = O1[t0]; b1 = O1[t1c];
-    sc1 = prm.off1_scale != nullptr ? __ldg(prm.off1_scale + pix) : 1.0f;     // applied where the record is consumed
-    u0 = u1 = make_float2(0.0f, 0.0f);
+  // ---- prologue of the first tile
+  int tile = blockIdx.x;
+  if (tile >= prm.num_tiles) return;
+  int n, pw;
+  tile_edge(tile, n, pw);
+  if (lane == 0) {
+    fetch_small(n, pw, 0);
+    fetch_strip(n, pw);
+    fetch_pair(n, pw);
+  }
+  wait(bar_small, 0);
+  {
+    const float2 c0 = lds64(small_base + (lane & 3) * 8);
+    const float c0x = __shfl_sync(0xffffffffu, c0.x, 0), c0y = __shfl_sync(0xffffffffu, c0.y, 0);
+    const float c1x = __shfl_sync(0xffffffffu, c0.x, 1), c1y = __shfl_sync(0xffffffffu, c0.y, 1);
+    if (lane == 0) {
+      issue(0, n * P + pw, c0x, c0y);
+      issue(1, n * P + pw + 1, c1x, c1y);
+    }
+  }
+  // upstream gradient on offset[1]_out (later calls of a training clip): prefetched one pixel ahead by LDG when present
+  float2 u0 = make_float2(0.0f, 0.0f), u1 = u0;
+  auto load_upstream = [&](size_t pix) {
     if (prm.g_off1_out != nullptr) {
       const float2* U = reinterpret_cast<const float2*>(prm.g_off1_out) + pix * TAPS;
       u0 = U[t0]; u1 = U[t1c];
     }
-    mk = __ldg(prm.mask + pix);
   };
-  load_offsets(0);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
+  load_upstream((size_t)n * P + pw);
+
+#pragma unroll 1
+  for (int it = 0; tile < prm.num_tiles; ++it, tile += gridDim.x) {
+  const int par = it & 1;
+  const int ntile = tile + gridDim.x;
+  const bool has_next = ntile < prm.num_tiles;
+  int nn = 0, npw = 0;
+  if (has_next) {
+    tile_edge(ntile, nn, npw);
+    if (lane == 0) fetch_small(nn, npw, par ^ 1);
+  }
+  const uint32_t small = small_base + par * kSmallBytes;
+  wait(bar_strip, par);                                         // this tile's upstream-gradient strip
+  const float2 cmine = lds64(small + (lane & 3) * 8);           // lane q (< 4) holds pixel q's coords
 
 #pragma unroll 1
   for (int k = 0; k < kPixPerWarp; ++k) {
     const int slot = k & 1;
-    const size_t pix = (size_t)n * P + min(pw + k, P - 1);
+    const size_t pix = (size_t)n * P + pw + k;
     const float x0 = __shfl_sync(0xffffffffu, cmine.x, k), y0 = __shfl_sync(0xffffffffu, cmine.y, k);
+    if ((k & 1) == 0) wait(bar_off, k >> 1);                    // the pair's offset records (two completions per tile)
+    const uint32_t orec = offs_base + (k & 1) * (TAPS * 8);
+    const float2 a0 = lds64(orec + t0 * 8), a1 = lds64(orec + t1c * 8);
+    const float2 b0 = lds64(orec + kPairBytes + t0 * 8), b1 = lds64(orec + kPairBytes + t1c * 8);
     float2 o00 = a0, o01 = a1, o10 = b0, o11 = b1;
     if (prm.off1_scale != nullptr) {                            // offset[1]_out = off1 * cum_mask: same product, same rounding as the forward
+      const float sc1 = lds32(small + 48 + k * 4);
       o10 = make_float2(__fmul_rn(b0.x, sc1), __fmul_rn(b0.y, sc1));
       o11 = make_float2(__fmul_rn(b1.x, sc1), __fmul_rn(b1.y, sc1));
     }
     const float2 o10_raw = o10;                                 // the stored centre tap still multiplies g_m (see header)
     const float2 up0 = u0, up1 = u1;
-    const float m = mk;
+    const float m = lds32(small + 32 + k * 4);
     if (lane == CENTER) { o00 = make_float2(0.0f, 0.0f); o10 = make_float2(0.0f, 0.0f); }    // Q5
-    if (k + 1 < kPixPerWarp) load_offsets(k + 1);
+    // this pixel's eight upstream gradients (2 taps x 4 levels) leave the strip for registers now
+    const float* sg = s_g + k;
+    float ga0 = sg[t0 * kPixPerWarp], gb0 = sg[t1c * kPixPerWarp];
+    float ga1 = sg[(TAPS + t0) * kPixPerWarp], gb1 = sg[(TAPS + t1c) * kPixPerWarp];
+    const float ga2 = sg[(2 * TAPS + t0) * kPixPerWarp], gb2 = sg[(2 * TAPS + t1c) * kPixPerWarp];
+    const float ga3 = sg[(3 * TAPS + t0) * kPixPerWarp], gb3 = sg[(3 * TAPS + t1c) * kPixPerWarp];
+    __syncwarp();                                               // every lane has read its records / gradients ...
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... and those generic-proxy reads are ordered before the
+    __syncwarp();                                               //     async-proxy refills below (measured: without the fence
+    if (k == 1) {                                               //     rare pixels read the NEXT pair's records)
+      if (lane == 0) fetch_pair(n, pw + 2);                     // pixels 2, 3 of this tile
+    } else if (k == kPixPerWarp - 1 && has_next) {
+      if (lane == 0) {                                          // the next tile's first pair and its strip
+        fetch_pair(nn, npw);
+        fetch_strip(nn, npw);
+      }
+    }
+    if (k + 1 < kPixPerWarp) load_upstream(pix + 1);
+    else if (has_next) load_upstream((size_t)nn * P + npw);
 
-    fl_mbar_wait(bars + slot, (k >> 1) & 1);
+    fl_mbar_wait(bars + slot, (k >> 1) & 1);                    // 2 completions per slot and tile: the parity repeats per tile
     const float* box0 = inbox + slot * kInSlotFloats;
     const float* box1 = box0 + kBW01 * kBH01;
-    const float* sg = s_g + k;
 
     const float x1c = __fmul_rn(x0, 0.5f), y1c = __fmul_rn(y0, 0.5f);
     const float x2c = __fmul_rn(x1c, 0.5f), y2c = __fmul_rn(y1c, 0.5f);
@@ -374,8 +466,6 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
 
     // ---------------- deformable levels 0 and 1: offset gradients + scatter
     BTap ta0, tb0, ta1, tb1;                                    // kept for the global slow path after the slice write
-    float ga0 = sg[t0 * kPixPerWarp], gb0 = sg[t1c * kPixPerWarp];
-    float ga1 = sg[(TAPS + t0) * kPixPerWarp], gb1 = sg[(TAPS + t1c) * kPixPerWarp];
     float gm_part = 0.0f;
     // fixed-point scale of this pixel: 2^(22 - exponent of the largest |gradient|); warp-uniform.  Falls back to the
     // float path for non-finite or vanishing gradients.
@@ -507,7 +597,7 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
     // ---------------- zero-offset levels 2 and 3: scatter only (their offsets are detached zeros, corr.py:131-134)
     BTap ta2, tb2, ta3, tb3;
     int xb2, yb2, xb3, yb3;
-    auto uniform_bwd = [&](int l, float cx, float cy, BTap& ta, BTap& tb, int& xb, int& yb) {
+    auto uniform_bwd = [&](int l, float cx, float cy, BTap& ta, BTap& tb, int& xb, int& yb, float ga, float gb) {
       const int H2 = prm.H2[l], W2 = prm.W2[l];
       const float px = __fadd_rn(0.0f, cx), py = __fadd_rn(0.0f, cy);
       const int fx = floor_to_int(px), fy = floor_to_int(py);
@@ -519,11 +609,11 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       btap_setup<kBW23, kBH23>(tb, xb, yb, fx, fy, i1, j1, R, H2, W2);
       float* ac = acc + (l == 2 ? kOff2 : kOff3);
       // (fixed-point adds were tried here too: no gain over the conflict-free read-modify-write phases)
-      btap_scatter<kBW23, false>(ac, ta, true, sg[(l * TAPS + t0) * kPixPerWarp]);
-      btap_scatter<kBW23, false>(ac, tb, has1, sg[(l * TAPS + t1c) * kPixPerWarp]);
+      btap_scatter<kBW23, false>(ac, ta, true, ga);
+      btap_scatter<kBW23, false>(ac, tb, has1, gb);
     };
-    uniform_bwd(2, x2c, y2c, ta2, tb2, xb2, yb2);
-    uniform_bwd(3, x3c, y3c, ta3, tb3, xb3, yb3);
+    uniform_bwd(2, x2c, y2c, ta2, tb2, xb2, yb2, ga2, gb2);
+    uniform_bwd(3, x3c, y3c, ta3, tb3, xb3, yb3, ga3, gb3);
     __syncwarp();
 
     // ---------------- stream the four dense slices (zeros + box), then the rare out-of-box taps with global atomics
@@ -561,16 +651,25 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       btap_scatter_global(G1, ta1, true, ga1, prm.W2[1]);
       btap_scatter_global(G1, tb1, has1, gb1, prm.W2[1]);
       btap_scatter_global(G1, tm, lane < 9, gvk, prm.W2[1]);
-      btap_scatter_global(G2, ta2, true, sg[(2 * TAPS + t0) * kPixPerWarp], prm.W2[2]);
-      btap_scatter_global(G2, tb2, has1, sg[(2 * TAPS + t1c) * kPixPerWarp], prm.W2[2]);
-      btap_scatter_global(G3, ta3, true, sg[(3 * TAPS + t0) * kPixPerWarp], prm.W2[3]);
-      btap_scatter_global(G3, tb3, has1, sg[(3 * TAPS + t1c) * kPixPerWarp], prm.W2[3]);
+      btap_scatter_global(G2, ta2, true, ga2, prm.W2[2]);
+      btap_scatter_global(G2, tb2, has1, gb2, prm.W2[2]);
+      btap_scatter_global(G3, ta3, true, ga3, prm.W2[3]);
+      btap_scatter_global(G3, tb3, has1, gb3, prm.W2[3]);
     }
     __syncwarp();
+    // refill the ring slot: pixel k + 2 of this tile, or pixel k - 2 of the NEXT tile (prefetch across tiles)
     if (k + 2 < kPixPerWarp) {
       const float nx = __shfl_sync(0xffffffffu, cmine.x, k + 2), ny = __shfl_sync(0xffffffffu, cmine.y, k + 2);
-      if (lane == 0) issue(k + 2, nx, ny);
+      if (lane == 0) issue(slot, n * P + pw + k + 2, nx, ny);
+    } else if (has_next) {
+      if (k + 2 == kPixPerWarp) wait(bar_small + (par ^ 1) * 8, ((it + 1) >> 1) & 1);
+      const float2 cn = lds64(small_base + (par ^ 1) * kSmallBytes + (lane & 3) * 8);
+      const int q = k + 2 - kPixPerWarp;
+      const float nx = __shfl_sync(0xffffffffu, cn.x, q), ny = __shfl_sync(0xffffffffu, cn.y, q);
+      if (lane == 0) issue(slot, nn * P + npw + q, nx, ny);
     }
+  }
+  n = nn; pw = npw;
   }
   if (BULK && !ACC) {                                           // the zero buffer must outlive the engine's reads
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -651,15 +750,36 @@ static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, co
     const int rc = make_slice_map(&maps.m[l], lv[l], nslices, H >> l, W >> l, fl::kBW01, fl::kBH01);
     if (rc) return rc;
   }
-  maps.m[2] = maps.m[0];
+  {  // the upstream gradient [E*196, P] as a 2-D tensor: one box = 196 channel rows x 4 pixels (this warp's strip)
+    const int rc = make_rows_map(&maps.m[2], corr_grad, (long long)E * fl::CH, P, fl::kPixPerWarp, fl::CH);
+    if (rc) return rc;
+  }
   maps.m[3] = maps.m[0];
+  LGU_REQUIRE(((reinterpret_cast<uintptr_t>(coords) | reinterpret_cast<uintptr_t>(off0) | reinterpret_cast<uintptr_t>(off1_out) |
+                reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(corr_grad) |
+                reinterpret_cast<uintptr_t>(off1_scale)) & 15) == 0,
+              "lgu_corr_lookup_fused_backward: coords / offsets / mask / corr_grad must be 16-byte aligned");
   prm.coords = coords; prm.off0 = off0; prm.off1 = off1_out; prm.mask = mask; prm.g_out = corr_grad;
   prm.g_off1_out = off1_out_grad; prm.g_off0 = off0_grad; prm.g_off1 = off1_grad;
   prm.off1_scale = off1_scale;
   prm.P = P;
   prm.tiles_per_edge = P / fl::kTile;
-  const long long nblk = (long long)E * prm.tiles_per_edge;
-  LGU_REQUIRE(nblk < 2147483647LL, "lgu_corr_lookup_fused_backward: grid too large (%lld CTAs)", nblk);
+  const long long ntiles = (long long)E * prm.tiles_per_edge;
+  LGU_REQUIRE(ntiles < 2147483647LL, "lgu_corr_lookup_fused_backward: too many tiles (%lld)", ntiles);
+  prm.num_tiles = (int)ntiles;
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // Schedule.  Accumulate mode (footprint-only reductions): persistent, two CTAs per SM, every CTA the same number of
+  // tiles (4608 tiles -> 288 CTAs x 16) -- 431 -> 373 us at E = 48.  Dense mode (every slice streamed once, write-bound):
+  // one tile per CTA -- persistent CTAs run in lock step and write in phase (690 us against 601 us); the hardware's CTA
+  // scheduler staggers them.  LGU_BWD_TILES_PER_CTA overrides (experiments).
+  long long per_cta = accumulate ? (ntiles + 2LL * sms - 1) / (2LL * sms) : 1;
+  if (const char* gk = getenv("LGU_BWD_TILES_PER_CTA")) {
+    const long long v = atoll(gk);
+    if (v > 0) per_cta = v;
+  }
+  const long long nblk = (ntiles + per_cta - 1) / per_cta;
   // bulk zero-fill needs row bands that tile a warp (W2 / 4 divides 32 at levels 0 and 1)
   const char* nb = getenv("LGU_BWD_NOBULK");
   const bool bulk = !accumulate && (W == 64 || W == 128) && !(nb != nullptr && nb[0] != '\0' && nb[0] != '0');
