@@ -51,6 +51,16 @@ P = H * W
 QS = [P >> (2 * l) for l in range(LEVELS)]
 TAPS = (2 * R + 1) ** 2
 METRIC = "correlation edges/sec (48x64, 4 lvl, r=3, deformable+Gaussian) fwd+bwd"
+# The Gaussian head's backward reads the level gradients only inside its 9 x 9 window.  LGU_BENCH_GAUSS selects how:
+#   fused  (default) the fused lookup backward forms that window from its shared-memory accumulators and finishes the
+#          Gaussian head's gradients in the same launch (lgu_corr_lookup_fused_backward_gauss);
+#   window the fused backward emits the window as a contiguous record, a second kernel consumes it
+#          (lgu_corr_lookup_fused_backward_win + lgu_build_backward_gauss_window);
+#   levels a second kernel gathers the window from the four dense level gradients (lgu_build_backward_gauss: the form a
+#          multi-lookup training step uses).  All three give the same bits (tests/test_fused_lookup_gpu.py).
+GAUSS_MODE = os.environ.get("LGU_BENCH_GAUSS", "fused")       # fused | window | levels
+GAUSS_WINDOW = GAUSS_MODE == "window"
+GAUSS_FUSED = GAUSS_MODE == "fused"
 
 
 def algorithmic_bytes_per_edge():
@@ -64,11 +74,14 @@ def algorithmic_bytes_per_edge():
         "lookup_fwd": P * (8 + 2 * 8 * TAPS + 8 + sum(gather) + 64 + 4 * LEVELS * TAPS),
         # fused backward: coords, 2 offset records + mask, 196-ch upstream grad, level-0/1 gathers (+ mask taps),
         # dense gradient slices of all 4 levels written once, 2 offset-gradient records
+        # ... plus the Gaussian head's part: folded in ("fused": the 81-tap window of lvl0 and 5 parameter floats in, 5
+        # gradient floats out) or prepared for a second kernel ("window": the window centres in, an 81-float record out)
         "lookup_bwd": P * (8 + 2 * 8 * TAPS + 4 + 4 * LEVELS * TAPS + gather[0] + gather[1] + 64 + 4 * sum(QS)
-                           + 2 * 8 * TAPS),
-        # Gaussian-head gradients from the level gradients: 81-tap windows of lvl0 and g0, their 2x2 / 4x4 / 8x8 parents
-        # in g1..g3 (25 + 9 + 4 taps), 5 parameter floats in, 5 gradient floats out
-        "gauss_bwd": P * (2 * 81 * 4 + (25 + 9 + 4) * 4 + 40),
+                           + 2 * 8 * TAPS + (81 * 4 + 40 if GAUSS_FUSED else 8 + 81 * 4 if GAUSS_WINDOW else 0)),
+        # Gaussian-head gradients as a kernel of their own: the 81-tap window of lvl0, 5 parameter floats in, 5 gradient
+        # floats out, and EITHER the 81-float window record of the merged level-0 gradient that the fused backward emitted,
+        # OR (from the level gradients) the 81-tap window of g0 and its 2x2 / 4x4 / 8x8 parents in g1..g3 (25 + 9 + 4 taps)
+        "gauss_bwd": 0 if GAUSS_FUSED else P * (2 * 81 * 4 + 40) if GAUSS_WINDOW else P * (2 * 81 * 4 + (25 + 9 + 4) * 4 + 40),
     }
 
 
@@ -205,11 +218,19 @@ class Workload:
         mark("lookup_fwd")
         # ---- its backward (what autograd runs for corr.py:88-109): one launch, dense gradients of all 4 levels; the
         # post-mask offsets offset[1] * cum_mask are formed in registers, as in the forward
-        grads = ops.corr_lookup_fused_backward(pyr, d["coords"], d["off0"], d["off1"], mask, d["corr_grad"],
-                                               cum_mask=self.cum)
-        mark("lookup_bwd")
-        gm, gc, gd = ops.build_backward_gauss(d["means"], d["covs"], d["den"], pyr[0], list(grads[:4]), GR)
-        mark("gauss_bwd")
+        # ---- ... and the Gaussian-head gradients of the build (gaussianMask_cuda.py:77-86 backward through corr.py:83-86)
+        if GAUSS_FUSED:
+            grads = ops.corr_lookup_fused_backward(pyr, d["coords"], d["off0"], d["off1"], mask, d["corr_grad"],
+                                                   cum_mask=self.cum, gauss_head=(d["means"], d["covs"], d["den"]))
+            gm, gc, gd = grads[6:9]
+            mark("lookup_bwd")
+        else:
+            grads = ops.corr_lookup_fused_backward(pyr, d["coords"], d["off0"], d["off1"], mask, d["corr_grad"],
+                                                   cum_mask=self.cum, gauss_window_means=d["means"] if GAUSS_WINDOW else None)
+            mark("lookup_bwd")
+            gm, gc, gd = ops.build_backward_gauss(d["means"], d["covs"], d["den"], pyr[0], list(grads[:4]), GR,
+                                                  window=grads[6] if GAUSS_WINDOW else None)
+            mark("gauss_bwd")
         if self.launches_per_step is None:
             self.launches_per_step = self.lib.LAUNCHES - n0
         return dict(corr=corr, offset_grad0=grads[4], offset_grad1=grads[5], means_grad=gm, covs_grad=gc, den_grad=gd,
@@ -734,8 +755,13 @@ def main():
     config = {"workload": "frontend_w20_e48" if (a.edges, a.frames) == (48, 20) else f"frontend_w{a.frames}_e{a.edges}",
               "edges_per_gpu": a.edges, "keyframes": a.frames, "fmap": [C, H, W], "levels": LEVELS, "radius": R,
               "gauss_radius": GR, "build_precision": "fp16 inputs (exact products), fp32 accumulate",
-              "step": "pack + build (tcgen05) + fused lookup + fused lookup backward (dense level gradients) + Gaussian-head "
-                      "gradients from the level gradients (SURVEY 8d composite)",
+              "step": "pack + build (tcgen05) + fused lookup + fused lookup backward (dense level gradients"
+                      + (" AND the Gaussian-head gradients, formed in the same launch from the shared-memory accumulators)"
+                         if GAUSS_FUSED else
+                         " + the Gaussian head's 9x9 window record of the merged level-0 gradient) + Gaussian-head gradients "
+                         "from that record" if GAUSS_WINDOW else ") + Gaussian-head gradients from the level gradients")
+                      + " (SURVEY 8d composite)",
+              "gauss_backward": GAUSS_MODE,
               "l2_policy": "working set per step (2.4 GB pyramid + 2.4 GB grads at E=48) >> 126 MB L2; no explicit flush",
               "parallelism": "single GPU (the frontend window stays on one GPU)"}
 
@@ -823,7 +849,7 @@ def main():
     alg = algorithmic_bytes_per_edge()
     table = {}
     for k, ms in per_op_ms.items():
-        if k in alg:
+        if k in alg and alg[k] > 0:
             gbs = alg[k] * a.edges / (ms * 1e-3) / 1e9
             table[k] = {"ms": round(ms, 4), "alg_MB_per_edge": round(alg[k] / 1e6, 3), "GBps": round(gbs, 1),
                         "frac": round(gbs / peak, 4)}

@@ -259,6 +259,40 @@ LGU_API int lgu_corr_lookup_fused_backward_cum(const float* lvl0, const float* l
                                    float* off0_grad, float* off1_grad,
                                    int E, int H, int W, int num_levels, int radius, int accumulate, void* stream);
 
+/* lgu_corr_lookup_fused_backward_cum (dense form) that ALSO emits the window record the Gaussian head's backward needs:
+ *   gwin[e,p, wy*9 + wx] = g0[q] + g1[q/2]/4 + g2[q/4]/16 + g3[q/8]/64   at q = (floor(my) - 4 + wy, floor(mx) - 4 + wx),
+ *                          0 outside the target grid                     (mx, my) = win_means[e,p]
+ * i.e. avg_pool2d^T (corr.py:83-86) of this call's level gradients, evaluated only inside the 9 x 9 window of
+ * gaussianMask (gaussianMask_cuda.py:77-86), formed from the kernel's shared-memory accumulators before the dense slices
+ * are streamed out.  win_means [E,H,W,2] (8-byte aligned), gwin [E,H,W,81].  Everything else as _cum with accumulate = 0. */
+LGU_API int lgu_corr_lookup_fused_backward_win(const float* lvl0, const float* lvl1, const float* coords,
+                                   const float* off0, const float* off1, const float* cum_mask, const float* mask,
+                                   const float* corr_grad, const float* off1_out_grad, const float* win_means,
+                                   float* gv0, float* gv1, float* gv2, float* gv3,
+                                   float* off0_grad, float* off1_grad, float* gwin,
+                                   int E, int H, int W, int num_levels, int radius, void* stream);
+
+/* The same dense backward with the Gaussian head's backward of the build FOLDED IN: the merged window gradient never
+ * leaves the SM -- the kernel fetches the 81 level-0 values of the window and evaluates lgu_build_backward_gauss's
+ * arithmetic (shared code, same bits) on the spot.  Returns, besides the level and offset gradients,
+ *   means_grad, covs_grad [E,H,W,2], den_grad [E,H,W] = lgu_build_backward_gauss(means, covs, den, lvl0, gv0..gv3)
+ * of THIS call's level gradients (one lookup per pyramid; a training step with several lookups accumulates level
+ * gradients and calls lgu_build_backward_gauss once).  gauss_radius must be 4 (gaussianMask_cuda.py:77). */
+LGU_API int lgu_corr_lookup_fused_backward_gauss(const float* lvl0, const float* lvl1, const float* coords,
+                                   const float* off0, const float* off1, const float* cum_mask, const float* mask,
+                                   const float* corr_grad, const float* off1_out_grad,
+                                   const float* means, const float* covs, const float* den,
+                                   float* gv0, float* gv1, float* gv2, float* gv3,
+                                   float* off0_grad, float* off1_grad,
+                                   float* means_grad, float* covs_grad, float* den_grad,
+                                   int E, int H, int W, int num_levels, int radius, int gauss_radius, void* stream);
+
+/* lgu_build_backward_gauss (below) from that window record instead of the four level gradients: same sums, same bits,
+ * one contiguous 324-byte read per pixel instead of four strided window gathers.  Radius 4 only. */
+LGU_API int lgu_build_backward_gauss_window(const float* means, const float* covs, const float* den, const float* lvl0,
+                                   const float* gwin, float* means_grad, float* covs_grad, float* den_grad,
+                                   int E, int H, int W, void* stream);
+
 /* Gaussian-head part of the backward of lgu_build_pyramid (what autograd runs for gaussianMask_cuda.py:84-86
  * followed by 3 x avg_pool2d, corr.py:83-86), straight from the four LEVEL gradients, without a dense pass:
  *   g(q)      = g0[q] + g1[q/2]/4 + g2[q/4]/16 + g3[q/8]/64          (avg_pool2d^T, evaluated at the window taps only)

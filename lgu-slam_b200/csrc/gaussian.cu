@@ -11,6 +11,7 @@
 // Arithmetic follows the reference's SASS: IEEE divides, s = fma(t2, dy, t1*dx), f = -0.5*s,
 // full-precision expf, ((V*3)*e); fp64 only for the covariance-gradient factor (:120,122).
 #include "common.cuh"
+#include "gauss_window.cuh"
 
 namespace lgu {
 
@@ -264,13 +265,18 @@ build_bwd_gauss_kernel(const float* __restrict__ means, const float* __restrict_
 // ~40 resident warps per SM: measured 86 us at E = 48 whatever the instruction count), so a warp takes NP = 4
 // consecutive pixels per trip: lanes 0..3 fetch the four parameter records together and the 4 x 3 gather passes are all
 // in flight before the first tap is consumed.
-template <bool FUSED, int NP>
-__global__ void __launch_bounds__(kGaWarps * 32)
+// MODE 0: drop-in gaussianMask backward (g0 = upstream gradient of the masked volume, vol = raw volume);
+// MODE 1: from the four level gradients (FUSED above); MODE 2: as 1, but g0 is the [npix, 81] WINDOW RECORD of the merged
+// gradient that lgu_corr_lookup_fused_backward_win emits -- one contiguous 324-byte read per pixel instead of four strided
+// window gathers (a 64-byte DRAM granule per 36-byte row: 513 MB per launch at E = 48 against 124 MB of algorithmic bytes).
+template <int MODE, int NP, int MINB = 2>
+__global__ void __launch_bounds__(kGaWarps * 32, MINB)
 gaussian_bwd_sep_kernel(const float* __restrict__ means, const float* __restrict__ covs, const float* __restrict__ den,
                         const float* __restrict__ vol, const float* __restrict__ g0, const float* __restrict__ g1,
                         const float* __restrict__ g2, const float* __restrict__ g3, float* __restrict__ means_grad,
                         float* __restrict__ covs_grad, float* __restrict__ den_grad, long long npix, int H2, int W2) {
   constexpr int r = 4, rd = 9, taps = 81, kPasses = 3;
+  constexpr bool FUSED = MODE != 0;
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -283,8 +289,6 @@ gaussian_bwd_sep_kernel(const float* __restrict__ means, const float* __restrict
     tj[ps] = t / rd;
     ti[ps] = t - tj[ps] * rd;
   }
-  const bool is_row = lane >= rd;                               // lanes 9..17 (18..31 compute unused duplicates)
-  const int kidx = (lane < rd ? lane : lane - rd) % rd;
   for (long long pb = wid * NP; pb < npix; pb += nwarps * NP) {
     // ---- parameters of the NP pixels: lane q loads pixel pb + q (the tail repeats the last pixel; its store is skipped)
     const long long pmine = min(pb + (lane < NP ? lane : 0), npix - 1);
@@ -312,8 +316,10 @@ gaussian_bwd_sep_kernel(const float* __restrict__ means, const float* __restrict
         const int xc = min(max(tap_coord(x0[q], 0, ti[ps]), 0), W2 - 1), yc = min(max(tap_coord(y0[q], 0, tj[ps]), 0), H2 - 1);
         const size_t at = (size_t)pix * Q + (size_t)yc * W2 + xc;
         v[q][ps] = __ldg(vol + at);
-        float gg = g0 != nullptr ? __ldg(g0 + at) : 0.0f;
-        if (FUSED) {                                            // avg_pool2d^T, level by level
+        float gg;
+        if (MODE == 2) gg = __ldg(g0 + (size_t)pix * taps + min(ps * 32 + lane, taps - 1));
+        else gg = g0 != nullptr ? __ldg(g0 + at) : 0.0f;
+        if (MODE == 1) {                                        // avg_pool2d^T, level by level
           if (g1 != nullptr) gg = __fadd_rn(gg, __fmul_rn(__ldg(g1 + (size_t)pix * (Q >> 2) + (yc >> 1) * (W2 >> 1) + (xc >> 1)), 0.25f));
           if (g2 != nullptr) gg = __fadd_rn(gg, __fmul_rn(__ldg(g2 + (size_t)pix * (Q >> 4) + (yc >> 2) * (W2 >> 2) + (xc >> 2)), 0.0625f));
           if (g3 != nullptr) gg = __fadd_rn(gg, __fmul_rn(__ldg(g3 + (size_t)pix * (Q >> 6) + (yc >> 3) * (W2 >> 3) + (xc >> 3)), 0.015625f));
@@ -323,62 +329,10 @@ gaussian_bwd_sep_kernel(const float* __restrict__ means, const float* __restrict
     }
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-      // ---- this lane's record: column kidx (lanes 0-8) or row kidx (lanes 9-17)
-      const float mean_a = is_row ? m[q].y : m[q].x, cov_a = is_row ? c[q].y : c[q].x;
-      const int coord = tap_coord(is_row ? y0[q] : x0[q], 0, kidx);
-      const bool inb = (unsigned)coord < (unsigned)(is_row ? H2 : W2);
-      const float rc = __fdiv_rn(1.0f, cov_a);
-      const float dd = __fsub_rn((float)coord, mean_a);
-      const float ev = expf(__fmul_rn(__fmul_rn(__fmul_rn(dd, rc), dd), -0.5f));
-      const float recE = inb ? ev : 0.0f;                                                      // e
-      const float recM = inb ? __fmul_rn(__fmul_rn(dd, ev), rc) : 0.0f;                        // e dd / cov
-      // 0.5 e dd^2 / cov^2 in fp64 like the reference (:120,122), with the correctly rounded fp32 reciprocal of cov^2
-      const float recC = inb ? (float)(((((double)ev * 0.5) * (double)dd) * (double)dd) * (double)__fmul_rn(rc, rc)) : 0.0f;
-      float k3 = 0.0f, rdn = 1.0f;
-      if (FUSED) {
-        rdn = __fdiv_rn(1.0f, dn[q]);
-        k3 = __fmul_rn(3.0f, rdn);                              // lvl0 = V (1 + 3 ex ey / den) inside the window
-      }
-      float gm0 = 0.0f, gm1 = 0.0f, gc0 = 0.0f, gc1 = 0.0f, gd = 0.0f;
-#pragma unroll
-      for (int ps = 0; ps < kPasses; ++ps) {
-        const float cE = __shfl_sync(0xffffffffu, recE, ti[ps]), cM = __shfl_sync(0xffffffffu, recM, ti[ps]);
-        const float cC = __shfl_sync(0xffffffffu, recC, ti[ps]);
-        const float rE = __shfl_sync(0xffffffffu, recE, rd + tj[ps]), rM = __shfl_sync(0xffffffffu, recM, rd + tj[ps]);
-        const float rC = __shfl_sync(0xffffffffu, recC, rd + tj[ps]);
-        const bool live = ps * 32 + lane < taps;
-        float vraw = v[q][ps];
-        if (FUSED) {
-          vraw = __fdividef(v[q][ps], __fmaf_rn(__fmul_rn(k3, cE), rE, 1.0f));   // the raw volume (== v outside the window)
-          if (live) gd = __fmaf_rn(g[q][ps], __fsub_rn(v[q][ps], vraw), gd);
-        }
-        const float w = live ? __fmul_rn(__fmul_rn(vraw, 3.0f), g[q][ps]) : 0.0f;
-        const float wa = __fmul_rn(w, rE), wb = __fmul_rn(w, cE);
-        gm0 = __fmaf_rn(wa, cM, gm0);
-        gc0 = __fmaf_rn(wa, cC, gc0);
-        gm1 = __fmaf_rn(wb, rM, gm1);
-        gc1 = __fmaf_rn(wb, rC, gc1);
-      }
-      // ---- reduce (gm0, gm1, gc0, gc1) over the warp with a value-splitting butterfly: 2 + 1 + 3 shuffles
-      float t;
-      {
-        const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
-        const float s0 = hi16 ? gm0 : gc0, s1 = hi16 ? gm1 : gc1;              // what this lane sends
-        const float k0 = hi16 ? gc0 : gm0, k1 = hi16 ? gc1 : gm1;              // what it keeps
-        const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16), a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
-        t = (hi8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi8 ? a0 : a1, 8);
-        t += __shfl_xor_sync(0xffffffffu, t, 4);
-        t += __shfl_xor_sync(0xffffffffu, t, 2);
-        t += __shfl_xor_sync(0xffffffffu, t, 1);                               // lane 0: gm0, 8: gm1, 16: gc0, 24: gc1
-      }
-      if (FUSED) gd = warp_sum(gd);
-      const float r1 = __shfl_sync(0xffffffffu, t, 8), r2 = __shfl_sync(0xffffffffu, t, 16), r3 = __shfl_sync(0xffffffffu, t, 24);
+      float o0, o1, o2, o3, od;
+      gauss_window_grads<FUSED>(v[q], g[q], m[q], c[q], dn[q], x0[q], y0[q], H2, W2, lane, o0, o1, o2, o3, od);
       if (lane == 0 && pb + q < npix) {
-        float o0 = t, o1 = r1, o2 = r2, o3 = r3;
-        if (FUSED) {                                            // g / den enters every parameter gradient linearly
-          o0 = __fmul_rn(o0, rdn); o1 = __fmul_rn(o1, rdn); o2 = __fmul_rn(o2, rdn); o3 = __fmul_rn(o3, rdn);
-          den_grad[pb + q] = -__fmul_rn(gd, rdn);
-        }
+        if (FUSED) den_grad[pb + q] = od;
         reinterpret_cast<float2*>(means_grad)[pb + q] = make_float2(o0, o1);
         reinterpret_cast<float2*>(covs_grad)[pb + q] = make_float2(o2, o3);
       }
@@ -427,7 +381,7 @@ extern "C" int lgu_gaussian_mask_backward(const float* means, const float* covs,
   const long long npix = (long long)E * H1 * W1;
   if (radius == 4) {                                             // the reference's only radius: lane = (pixel, window row)
     const unsigned grid3 = lgu::grid_for_warps((npix + 3) / 4, lgu::kGaWarps, 8);
-    lgu::gaussian_bwd_sep_kernel<false, 4><<<grid3, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
+    lgu::gaussian_bwd_sep_kernel<0, 4><<<grid3, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
         means, covs, nullptr, volume, volume1_grad, nullptr, nullptr, nullptr, means_grad, covs_grad, nullptr, npix, H2, W2);
     return lgu::check_launch("lgu_gaussian_mask_backward");
   }
@@ -450,7 +404,7 @@ extern "C" int lgu_build_backward_gauss(const float* means, const float* covs, c
   const long long npix = (long long)E * H * W;
   if (radius == 4) {
     const unsigned grid3 = lgu::grid_for_warps((npix + 3) / 4, lgu::kGaWarps, 8);
-    lgu::gaussian_bwd_sep_kernel<true, 4><<<grid3, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
+    lgu::gaussian_bwd_sep_kernel<1, 4><<<grid3, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
         means, covs, den, lvl0, g0, g1, g2, g3, means_grad, covs_grad, den_grad, npix, H, W);
     return lgu::check_launch("lgu_build_backward_gauss");
   }
@@ -458,4 +412,23 @@ extern "C" int lgu_build_backward_gauss(const float* means, const float* covs, c
   lgu::build_bwd_gauss_kernel<<<grid, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
       means, covs, den, lvl0, g0, g1, g2, g3, means_grad, covs_grad, den_grad, npix, H, W, radius);
   return lgu::check_launch("lgu_build_backward_gauss");
+}
+
+// Gaussian-head gradients from the window record of the merged level-0 gradient (lgu_corr_lookup_fused_backward_win):
+// the same sums as lgu_build_backward_gauss, bit for bit, with one contiguous 324-byte read per pixel where the
+// from-levels form gathers four strided windows.  Radius 4 (the reference's only one, gaussianMask_cuda.py:77).
+extern "C" int lgu_build_backward_gauss_window(const float* means, const float* covs, const float* den, const float* lvl0,
+                                               const float* gwin, float* means_grad, float* covs_grad, float* den_grad,
+                                               int E, int H, int W, void* stream) {
+  if (E == 0) return LGU_OK;
+  LGU_REQUIRE(means && covs && den && lvl0 && gwin && means_grad && covs_grad && den_grad,
+              "lgu_build_backward_gauss_window: null pointer");
+  LGU_REQUIRE(E >= 0 && H > 0 && W > 0, "lgu_build_backward_gauss_window: bad sizes E=%d H=%d W=%d", E, H, W);
+  LGU_REQUIRE((long long)H * W < (1LL << 30), "lgu_build_backward_gauss_window: H*W too large");
+  const long long npix = (long long)E * H * W;
+  // (occupancy does not matter here: 2 / 3 / 4 / 5 CTAs per SM with 4 or 2 pixels per trip all ran within 7 % of each other)
+  const unsigned grid3 = lgu::grid_for_warps((npix + 3) / 4, lgu::kGaWarps, 8);
+  lgu::gaussian_bwd_sep_kernel<2, 4><<<grid3, lgu::kGaWarps * 32, 0, (cudaStream_t)stream>>>(
+      means, covs, den, lvl0, gwin, nullptr, nullptr, nullptr, means_grad, covs_grad, den_grad, npix, H, W);
+  return lgu::check_launch("lgu_build_backward_gauss_window");
 }

@@ -27,6 +27,7 @@
 //   gV_1     += corr_index_backward(g_v)                      (corrSample_kernel.cu:84-136)
 #include <cstdlib>
 #include "fused_common.cuh"
+#include "gauss_window.cuh"
 
 namespace lgu {
 
@@ -69,6 +70,13 @@ struct FusedLookupBwdParams {
   float* gv[4];              // dense volume gradients [E,P,H2,W2]
   float* g_off0;             // [E,P,49,2]
   float* g_off1;             // [E,P,49,2]  gradient of offset[1]_in
+  const float* win_means;    // [E,P,2] or null: centres of the Gaussian head's 9 x 9 windows (gaussianMask_cuda.py:77-86)
+  float* gwin;               // [E,P,81] or null: the level-0 gradient INCLUDING the pooled levels' share, inside that window
+  const float* win_covs;     // GAUSS kernels: [E,P,2], [E,P] -- the Gaussian head's covariances and denominators, and the
+  const float* win_den;      //   gradients of (means, covs, den) this call contributes through the build's Gaussian residual
+  float* g_means;            // [E,P,2]
+  float* g_covs;             // [E,P,2]
+  float* g_den;              // [E,P]
   int P, tiles_per_edge, num_tiles;
   int H2[4], W2[4];
 };
@@ -255,6 +263,53 @@ __device__ __forceinline__ void add_box(float* __restrict__ G, float* acc, int x
   }
 }
 
+// The Gaussian head's backward (lgu_build_backward_gauss) needs the gradient of the level-0 volume only inside the
+// 9 x 9 window around each pixel's mean -- with avg_pool2d's transpose folded in: g0 + g1/4 + g2/16 + g3/64 of the
+// cells above the tap.  Reading those four windows back from the dense gradients costs a 64-byte DRAM granule per
+// 36-byte window row (ncu: 513 MB per launch for 124 MB of algorithmic bytes); here the four boxes are still in shared
+// memory, so the merged window leaves as one contiguous 324-byte record per pixel.  Same order of additions as the
+// from-levels kernel (gaussian.cu), so both give the same bits.  GLOBAL: rare pixels with out-of-box taps re-read the
+// finished slices instead (their global atomics are not in the boxes).
+constexpr int kWinR = 4, kWinD = 2 * kWinR + 1, kWinTaps = kWinD * kWinD;
+template <bool GLOBAL>
+__device__ __forceinline__ void emit_window(float* __restrict__ gw, float (&out)[3], int wx0, int wy0, const float* acc,
+                                            const int* xb, const int* yb, float* const* G, const int* H2, const int* W2,
+                                            int lane) {
+  using namespace fl;
+  static_assert((kWinTaps + 31) / 32 == 3, "three passes");
+#pragma unroll
+  for (int ps = 0; ps < 3; ++ps) {
+    const int t = ps * 32 + lane;
+    out[ps] = 0.0f;
+    if (t < kWinTaps) {
+      const int wy = t / kWinD, wx = t - wy * kWinD;
+      const int x = tap_coord(wx0, 0, wx), y = tap_coord(wy0, 0, wy);
+      float gg = 0.0f;
+      if ((unsigned)x < (unsigned)W2[0] && (unsigned)y < (unsigned)H2[0]) {
+        float part[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int xl = x >> l, yl = y >> l;
+          if (GLOBAL) {
+            part[l] = ((unsigned)xl < (unsigned)W2[l] && (unsigned)yl < (unsigned)H2[l]) ? __ldcg(G[l] + (size_t)yl * W2[l] + xl) : 0.0f;
+          } else {
+            const int BW = l < 2 ? kBW01 : kBW23, BH = l < 2 ? kBH01 : kBH23;
+            const int off = l == 0 ? kOff0 : l == 1 ? kOff1 : l == 2 ? kOff2 : kOff3;
+            const unsigned rx = (unsigned)(xl - xb[l]), ry = (unsigned)(yl - yb[l]);
+            part[l] = (rx < (unsigned)BW && ry < (unsigned)BH) ? acc[off + ry * BW + rx] : 0.0f;
+          }
+        }
+        gg = part[0];
+        gg = __fadd_rn(gg, __fmul_rn(part[1], 0.25f));
+        gg = __fadd_rn(gg, __fmul_rn(part[2], 0.0625f));
+        gg = __fadd_rn(gg, __fmul_rn(part[3], 0.015625f));
+      }
+      out[ps] = gg;
+      if (gw != nullptr) __stcs(gw + t, gg);
+    }
+  }
+}
+
 // Round 2: PERSISTENT CTAs (two per SM) walk the tiles, and nothing a pixel needs is fetched by LDG inside the pixel loop
 // (ncu's source view of the per-tile version: 28 % of all samples were long-scoreboard stalls -- the first use of the
 // prefetched offset records, the cp.async loop of the upstream-gradient strip, the coords load of every CTA's prologue --
@@ -263,7 +318,11 @@ __device__ __forceinline__ void add_box(float* __restrict__ G, float* acc, int x
 // as the second pixel of a pair has read its records), coords / mask / cumulative-mask scale arrive as 64 bytes per tile
 // one tile ahead, and the box ring keeps prefetching across tile boundaries.  The strip of the next tile is requested as
 // soon as the last pixel of the current one has moved its eight gradient values to registers.
-template <bool ACC, bool BULK, bool FXP>
+// GAUSS (dense mode): the Gaussian head's backward of the build (gaussianMask_cuda.py:77-86 through corr.py:83-86) is
+// finished HERE: the merged window gradient is in registers (emit_window), the 81 window values of level 0 are fetched at
+// the top of the pixel, and gauss_window_grads -- the arithmetic of lgu_build_backward_gauss, shared code -- gives the
+// pixel's (means, covs, den) gradients.  The separate kernel was bound by its window gathers from the dense gradients.
+template <bool ACC, bool BULK, bool FXP, bool GAUSS = false>
 __global__ void __launch_bounds__(fl::kThreads, 2)
 lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupBwdParams prm) {
   using namespace flb;
@@ -414,12 +473,36 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
   const uint32_t small = small_base + par * kSmallBytes;
   wait(bar_strip, par);                                         // this tile's upstream-gradient strip
   const float2 cmine = lds64(small + (lane & 3) * 8);           // lane q (< 4) holds pixel q's coords
+  float2 wmean = make_float2(0.0f, 0.0f), wcov = make_float2(1.0f, 1.0f);   // lane q (< 4): pixel q's Gaussian window
+  float wden = 1.0f;
+  const bool want_win = !ACC && (GAUSS || prm.gwin != nullptr);
+  if (want_win) wmean = __ldg(reinterpret_cast<const float2*>(prm.win_means) + (size_t)n * P + pw + (lane & 3));
+  if (GAUSS) {
+    wcov = __ldg(reinterpret_cast<const float2*>(prm.win_covs) + (size_t)n * P + pw + (lane & 3));
+    wden = __ldg(prm.win_den + (size_t)n * P + pw + (lane & 3));
+  }
 
 #pragma unroll 1
   for (int k = 0; k < kPixPerWarp; ++k) {
     const int slot = k & 1;
     const size_t pix = (size_t)n * P + pw + k;
     const float x0 = __shfl_sync(0xffffffffu, cmine.x, k), y0 = __shfl_sync(0xffffffffu, cmine.y, k);
+    int wx0 = 0, wy0 = 0;                                       // origin of the Gaussian head's 9 x 9 window
+    float wv[3] = {0.0f, 0.0f, 0.0f}, wg[3] = {0.0f, 0.0f, 0.0f};
+    if (want_win) {
+      wx0 = tap_coord(floor_to_int(__shfl_sync(0xffffffffu, wmean.x, k)), kWinR, 0);
+      wy0 = tap_coord(floor_to_int(__shfl_sync(0xffffffffu, wmean.y, k)), kWinR, 0);
+    }
+    if (GAUSS) {                                                // level-0 values inside the window (clamped addresses: the
+      const float* V0 = prm.lvl[0] + pix * (size_t)(prm.H2[0] * prm.W2[0]);   // records zero what the bounds test drops),
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {                          // consumed after the slices have left
+        const int t = min(ps * 32 + lane, kWinTaps - 1);
+        const int tj = t / kWinD, ti = t - tj * kWinD;
+        const int xc = min(max(tap_coord(wx0, 0, ti), 0), prm.W2[0] - 1), yc = min(max(tap_coord(wy0, 0, tj), 0), prm.H2[0] - 1);
+        wv[ps] = __ldg(V0 + (size_t)yc * prm.W2[0] + xc);
+      }
+    }
     if ((k & 1) == 0) wait(bar_off, k >> 1);                    // the pair's offset records (two completions per tile)
     const uint32_t orec = offs_base + (k & 1) * (TAPS * 8);
     const float2 a0 = lds64(orec + t0 * 8), a1 = lds64(orec + t1c * 8);
@@ -615,6 +698,12 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
     uniform_bwd(2, x2c, y2c, ta2, tb2, xb2, yb2, ga2, gb2);
     uniform_bwd(3, x3c, y3c, ta3, tb3, xb3, yb3, ga3, gb3);
     __syncwarp();
+    if (want_win) {                                             // the Gaussian head's window of the merged level-0 gradient
+      const int xbs[4] = {xb0, xb1, xb2, xb3}, ybs[4] = {yb0, yb1, yb2, yb3};
+      emit_window<false>(prm.gwin != nullptr ? prm.gwin + pix * kWinTaps : nullptr, wg, wx0, wy0, acc, xbs, ybs, nullptr,
+                         prm.H2, prm.W2, lane);
+      __syncwarp();                                             // the boxes are read before the slice pass re-zeroes them
+    }
 
     // ---------------- stream the four dense slices (zeros + box), then the rare out-of-box taps with global atomics
     float* G2 = prm.gv[2] + pix * (size_t)(prm.H2[2] * prm.W2[2]);
@@ -655,6 +744,25 @@ lookup_fused_bwd_kernel(const __grid_constant__ FusedMaps maps, const FusedLooku
       btap_scatter_global(G2, tb2, has1, gb2, prm.W2[2]);
       btap_scatter_global(G3, ta3, true, ga3, prm.W2[3]);
       btap_scatter_global(G3, tb3, has1, gb3, prm.W2[3]);
+      if (want_win) {                                           // out-of-box taps are not in the boxes: window from the slices
+        __threadfence();
+        __syncwarp();
+        float* const Gs[4] = {G0, G1, G2, G3};
+        emit_window<true>(prm.gwin != nullptr ? prm.gwin + pix * kWinTaps : nullptr, wg, wx0, wy0, nullptr, nullptr, nullptr,
+                          Gs, prm.H2, prm.W2, lane);
+      }
+    }
+    if (GAUSS) {
+      const float2 gm_ = make_float2(__shfl_sync(0xffffffffu, wmean.x, k), __shfl_sync(0xffffffffu, wmean.y, k));
+      const float2 gc_ = make_float2(__shfl_sync(0xffffffffu, wcov.x, k), __shfl_sync(0xffffffffu, wcov.y, k));
+      const float gdn = __shfl_sync(0xffffffffu, wden, k);
+      float o0, o1, o2, o3, od;
+      gauss_window_grads<true>(wv, wg, gm_, gc_, gdn, wx0, wy0, prm.H2[0], prm.W2[0], lane, o0, o1, o2, o3, od);
+      if (lane == 0) {
+        reinterpret_cast<float2*>(prm.g_means)[pix] = make_float2(o0, o1);
+        reinterpret_cast<float2*>(prm.g_covs)[pix] = make_float2(o2, o3);
+        prm.g_den[pix] = od;
+      }
     }
     __syncwarp();
     // refill the ring slot: pixel k + 2 of this tile, or pixel k - 2 of the NEXT tile (prefetch across tiles)
@@ -684,7 +792,10 @@ static int launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, const f
                                    const float* off1_out, const float* mask, const float* corr_grad,
                                    const float* off1_out_grad, float* gv0, float* gv1, float* gv2, float* gv3,
                                    float* off0_grad, float* off1_grad, int E, int H, int W, int num_levels, int radius,
-                                   bool accumulate, const float* off1_scale, void* stream);
+                                   bool accumulate, const float* off1_scale, void* stream,
+                                   const float* win_means = nullptr, float* gwin = nullptr, const float* win_covs = nullptr,
+                                   const float* win_den = nullptr, float* g_means = nullptr, float* g_covs = nullptr,
+                                   float* g_den = nullptr);
 }
 extern "C" int lgu_corr_lookup_fused_backward_cum(const float* lvl0, const float* lvl1, const float* coords,
                                                   const float* off0, const float* off1, const float* cum_mask,
@@ -695,6 +806,45 @@ extern "C" int lgu_corr_lookup_fused_backward_cum(const float* lvl0, const float
   LGU_REQUIRE(E == 0 || cum_mask != nullptr, "lgu_corr_lookup_fused_backward_cum: null cumulative-mask buffer");
   return lgu::launch_lookup_fused_bwd(lvl0, lvl1, coords, off0, off1, mask, corr_grad, off1_out_grad, gv0, gv1, gv2, gv3,
                                       off0_grad, off1_grad, E, H, W, num_levels, radius, accumulate != 0, cum_mask, stream);
+}
+// Dense cumulative-mask form that ALSO emits, per source pixel, the 9 x 9 window (centre floor(win_means), x fastest) of
+// the merged level-0 gradient g0 + g1/4 + g2/16 + g3/64 -- the only part of the level gradients the Gaussian head's
+// backward reads (lgu_build_backward_gauss_window).
+extern "C" int lgu_corr_lookup_fused_backward_win(const float* lvl0, const float* lvl1, const float* coords,
+                                                  const float* off0, const float* off1, const float* cum_mask,
+                                                  const float* mask, const float* corr_grad, const float* off1_out_grad,
+                                                  const float* win_means, float* gv0, float* gv1, float* gv2, float* gv3,
+                                                  float* off0_grad, float* off1_grad, float* gwin, int E, int H, int W,
+                                                  int num_levels, int radius, void* stream) {
+  LGU_REQUIRE(E == 0 || (win_means != nullptr && gwin != nullptr), "lgu_corr_lookup_fused_backward_win: null window buffers");
+  LGU_REQUIRE((reinterpret_cast<uintptr_t>(win_means) & 7) == 0, "lgu_corr_lookup_fused_backward_win: win_means not 8-byte aligned");
+  return lgu::launch_lookup_fused_bwd(lvl0, lvl1, coords, off0, off1, mask, corr_grad, off1_out_grad, gv0, gv1, gv2, gv3,
+                                      off0_grad, off1_grad, E, H, W, num_levels, radius, false, cum_mask, stream, win_means,
+                                      gwin);
+}
+// Dense cumulative-mask form with the Gaussian head's backward of the build folded in (GAUSS kernels): besides the level
+// and offset gradients, the launch returns what lgu_build_backward_gauss would compute from THIS call's level gradients.
+extern "C" int lgu_corr_lookup_fused_backward_gauss(const float* lvl0, const float* lvl1, const float* coords,
+                                                    const float* off0, const float* off1, const float* cum_mask,
+                                                    const float* mask, const float* corr_grad, const float* off1_out_grad,
+                                                    const float* means, const float* covs, const float* den, float* gv0,
+                                                    float* gv1, float* gv2, float* gv3, float* off0_grad, float* off1_grad,
+                                                    float* means_grad, float* covs_grad, float* den_grad, int E, int H,
+                                                    int W, int num_levels, int radius, int gauss_radius, void* stream) {
+  LGU_REQUIRE(E == 0 || (means && covs && den && means_grad && covs_grad && den_grad),
+              "lgu_corr_lookup_fused_backward_gauss: null Gaussian-head buffers");
+  if (gauss_radius != 4) {
+    lgu::set_error("lgu_corr_lookup_fused_backward_gauss: only gauss_radius=4 is implemented (got %d); use "
+                   "lgu_build_backward_gauss", gauss_radius);
+    return LGU_ERR_UNSUPPORTED;
+  }
+  LGU_REQUIRE(((reinterpret_cast<uintptr_t>(means) | reinterpret_cast<uintptr_t>(covs) | reinterpret_cast<uintptr_t>(means_grad) |
+                reinterpret_cast<uintptr_t>(covs_grad)) & 7) == 0 && ((reinterpret_cast<uintptr_t>(den) | reinterpret_cast<uintptr_t>(den_grad)) & 3) == 0,
+              "lgu_corr_lookup_fused_backward_gauss: means / covs must be 8-byte aligned");
+  LGU_REQUIRE(E == 0 || cum_mask != nullptr, "lgu_corr_lookup_fused_backward_gauss: null cumulative-mask buffer");
+  return lgu::launch_lookup_fused_bwd(lvl0, lvl1, coords, off0, off1, mask, corr_grad, off1_out_grad, gv0, gv1, gv2, gv3,
+                                      off0_grad, off1_grad, E, H, W, num_levels, radius, false, cum_mask, stream, means,
+                                      nullptr, covs, den, means_grad, covs_grad, den_grad);
 }
 extern "C" int lgu_corr_lookup_fused_backward(const float* lvl0, const float* lvl1, const float* coords,
                                               const float* off0, const float* off1_out, const float* mask,
@@ -717,7 +867,9 @@ static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, co
                                         const float* off1_out, const float* mask, const float* corr_grad,
                                         const float* off1_out_grad, float* gv0, float* gv1, float* gv2, float* gv3,
                                         float* off0_grad, float* off1_grad, int E, int H, int W, int num_levels,
-                                        int radius, bool accumulate, const float* off1_scale, void* stream) {
+                                        int radius, bool accumulate, const float* off1_scale, void* stream,
+                                        const float* win_means, float* gwin, const float* win_covs, const float* win_den,
+                                        float* g_means, float* g_covs, float* g_den) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(lvl0 && lvl1 && coords && off0 && off1_out && mask && corr_grad && gv0 && gv1 && gv2 && gv3 &&
@@ -762,6 +914,9 @@ static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, co
   prm.coords = coords; prm.off0 = off0; prm.off1 = off1_out; prm.mask = mask; prm.g_out = corr_grad;
   prm.g_off1_out = off1_out_grad; prm.g_off0 = off0_grad; prm.g_off1 = off1_grad;
   prm.off1_scale = off1_scale;
+  prm.win_means = win_means; prm.gwin = gwin;
+  prm.win_covs = win_covs; prm.win_den = win_den; prm.g_means = g_means; prm.g_covs = g_covs; prm.g_den = g_den;
+  const bool gauss = g_means != nullptr;
   prm.P = P;
   prm.tiles_per_edge = P / fl::kTile;
   const long long ntiles = (long long)E * prm.tiles_per_edge;
@@ -789,6 +944,8 @@ static int lgu::launch_lookup_fused_bwd(const float* lvl0, const float* lvl1, co
   auto kern = accumulate ? (fxp ? lookup_fused_bwd_kernel<true, false, true> : lookup_fused_bwd_kernel<true, false, false>)
               : bulk     ? (fxp ? lookup_fused_bwd_kernel<false, true, true> : lookup_fused_bwd_kernel<false, true, false>)
                          : (fxp ? lookup_fused_bwd_kernel<false, false, true> : lookup_fused_bwd_kernel<false, false, false>);
+  if (gauss)   // dense mode only (the fixed-point scatter always: the float-atomics switch is an experiment of the plain form)
+    kern = bulk ? lookup_fused_bwd_kernel<false, true, true, true> : lookup_fused_bwd_kernel<false, false, true, true>;
   if (int rc = optin_smem(reinterpret_cast<const void*>(kern), flb::kSmemBytes, "lgu_corr_lookup_fused_backward")) return rc;
   kern<<<(unsigned)nblk, fl::kThreads, flb::kSmemBytes, (cudaStream_t)stream>>>(maps, prm);
   return check_launch("lgu_corr_lookup_fused_backward");

@@ -457,7 +457,7 @@ def corr_lookup_fused_enc(pyramid, coords, off0, off1, cum_mask, wfrag, bias=Non
 
 
 def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad, off1_out_grad=None,
-                               accumulate_into=None, cum_mask=None):
+                               accumulate_into=None, cum_mask=None, gauss_window_means=None, gauss_head=None):
     """Backward of corr_lookup_fused in one launch (what autograd runs for corr.py:88-109 in training).
     pyramid: the 4 levels (only levels 0-1 are read); off1_out: off1 after the forward; mask [E,H,W] from the
     forward; corr_grad [E,196,H,W]; off1_out_grad: upstream gradient on the post-mask offsets (later calls) or None.
@@ -465,7 +465,14 @@ def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad,
     accumulate_into: 4 persistent level-gradient buffers (same shapes as the pyramid, zeroed once by the caller); the
     launch ADDS this call's gradient into them, touching only the per-pixel footprints, and returns them as gv0..gv3.
     cum_mask [E,H,W]: the forward ran in the cumulative-mask form -- `off1_out` is then the PRISTINE offset[1] and the
-    post-mask offsets are off1_out * cum_mask (cum_mask as left by that forward), formed in registers."""
+    post-mask offsets are off1_out * cum_mask (cum_mask as left by that forward), formed in registers.
+    gauss_window_means [E,H,W,2] (dense cum form only): also return, as a 7th value, the [E,H,W,81] window record of the
+    merged level-0 gradient around floor(means) that build_backward_gauss(..., window=) consumes
+    (lgu_corr_lookup_fused_backward_win in include/lgu_corr.h).
+    gauss_head = (means [E,H,W,2], covs [E,H,W,2], den [E,H,W]) (dense cum form only): the Gaussian head's backward of
+    the build is folded into the launch; returns 9 values, the last three being (means_grad, covs_grad, den_grad) =
+    build_backward_gauss(means, covs, den, pyramid[0], this call's level gradients, 4)
+    (lgu_corr_lookup_fused_backward_gauss)."""
     E, H, W = pyramid[0].shape[:3]
     for l, t in enumerate(pyramid):
         _chk(t, f"pyramid[{l}]", 5)
@@ -494,6 +501,37 @@ def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad,
         _chk(cum_mask, "cum_mask", 3)
         if tuple(cum_mask.shape) != (E, H, W):
             raise RuntimeError("cum_mask must be [E,H,W]")
+        if gauss_head is not None:
+            if accumulate_into is not None or gauss_window_means is not None:
+                raise RuntimeError("corr_lookup_fused_backward: gauss_head needs the dense form (and excludes the window record)")
+            means, covs, den = gauss_head
+            _chk(means, "means", 4); _chk(covs, "covs", 4); _chk(den, "den", 3)
+            if tuple(means.shape) != (E, H, W, 2) or tuple(covs.shape) != (E, H, W, 2) or tuple(den.shape) != (E, H, W):
+                raise RuntimeError("gauss_head must be (means [E,H,W,2], covs [E,H,W,2], den [E,H,W])")
+            gm, gc, gd = torch.empty_like(means), torch.empty_like(covs), torch.empty_like(den)
+            with torch.cuda.device(coords.device):
+                st = _lib.lib().lgu_corr_lookup_fused_backward_gauss(
+                    _p(pyramid[0]), _p(pyramid[1]), _p(coords), _p(off0), _p(off1_out), _p(cum_mask), _p(mask),
+                    _p(corr_grad), _p(off1_out_grad) if off1_out_grad is not None else ctypes.c_void_p(0),
+                    _p(means), _p(covs), _p(den), _p(gv[0]), _p(gv[1]), _p(gv[2]), _p(gv[3]), _p(g0), _p(g1),
+                    _p(gm), _p(gc), _p(gd), _i(E), _i(H), _i(W), _i(4), _i(3), _i(4), _stream(coords))
+            _lib.check(st, "corr_lookup_fused_backward (gauss)")
+            return gv[0], gv[1], gv[2], gv[3], g0, g1, gm, gc, gd
+        if gauss_window_means is not None:
+            if accumulate_into is not None:
+                raise RuntimeError("corr_lookup_fused_backward: the Gaussian window record needs the dense form")
+            _chk(gauss_window_means, "gauss_window_means", 4)
+            if tuple(gauss_window_means.shape) != (E, H, W, 2):
+                raise RuntimeError("gauss_window_means must be [E,H,W,2]")
+            gwin = torch.empty(E, H, W, 81, dtype=torch.float32, device=coords.device)
+            with torch.cuda.device(coords.device):
+                st = _lib.lib().lgu_corr_lookup_fused_backward_win(
+                    _p(pyramid[0]), _p(pyramid[1]), _p(coords), _p(off0), _p(off1_out), _p(cum_mask), _p(mask),
+                    _p(corr_grad), _p(off1_out_grad) if off1_out_grad is not None else ctypes.c_void_p(0),
+                    _p(gauss_window_means), _p(gv[0]), _p(gv[1]), _p(gv[2]), _p(gv[3]), _p(g0), _p(g1), _p(gwin),
+                    _i(E), _i(H), _i(W), _i(4), _i(3), _stream(coords))
+            _lib.check(st, "corr_lookup_fused_backward (window)")
+            return gv[0], gv[1], gv[2], gv[3], g0, g1, gwin
         with torch.cuda.device(coords.device):
             st = _lib.lib().lgu_corr_lookup_fused_backward_cum(
                 _p(pyramid[0]), _p(pyramid[1]), _p(coords), _p(off0), _p(off1_out), _p(cum_mask), _p(mask), _p(corr_grad),
@@ -502,6 +540,8 @@ def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad,
                 _i(1 if accumulate_into is not None else 0), _stream(coords))
         _lib.check(st, "corr_lookup_fused_backward (cum)")
         return gv[0], gv[1], gv[2], gv[3], g0, g1
+    if gauss_window_means is not None or gauss_head is not None:
+        raise RuntimeError("corr_lookup_fused_backward: gauss_window_means / gauss_head need cum_mask (the cumulative-mask form)")
     with torch.cuda.device(coords.device):
         st = fn(
             _p(pyramid[0]), _p(pyramid[1]), _p(coords), _p(off0), _p(off1_out), _p(mask), _p(corr_grad),
@@ -512,15 +552,27 @@ def corr_lookup_fused_backward(pyramid, coords, off0, off1_out, mask, corr_grad,
     return gv[0], gv[1], gv[2], gv[3], g0, g1
 
 
-def build_backward_gauss(means, covs, den, lvl0, level_grads, radius):
+def build_backward_gauss(means, covs, den, lvl0, level_grads, radius, window=None):
     """Gaussian-head gradients of the fused build straight from the four level gradients (no dense pass):
     means, covs [E,H,W,2], den [E,H,W], lvl0 [E,H,W,H,W], level_grads = 4 tensors [E,H,W,H>>l,W>>l] or None.
+    window [E,H,W,81]: the record corr_lookup_fused_backward(gauss_window_means=means) returned -- used INSTEAD of
+    level_grads (radius 4; same result bit for bit, one contiguous read per pixel).
     Returns (means_grad, covs_grad, den_grad); see lgu_build_backward_gauss in include/lgu_corr.h."""
     _chk(means, "means", 4); _chk(covs, "covs", 4); _chk(den, "den", 3); _chk(lvl0, "lvl0", 5)
     E, H, W = lvl0.shape[:3]
     if tuple(lvl0.shape) != (E, H, W, H, W) or tuple(means.shape) != (E, H, W, 2) or tuple(covs.shape) != (E, H, W, 2) \
             or tuple(den.shape) != (E, H, W):
         raise RuntimeError("build_backward_gauss: inconsistent shapes")
+    if window is not None:
+        _chk(window, "window", 4)
+        if tuple(window.shape) != (E, H, W, 81) or radius != 4:
+            raise RuntimeError("build_backward_gauss: window must be [E,H,W,81] and radius 4")
+        gm, gc, gd = torch.empty_like(means), torch.empty_like(covs), torch.empty_like(den)
+        with torch.cuda.device(lvl0.device):
+            st = _lib.lib().lgu_build_backward_gauss_window(_p(means), _p(covs), _p(den), _p(lvl0), _p(window), _p(gm),
+                                                            _p(gc), _p(gd), _i(E), _i(H), _i(W), _stream(lvl0))
+        _lib.check(st, "build_backward_gauss (window)")
+        return gm, gc, gd
     ptrs = []
     for l, g in enumerate(level_grads):
         if g is None:

@@ -296,6 +296,71 @@ def test_fused_backward_cumulative_mask_form_equals_materialised_form(ops, accum
         assert torch.equal(a, b), f"output {k}"
 
 
+@pytest.mark.parametrize("big,edge_means", [(False, False), (True, False), (False, True)])
+def test_fused_backward_window_record_equals_merged_level_gradients(ops, big, edge_means):
+    """lgu_corr_lookup_fused_backward_win: the 9 x 9 window record of g0 + g1/4 + g2/16 + g3/64 around floor(means) is,
+    bit for bit, what avg_pool2d^T (corr.py:83-86) of the dense level gradients gives at those taps (zeros outside the
+    grid), the dense gradients themselves are unchanged, and the Gaussian-head gradients from the record equal the ones
+    from the four level gradients (gaussianMask_cuda.py:77-86 backward).  `big`: offsets beyond the staged boxes, whose
+    contributions travel by global atomics and are not in the shared-memory boxes the record is normally formed from."""
+    E, dev, H, W = 2, "cuda", 48, 64
+    g = inputs.gen(131)
+    pyr = [torch.randn(E, H, W, H >> l, W >> l, generator=g).to(dev) for l in range(4)]
+    c = _case(E, 132, big_offsets=big)
+    coords, off0, off1 = c["coords"].to(dev), c["offsets"][0].to(dev), c["offsets"][1].to(dev)
+    means, covs = c["means"].to(dev).contiguous(), c["covs"].to(dev).contiguous()
+    if edge_means:                                                # windows hanging over every border, far outside, NaN
+        means[0, 0, 0] = torch.tensor([-3.5, -2.25]); means[0, 0, 1] = torch.tensor([66.0, 49.5])
+        means[0, 0, 2] = torch.tensor([-100.0, 1e9]); means[0, 0, 3] = torch.tensor([float("nan"), 5.0])
+        means[0, 0, 4] = torch.tensor([63.9, 47.9]); means[0, 0, 5] = torch.tensor([0.0, 0.0])
+    den = (6.28 * torch.sqrt(covs[..., 0] * covs[..., 1])).contiguous()
+    cum = torch.ones(E, H, W, device=dev)
+    _, mask = ops.corr_lookup_fused(pyr, coords, off0, off1, 3, return_mask=True, cum_mask=cum)
+    g_corr = torch.randn(E, 196, H, W, generator=g).to(dev)
+    want = ops.corr_lookup_fused_backward(pyr, coords, off0, off1, mask, g_corr, cum_mask=cum)
+    got = ops.corr_lookup_fused_backward(pyr, coords, off0, off1, mask, g_corr, cum_mask=cum, gauss_window_means=means)
+    assert len(got) == 7
+    for k in (4, 5):
+        assert torch.equal(got[k], want[k]), f"output {k}"
+    for k in range(4):                                            # out-of-box taps arrive by float atomics: order-dependent
+        if big:
+            assert (got[k] - want[k]).abs().max().item() <= 1e-5 * max(1.0, want[k].abs().max().item())
+        else:
+            assert torch.equal(got[k], want[k]), f"output {k}"
+    # the record, from the dense gradients of the SAME call
+    gl = got[:4]
+    merged = gl[0].clone()
+    for l, f in ((1, 0.25), (2, 0.0625), (3, 0.015625)):
+        up = gl[l].repeat_interleave(1 << l, dim=3).repeat_interleave(1 << l, dim=4)
+        merged = merged + up * f                                  # same order of fp32 additions as the kernels
+    fx = torch.floor(torch.nan_to_num(means[..., 0], nan=0.0)).clamp(-2**31, 2**31 - 1).long() - 4
+    fy = torch.floor(torch.nan_to_num(means[..., 1], nan=0.0)).clamp(-2**31, 2**31 - 1).long() - 4
+    wy, wx = torch.meshgrid(torch.arange(9, device=dev), torch.arange(9, device=dev), indexing="ij")
+    X = fx[..., None, None] + wx; Y = fy[..., None, None] + wy    # [E,H,W,9,9]
+    ok = (X >= 0) & (X < W) & (Y >= 0) & (Y < H)
+    flat = merged.reshape(E, H, W, H * W)
+    idx = (Y.clamp(0, H - 1) * W + X.clamp(0, W - 1)).reshape(E, H, W, 81)
+    ref = torch.where(ok.reshape(E, H, W, 81), flat.gather(3, idx), torch.zeros((), device=dev))
+    assert torch.equal(got[6], ref)                              # (also for out-of-box taps: re-read from the finished slices)
+    a = ops.build_backward_gauss(means, covs, den, pyr[0], list(gl), 4)
+    b = ops.build_backward_gauss(means, covs, den, pyr[0], None, 4, window=got[6])
+    for k, (u, v) in enumerate(zip(a, b)):
+        assert torch.equal(torch.nan_to_num(u), torch.nan_to_num(v)), f"gauss output {k}"
+    # ... and folded into the launch itself (lgu_corr_lookup_fused_backward_gauss)
+    fused = ops.corr_lookup_fused_backward(pyr, coords, off0, off1, mask, g_corr, cum_mask=cum, gauss_head=(means, covs, den))
+    assert len(fused) == 9
+    for k in (4, 5):
+        assert torch.equal(fused[k], want[k]), f"output {k}"
+    ref_g = ops.build_backward_gauss(means, covs, den, pyr[0], list(fused[:4]), 4)   # from the fused call's OWN level gradients
+    for k in range(4):
+        if big:
+            assert (fused[k] - want[k]).abs().max().item() <= 1e-5 * max(1.0, want[k].abs().max().item())
+        else:
+            assert torch.equal(fused[k], want[k]), f"output {k}"
+    for k, (u, v) in enumerate(zip(ref_g, fused[6:])):
+        assert torch.equal(torch.nan_to_num(u), torch.nan_to_num(v)), f"fused gauss output {k}"
+
+
 @pytest.mark.parametrize("keep_corr,half", [(True, False), (False, False), (False, True)])
 def test_fused_lookup_with_corr_encoder_epilogue(ops, keep_corr, half):
     """UpdateModule.corr_encoder[0:2] (Conv2d(196,128,1) + ReLU, droid_net.py:74-76,115) folded into the
