@@ -99,7 +99,9 @@ build_bwd_kernel(const __grid_constant__ BbMaps maps, const BbParams prm) {
   using namespace bb;
   using C_ = Cfg<TR, TS>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the shared array: an integer round trip makes every derived pointer
+  // generic, and all staging accesses compile to generic LD.E / ST.E instead of LDS / STS (ncu: the top stall site)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::kBarOffset);
   uint64_t* full = bars;                         // [kStages]  TMA bytes landed
   uint64_t* conv = bars + C_::kStages;           // [kStages]  converted tiles visible to the tensor core

@@ -1,6 +1,7 @@
 // build_common.cuh -- parameter block and Gaussian residual shared by build_pyramid.cu (8 epilogue warps; every
 // precision / flat volumes) and build_pyramid16.cu (16 epilogue warps; the fp16-input pyramid build).
 #pragma once
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace lgu {
@@ -26,6 +27,7 @@ struct BpParams {
   int wide;     // 1: level-0 rows leave as pair-shared 16 KB boxes (512 contiguous bytes per source pixel; PREC 1, Q % 64 == 0)
   int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
   int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
+  int dbg;      // experiment switches of build_pyramid16_kernel (LGU_BUILD_DBG; 0 in production)
 };
 
 // Gaussian residual of one element (gaussianAttn.cu:58-64 + gaussianMask_cuda.py:85-86), fp32, no contraction.
@@ -39,6 +41,13 @@ __device__ __forceinline__ float gauss_residual(float v, int x1, int y1, float m
   return __fadd_rn(__fdiv_rn(masked, den), v);
 }
 
+
+static inline bool env_flag(const char* name) {   // experiment switches of the build kernels
+  const char* v = getenv(name);
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
+
+// (Forming the row-invariant ddy / cov_y once per window row instead of per tap was measured: 542 -> 553 us, reverted.)
 
 // The 16-epilogue-warp kernel (build_pyramid16.cu).  Returns LGU_OK / an error code.
 int launch_build16(const CUtensorMap& mh, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st);

@@ -97,7 +97,9 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
                      const __grid_constant__ CUtensorMap map_l0w, const BpParams prm) {
   using Cfg = BpCfg<PREC>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the shared array: an integer round trip makes every derived pointer
+  // generic, and all staging accesses compile to generic LD.E / ST.E instead of LDS / STS (ncu: the top stall site)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // [plane][atom][128 rows][128 B]
   uint8_t* sB = smem + Cfg::kABytes;                    // [stage][plane][atom][128 rows][128 B]
   uint8_t* sStore = sB + Cfg::kStages * Cfg::kStageBytes;   // [warp][buf][32 rows][128 B]
@@ -563,10 +565,6 @@ __global__ void __launch_bounds__(256) pack_fmaps_vec_kernel(const SRC* __restri
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-static inline bool env_flag(const char* name) {
-  const char* v = getenv(name);
-  return v != nullptr && v[0] != '\0' && v[0] != '0';
-}
 
 template <int PREC>
 static int launch_build(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mbh, const CUtensorMap& mbl,
@@ -681,7 +679,7 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   BpParams prm;
   prm.wide = wide;
   prm.trace = nullptr;
-#ifdef LGU_BP_TRACE
+#if defined(LGU_BP_TRACE) || defined(LGU_B16_TRACE)
   if (const char* tp = getenv("LGU_BP_TRACE_PTR")) prm.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
 #endif
   prm.ii = ii; prm.jj = jj; prm.means = means; prm.covs = covs; prm.den = den;
@@ -689,6 +687,7 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   prm.E = E; prm.P = P; prm.H = H; prm.gauss_radius = gauss_radius; prm.round_half = round_half;
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = lvl1 != nullptr;
+  prm.dbg = getenv("LGU_BUILD_DBG") ? atoi(getenv("LGU_BUILD_DBG")) : 0;
   prm.out_slots = out_slots;
   prm.Q = P;
   prm.halves = H / 4;
@@ -743,6 +742,7 @@ extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, co
   prm.E = E; prm.P = P; prm.H = 0; prm.gauss_radius = 0; prm.round_half = 0;
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = 0;
+  prm.dbg = 0;
   prm.out_slots = nullptr;
   prm.Q = Q;
   prm.halves = (Q + 255) / 256;

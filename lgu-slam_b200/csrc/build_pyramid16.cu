@@ -19,6 +19,17 @@
 // Shared memory: A 32 KB + 3 x 32 KB operand stages + 16 x 4 KB level-0 staging + 8 x 4 KB level-1 tiles = 224 KB.
 #include "build_common.cuh"
 
+// LGU_B16_TRACE (diagnostic builds only, tools/diag/b16_trace.py): per epilogue warp, cycles in (0) waiting for the
+// accumulator half, (1) the two tcgen05.ld, (2) waiting for the staging tile to be free, (3) staging writes + Gaussian patch,
+// (4) fence + syncwarp + store issue, (5) quadrant barrier A, (6) level-1 staging + barrier B, (7) in total.
+#ifdef LGU_B16_TRACE
+#define B16_T0() const long long _t0 = clock64()
+#define B16_ADD(slot) tr[slot] += clock64() - _t0
+#else
+#define B16_T0()
+#define B16_ADD(slot)
+#endif
+
 namespace lgu {
 
 namespace b16 {
@@ -33,12 +44,15 @@ constexpr int kBarOffset = kABytes + kStages * kStageBytes + kStoreBytes + kL1By
 constexpr int kSmemBytes = kBarOffset + 256 + 1024;
 }  // namespace b16
 
+template <bool L1_LSU>
 __global__ void __launch_bounds__(b16::kThreads, 1)
 build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_l0,
                        const __grid_constant__ CUtensorMap map_l1, const BpParams prm) {
   using namespace b16;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the shared array: an integer round trip makes every derived pointer
+  // generic, and all staging accesses compile to generic LD.E / ST.E instead of LDS / STS (ncu: the top stall site)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kABytes;
   uint8_t* sStore = sB + kStages * kStageBytes;        // [epilogue warp][32 rows][128 B]
@@ -153,13 +167,22 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
     const int rsw = lane & 7;                           // 128B swizzle phase of this thread's staging row
     const int x0 = xs * 32;
     const int bar_id = 1 + quad;                        // named barrier of the quadrant's four warps (128 threads)
+#ifdef LGU_B16_TRACE
+    long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tr_begin = clock64();
+#endif
 
     // stage one 32-float row segment per lane (single staging tile: the previous store must have been read) and hand the
     // 32 x 32 tile to the TMA store engine; patched values are read back into v (they feed the pooled levels)
     auto store_tile = [&](float (&v)[32], int col, int row0, bool patch, int yy, float mx, float my, float c1, float c2,
                           float den, unsigned bx) {
-      if (lane == 0) tma_wait_read<0>();
-      __syncwarp();
+      {
+        B16_T0();
+        if (lane == 0) tma_wait_read<0>();
+        __syncwarp();
+        B16_ADD(2);
+      }
+      B16_T0();
       float4* rowp = reinterpret_cast<float4*>(my_store + lane * 128);
 #pragma unroll
       for (int c = 0; c < 8; ++c) rowp[c ^ rsw] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -183,11 +206,16 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
           }
         }
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&map_l0, my_store, col, row0);
-        tma_commit();
+      B16_ADD(3);
+      {
+        B16_T0();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !(prm.dbg & 1)) {
+          tma_store_2d(&map_l0, my_store, col, row0);
+          tma_commit();
+        }
+        B16_ADD(4);
       }
     };
 
@@ -213,14 +241,22 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
 
       for (int h = 0; h < halves; ++h, ++half_it) {
         const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
-        mbar_wait(t_full + buf, buf_use & 1);
+        {
+          B16_T0();
+          mbar_wait(t_full + buf, buf_use & 1);
+          B16_ADD(0);
+        }
         tc_fence_after();
         const uint32_t tcol = tmem_base + lane_base + buf * 256 + xs * 32;
         const int ya = 4 * h + 2 * rp, yb = ya + 1;
         float ha[16], l1[16];
         {
           float a[32];
-          tmem_ld32(tcol + (2 * rp) * 64, a);
+          {
+            B16_T0();
+            tmem_ld32(tcol + (2 * rp) * 64, a);
+            B16_ADD(1);
+          }
           if (prm.round_half) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] = __half2float(__float2half_rn(a[i]));
@@ -232,7 +268,11 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         }
         {
           float b[32];
-          tmem_ld32(tcol + (2 * rp + 1) * 64, b);
+          {
+            B16_T0();
+            tmem_ld32(tcol + (2 * rp + 1) * 64, b);
+            B16_ADD(1);
+          }
           tc_fence_before();                            // last TMEM read of this half by this warp
           __syncwarp();
           if (lane == 0) mbar_arrive(t_empty + buf);
@@ -248,16 +288,37 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         }
         // ---- level 1: quadrant barrier A (the tiles of the previous half were read by the engine -- the issuer's
         // wait_read before its level-0 stores of this half -- and by every warp's level-2 pass), stage, barrier B, store
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        {
+          B16_T0();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          B16_ADD(5);
+        }
+        B16_T0();
         {
           float4* rowp = reinterpret_cast<float4*>(l1_mine + lane * 128);
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             rowp[(xs * 4 + c) ^ rsw] = make_float4(l1[4 * c], l1[4 * c + 1], l1[4 * c + 2], l1[4 * c + 3]);
         }
-        fence_proxy_async();
+        if (!L1_LSU) fence_proxy_async();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        if (l1_issuer && lane == 0) {
+        B16_ADD(6);
+        if (prm.dbg & 2) {
+        } else if (L1_LSU) {
+          // The TMA store engine is what bounds this kernel (one 128-byte row segment per ~7 cycles and SM): the level-1
+          // tiles -- a fifth of its row segments -- leave through the LSU instead.  Each warp takes 8 rows of both tiles;
+          // a store instruction covers 4 rows x 128 contiguous bytes (lane = row % 4 x 16-byte chunk), i.e. full lines.
+#pragma unroll
+          for (int tix = 0; tix < 2; ++tix) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int row = sub * 8 + rr * 4 + (lane >> 3), ch = lane & 7;
+              const float4 vv = *reinterpret_cast<const float4*>(l1_rows[tix] + row * 128 + ((ch ^ (row & 7)) << 4));
+              float* dst = prm.lvl1 + (size_t)(row0 + row) * (size_t)(Q >> 2) + (2 * h + tix) * 32 + ch * 4;
+              __stcs(reinterpret_cast<float4*>(dst), vv);
+            }
+          }
+        } else if (l1_issuer && lane == 0) {
           tma_store_2d(&map_l1, l1_rows[0], (2 * h) * 32, row0);
           tma_store_2d(&map_l1, l1_rows[1], (2 * h + 1) * 32, row0);
           tma_commit();
@@ -273,6 +334,7 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
           l2[1] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(u0.z, u0.w), w0.z), w0.w), 0.25f);
           l2[2] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(u1.x, u1.y), w1.x), w1.y), 0.25f);
           l2[3] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(u1.z, u1.w), w1.z), w1.w), 0.25f);
+          if (!(prm.dbg & 4))
           *reinterpret_cast<float4*>(prm.lvl2 + pix * (size_t)(Q >> 4) + h * 16 + sub * 4) =
               make_float4(l2[0], l2[1], l2[2], l2[3]);
           if ((h & 1) == 0) {
@@ -281,6 +343,7 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
           } else {
             const float l3a = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(l2_prev[0], l2_prev[1]), l2[0]), l2[1]), 0.25f);
             const float l3b = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(l2_prev[2], l2_prev[3]), l2[2]), l2[3]), 0.25f);
+            if (!(prm.dbg & 4))
             *reinterpret_cast<float2*>(prm.lvl3 + pix * (size_t)(Q >> 6) + (h >> 1) * 8 + sub * 2) = make_float2(l3a, l3b);
           }
         }
@@ -288,6 +351,11 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
     }
     if (lane == 0) tma_wait_all();
     __syncwarp();
+#ifdef LGU_B16_TRACE
+    tr[7] = clock64() - tr_begin;
+    if (lane == 0 && prm.trace != nullptr)
+      for (int q = 0; q < 8; ++q) atomicAdd(prm.trace + q, (unsigned long long)tr[q]);
+#endif
   }
 
   tc_fence_before();
@@ -296,12 +364,15 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
 }
 
 int launch_build16(const CUtensorMap& mh, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st) {
-  if (int rc = optin_smem(reinterpret_cast<const void*>(build_pyramid16_kernel), b16::kSmemBytes, "lgu_build_pyramid")) return rc;
+  // level-1 tiles through the LSU (default; 559 -> 540 us at E = 48); LGU_BUILD_L1_TMA=1: through the TMA store engine
+  const bool l1_lsu = !env_flag("LGU_BUILD_L1_TMA") && prm.lvl1 != nullptr;
+  auto kern = l1_lsu ? build_pyramid16_kernel<true> : build_pyramid16_kernel<false>;
+  if (int rc = optin_smem(reinterpret_cast<const void*>(kern), b16::kSmemBytes, "lgu_build_pyramid")) return rc;
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = prm.num_units < sms ? prm.num_units : sms;
-  build_pyramid16_kernel<<<grid, b16::kThreads, b16::kSmemBytes, st>>>(mh, m0, m1, prm);
+  kern<<<grid, b16::kThreads, b16::kSmemBytes, st>>>(mh, m0, m1, prm);
   return check_launch("lgu_build_pyramid(16)");
 }
 
