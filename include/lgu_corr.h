@@ -347,6 +347,18 @@ LGU_API int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, const
                      const int32_t* ii, const int32_t* jj, float* volume,
                      int T1, int T2, int E, int P, int Q, int C, int precision, void* stream);
 
+/* Sparse form for the fused backend lookup (lgu_altcorr_lookup_fused*), whose per-pixel reads stay inside a 20 x 16 box
+ * around coords / 2^level when the learned offsets are bounded by 4 (4 * tanh, corr.py:121-128): only the 256-column
+ * "halves" (256 / (W >> level) target rows each) named in half_mask [E * H*W / 128] -- one word per unit of 128 consecutive
+ * source pixels, bit h = half h -- are computed and written; the rest of `volume` is left untouched and must not be read.
+ * lgu_volume_half_mask derives the mask from the coords the lookup will be called with (box rows +- 1 row of slack).
+ * With dense, smooth coords about 60 % of level 0 is built (tools/diag/t_backend1.py). */
+LGU_API int lgu_volume_half_mask(const float* coords, uint32_t* half_mask, int E, int H, int W, int level, void* stream);
+LGU_API int lgu_build_volume_sparse(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
+                                   const void* fmaps2_lo, const int32_t* ii, const int32_t* jj,
+                                   const uint32_t* half_mask, float* volume,
+                                   int T1, int T2, int E, int P, int Q, int C, int precision, void* stream);
+
 /* fmaps [T,C,P] fp32 or fp16 (NCHW as the encoders emit) -> channels-last fp16 planes
  * hi [T,P,C] (and lo [T,P,C] = fp16(x/4 - hi) when lo != NULL), pre-scaled by 1/4 (corr.py:148-149). */
 LGU_API int lgu_pack_fmaps(const void* fmaps, int src_is_half, void* hi, void* lo,

@@ -675,8 +675,10 @@ class AltCorrBlock:
     MAX_EDGES_PER_PASS = 256          # scratch bound: 256 x 50 MB = 12.8 GB
 
     def __init__(self, ofsMap, ofs_residual, GA, fmaps, num_levels=4, radius=3, strict_ref=True, materialize=None,
-                 sampler_ops=None, cache=False, volume_cache_gb=None):
-        """cache (materialised path only): global BA calls the SAME block for the same chunks in every one of its
+                 sampler_ops=None, cache=False, volume_cache_gb=None, sparse_volumes=True):
+        """sparse_volumes (materialised path, volumes not cached): level 0 is built only where the lookup's per-pixel
+        boxes can reach (lgu_volume_half_mask / lgu_build_volume_sparse); results are identical.
+        cache (materialised path only): global BA calls the SAME block for the same chunks in every one of its
         `steps` iterations (factor_graph.py:265-279) while the feature maps stay fixed, so everything that depends
         only on (ii, jj) is kept per chunk after the first call:
           * the pre-mask offsets -- the two 3x3 convs and the normalise / tanh / permute chain of corr.py:217-235 are
@@ -690,6 +692,7 @@ class AltCorrBlock:
         coords-dependent work (mask, lookups) runs per call.
         `clear_cache()` drops everything (call it when the feature maps change)."""
         self.cache = bool(cache)
+        self.sparse_volumes = bool(sparse_volumes)
         self._cache = {}
         self._vol_bytes = 0
         if volume_cache_gb is None and self.cache and fmaps.is_cuda:
@@ -778,7 +781,13 @@ class AltCorrBlock:
             e = slice(s, min(N, s + step))
             vols = ent["vols"].get(s) if ent is not None else None
             if vols is None:
-                vols = [ops.build_volume(planes[0][0], planes[0][1], planes[l][0], planes[l][1], ii32[e], jj32[e])
+                # Level 0 is 3/4 of the volume bytes, and the lookup below reads it only inside a 20 x 16 box per source
+                # pixel (offsets are 4 * tanh, corr.py:121-128): build only the row bands those boxes touch.  Not when the
+                # volumes are kept for later calls with other coords (the per-chunk cache).
+                sparse = self.sparse_volumes and self._vol_budget == 0 and (H * W) % 128 == 0 and 256 % W == 0
+                hm = ops.volume_half_mask(c[e], 0) if sparse else None
+                vols = [ops.build_volume(planes[0][0], planes[0][1], planes[l][0], planes[l][1], ii32[e], jj32[e],
+                                         half_mask=hm if l == 0 else None)
                         .view(-1, H, W, H >> l, W >> l) for l in range(self.num_levels)]
                 nbytes = sum(v.numel() * 4 for v in vols)
                 if ent is not None and self._vol_bytes + nbytes <= self._vol_budget:

@@ -27,6 +27,7 @@ struct BpParams {
   int wide;     // 1: level-0 rows leave as pair-shared 16 KB boxes (512 contiguous bytes per source pixel; PREC 1, Q % 64 == 0)
   int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
   int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
+  const uint32_t* half_mask;   // [num_units] or null: bit h set = accumulator half h (256 target columns) of the unit is built
   int dbg;      // experiment switches of build_pyramid16_kernel (LGU_BUILD_DBG; 0 in production)
 };
 

@@ -30,6 +30,7 @@
 //            per product, for fp32-valued feature maps (the training path).
 #include <cstdlib>
 #include "build_common.cuh"
+#include "fused_common.cuh"
 
 // LGU_BP_TRACE (diagnostic builds only): per epilogue warp, cycles spent waiting for (0) the accumulator half, (1) a
 // free staging buffer (the TMA store engine), (2) the quadrant's pair barriers, and (3) in total.  lane 0 of every
@@ -160,10 +161,13 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
           tma_load_2d(sA + kPlaneBytes, &map_lo, a_full, 0, a_row);
           tma_load_2d(sA + kPlaneBytes + kAtomBytes, &map_lo, a_full, 64, a_row);
         }
+        const uint32_t hmask = prm.half_mask != nullptr ? __ldg(prm.half_mask + u) : 0xffffffffu;
         const int nchunks = halves * 2;
-        for (int c = 0; c < nchunks; ++c, ++chunk_it) {
+        for (int c = 0; c < nchunks; ++c) {
+          if (!((hmask >> (c >> 1)) & 1u)) continue;   // sparse volume: this half is never sampled (lgu_volume_half_mask)
           const int s = chunk_it % Cfg::kStages;
           const uint32_t use = chunk_it / Cfg::kStages;
+          ++chunk_it;
           mbar_wait(b_empty + s, (use & 1) ^ 1);
           uint8_t* dst = sB + s * Cfg::kStageBytes;
           const int b_row = b_row0 + c * kChunkN;
@@ -185,8 +189,11 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
       uint32_t unit_it = 0, chunk_it = 0, half_it = 0;
       for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x, ++unit_it) {
         mbar_wait(a_full, unit_it & 1);
-        for (int h = 0; h < halves; ++h, ++half_it) {
+        const uint32_t hmask = prm.half_mask != nullptr ? __ldg(prm.half_mask + u) : 0xffffffffu;
+        for (int h = 0; h < halves; ++h) {
+          if (!((hmask >> h) & 1u)) continue;
           const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
+          ++half_it;
           mbar_wait(t_empty + buf, (buf_use & 1) ^ 1);
           tc_fence_after();
           for (int c = 0; c < 2; ++c, ++chunk_it) {
@@ -356,8 +363,11 @@ build_pyramid_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_co
 #pragma unroll
       for (int i = 0; i < 8; ++i) l2_prev[i] = 0.f;
 
-      for (int h = 0; h < halves; ++h, ++half_it) {
+      const uint32_t hmask = prm.half_mask != nullptr ? __ldg(prm.half_mask + u) : 0xffffffffu;
+      for (int h = 0; h < halves; ++h) {
+        if (!((hmask >> h) & 1u)) continue;               // (flat volumes only: the pooled levels need every half)
         const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
+        ++half_it;
         {
           BP_T0();
           mbar_wait(t_full + buf, buf_use & 1);
@@ -688,6 +698,7 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = lvl1 != nullptr;
   prm.dbg = getenv("LGU_BUILD_DBG") ? atoi(getenv("LGU_BUILD_DBG")) : 0;
+  prm.half_mask = nullptr;
   prm.out_slots = out_slots;
   prm.Q = P;
   prm.halves = H / 4;
@@ -698,9 +709,9 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   return launch_build<2>(mh, ml, mh, ml, m0, m1, m0w, prm, (cudaStream_t)stream);
 }
 
-extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
-                                const void* fmaps2_lo, const int32_t* ii, const int32_t* jj, float* volume, int T1,
-                                int T2, int E, int P, int Q, int C, int precision, void* stream) {
+static int build_volume_impl(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
+                             const void* fmaps2_lo, const int32_t* ii, const int32_t* jj, float* volume, int T1,
+                             int T2, int E, int P, int Q, int C, int precision, const uint32_t* half_mask, void* stream) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(fmaps1_hi && fmaps2_hi && ii && jj && volume, "lgu_build_volume: null pointer");
@@ -743,9 +754,73 @@ extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, co
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = 0;
   prm.dbg = 0;
+  prm.half_mask = half_mask;
   prm.out_slots = nullptr;
   prm.Q = Q;
   prm.halves = (Q + 255) / 256;
   if (precision == 1) return launch_build<1>(mh, ml, mbh, mbl, m0, m0, m0w, prm, (cudaStream_t)stream);
   return launch_build<2>(mh, ml, mbh, mbl, m0, m0, m0w, prm, (cudaStream_t)stream);
+}
+
+extern "C" int lgu_build_volume(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
+                                const void* fmaps2_lo, const int32_t* ii, const int32_t* jj, float* volume, int T1,
+                                int T2, int E, int P, int Q, int C, int precision, void* stream) {
+  return build_volume_impl(fmaps1_hi, fmaps1_lo, fmaps2_hi, fmaps2_lo, ii, jj, volume, T1, T2, E, P, Q, C, precision, nullptr,
+                           stream);
+}
+
+extern "C" int lgu_build_volume_sparse(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
+                                       const void* fmaps2_lo, const int32_t* ii, const int32_t* jj,
+                                       const uint32_t* half_mask, float* volume, int T1, int T2, int E, int P, int Q, int C,
+                                       int precision, void* stream) {
+  LGU_REQUIRE(E == 0 || half_mask != nullptr, "lgu_build_volume_sparse: null half mask");
+  LGU_REQUIRE(Q <= 32 * 256, "lgu_build_volume_sparse: more than 32 halves (Q = %d)", Q);
+  return build_volume_impl(fmaps1_hi, fmaps1_lo, fmaps2_hi, fmaps2_lo, ii, jj, volume, T1, T2, E, P, Q, C, precision,
+                           half_mask, stream);
+}
+
+namespace lgu {
+// Which 256-column halves of a [E,P,Q] volume (target rows of W2 = W >> level columns: 256 / W2 rows per half) the fused
+// backend lookup can touch: per unit of 128 source pixels, the union over its pixels of the rows [yb - 1, yb + kRows + 1] of
+// the lookup's staged box, yb = box_origin_y(floor(cy / 2^level), 7, H2) (lookup_fused.cu; offsets bounded by 4 keep every
+// tap inside that box, one row of slack for px = c + 4.0 rounding up to the next integer).  One warp per unit.
+__global__ void __launch_bounds__(256) volume_half_mask_kernel(const float* __restrict__ coords, uint32_t* __restrict__ mask,
+                                                               int num_units, int H2, int rows_per_half, int halves, int level) {
+  const int lane = threadIdx.x & 31;
+  const int u = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (u >= num_units) return;
+  uint32_t m = 0;
+#pragma unroll
+  for (int q = 0; q < kTileM / 32; ++q) {
+    float cy = __ldg(coords + ((size_t)u * kTileM + q * 32 + lane) * 2 + 1);
+    for (int l = 0; l < level; ++l) cy = __fmul_rn(cy, 0.5f);     // the lookup's own successive halving
+    const int yb = box_origin_y(floor_to_int(cy), 7, H2);
+    const int y0 = max(yb - 1, 0), y1 = min(yb + fl::kBH01 + 1, H2 - 1);
+    if (y0 <= y1) {
+      const int h0 = y0 / rows_per_half, h1 = min(y1 / rows_per_half, halves - 1);
+      m |= (h1 >= 31 ? 0xffffffffu : ((2u << h1) - 1u)) & ~((1u << h0) - 1u);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+  if (lane == 0) mask[u] = m;
+}
+}  // namespace lgu
+
+extern "C" int lgu_volume_half_mask(const float* coords, uint32_t* half_mask, int E, int H, int W, int level, void* stream) {
+  using namespace lgu;
+  if (E == 0) return LGU_OK;
+  LGU_REQUIRE(coords && half_mask, "lgu_volume_half_mask: null pointer");
+  LGU_REQUIRE(E > 0 && H > 0 && W > 0 && level >= 0 && level < 4, "lgu_volume_half_mask: bad sizes");
+  const int P = H * W, H2 = H >> level, W2 = W >> level;
+  if ((P % kTileM) != 0 || W2 <= 0 || (256 % W2) != 0 || (long long)H2 * W2 > 32 * 256) {
+    set_error("lgu_volume_half_mask: needs H*W %% 128 == 0, (W >> level) dividing 256 and at most 32 halves (H=%d W=%d level=%d)",
+              H, W, level);
+    return LGU_ERR_UNSUPPORTED;
+  }
+  const int num_units = E * (P / kTileM);
+  const int halves = (H2 * W2 + 255) / 256;
+  volume_half_mask_kernel<<<(num_units + 7) / 8, 256, 0, (cudaStream_t)stream>>>(coords, half_mask, num_units, H2, 256 / W2,
+                                                                               halves, level);
+  return check_launch("lgu_volume_half_mask");
 }

@@ -647,10 +647,24 @@ def build_backward_fmaps(level_grads, f1, f2):
     return g_f1.view(E, C, H, W), g_f2
 
 
-def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj):
+def volume_half_mask(coords, level=0):
+    """Which 256-column halves of a level's [E,P,Q] volume the fused backend lookup at `coords` [E,H,W,2] can touch
+    (offsets bounded by 4): uint32 [E*H*W/128] as int32 storage, for build_volume(..., half_mask=)."""
+    _chk(coords, "coords", 4)
+    E, H, W, _ = coords.shape
+    mask = torch.empty(E * H * W // 128, dtype=torch.int32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        st = _lib.lib().lgu_volume_half_mask(_p(coords), _p(mask), _i(E), _i(H), _i(W), _i(level), _stream(coords))
+    _lib.check(st, "volume_half_mask")
+    return mask
+
+
+def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj, half_mask=None):
     """volume[e,p,q] = sum_c f1[ii[e],p,c] * f2[jj[e],q,c] on tcgen05 (fp32 accumulate).  f1_* [T1,P,C],
     f2_* [T2,Q,C] contiguous CUDA fp16 planes (lo planes None for single-product precision); ii, jj int32 [E].
-    Returns [E,P,Q] fp32.  The backend path's per-level volume (source level 0 x pooled target level l)."""
+    Returns [E,P,Q] fp32.  The backend path's per-level volume (source level 0 x pooled target level l).
+    half_mask (volume_half_mask): sparse form -- only the named halves are computed; the rest of the result is
+    UNINITIALISED memory that the fused backend lookup at those coords never reads."""
     for t, name in ((f1_hi, "f1_hi"), (f2_hi, "f2_hi")):
         if not (t.is_cuda and t.dtype == torch.float16 and t.dim() == 3 and t.is_contiguous()):
             raise RuntimeError(f"{name} must be a contiguous CUDA fp16 tensor [T,P,C]")
@@ -667,6 +681,17 @@ def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj):
     E = ii.numel()
     vol = torch.empty(E, P, Q, dtype=torch.float32, device=f1_hi.device)
     null = ctypes.c_void_p(0)
+    if half_mask is not None:
+        if not (half_mask.is_cuda and half_mask.dtype == torch.int32 and half_mask.is_contiguous()
+                and half_mask.numel() == E * (P // 128)):
+            raise RuntimeError(f"half_mask must be a contiguous CUDA int32 vector of {E * (P // 128)} words")
+        with torch.cuda.device(f1_hi.device):
+            st = _lib.lib().lgu_build_volume_sparse(_p(f1_hi), _p(f1_lo) if split else null, _p(f2_hi),
+                                                    _p(f2_lo) if split else null, _p(ii), _p(jj), _p(half_mask), _p(vol),
+                                                    _i(T1), _i(T2), _i(E), _i(P), _i(Q), _i(C), _i(2 if split else 1),
+                                                    _stream(f1_hi))
+        _lib.check(st, "build_volume (sparse)")
+        return vol
     with torch.cuda.device(f1_hi.device):
         st = _lib.lib().lgu_build_volume(_p(f1_hi), _p(f1_lo) if split else null, _p(f2_hi), _p(f2_lo) if split else null,
                                          _p(ii), _p(jj), _p(vol), _i(T1), _i(T2), _i(E), _i(P), _i(Q), _i(C),

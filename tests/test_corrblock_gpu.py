@@ -466,3 +466,43 @@ def test_corrblock_lookup_encoded_matches_call_plus_corr_encoder():
             assert enc_only.shape == (1, 3, 128, 48, 64)
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("probes", [False, True])
+def test_sparse_level0_volume_is_what_the_backend_lookup_reads(probes):
+    """lgu_volume_half_mask + lgu_build_volume_sparse: the halves the mask names are bit-identical to the dense build,
+    and the fused backend lookup (per-corner gating, offsets bounded by 4 -- 4 * tanh, corr.py:121-128, including the
+    bound itself) returns the same bits from the sparse volume although everything else in it is NaN-poisoned scratch."""
+    from lgu_slam_b200 import ops
+    dev, E, H, W, T = "cuda", 5, 48, 64, 4
+    g = inputs.gen(77)
+    fm = (torch.randn(T, 128, H, W, generator=g) / 4).half().to(dev)
+    planes = []
+    cur = fm.float()
+    for l in range(4):
+        planes.append(cur.permute(0, 2, 3, 1).reshape(T, -1, 128).half().contiguous())
+        cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+    ii = torch.tensor([0, 1, 2, 3, 1], dtype=torch.int32, device=dev)
+    jj = torch.tensor([1, 2, 3, 0, 0], dtype=torch.int32, device=dev)
+    coords = inputs.make_coords(E, H, W, H, W, g, probes=probes).permute(0, 2, 3, 1).contiguous().to(dev)
+    off = [(4.0 * torch.tanh(3.0 * torch.randn(E, H, W, 98, generator=g))).to(dev).contiguous() for _ in range(2)]
+    off[0][0, 0, :, :] = 4.0                                      # the bound itself, both signs
+    off[0][0, 1, :, :] = -4.0
+    off[1][1, 0, :, :] = 4.0
+    dense = [ops.build_volume(planes[0], None, planes[l], None, ii, jj).view(E, H, W, H >> l, W >> l) for l in range(4)]
+    hm = ops.volume_half_mask(coords, 0)
+    assert hm.shape == (E * H * W // 128,)
+    poison = torch.full((E, H * W, H * W), float("nan"), device=dev)
+    del poison                                                    # the caching allocator hands this block to the next call
+    sparse0 = ops.build_volume(planes[0], None, planes[0], None, ii, jj, half_mask=hm).view(E, H, W, H, W)
+    bits = ((hm.view(E, H * W // 128, 1).long() & 0xffffffff) >> torch.arange(12, device=dev).view(1, 1, 12)) & 1   # [E,units,12]
+    frac = bits.float().mean().item()
+    assert 0.2 < frac < 1.0, f"mask density {frac}"
+    written = bits.bool().view(E, H * W // 128, 1, 12, 1, 1).expand(E, H * W // 128, 128, 12, 4, W)
+    written = written.reshape(E, H, W, H, W)
+    assert torch.equal(sparse0[written], dense[0][written])
+    want = ops.altcorr_lookup_fused(dense, coords, off[0], off[1].clone(), 3, shared_offsets=False, apply_mask=True)
+    got = ops.altcorr_lookup_fused([sparse0] + dense[1:], coords, off[0], off[1].clone(), 3, shared_offsets=False,
+                                   apply_mask=True)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))       # (NaN only where a probe coordinate produces one)
+    assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
