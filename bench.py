@@ -508,7 +508,7 @@ class BackendWorkload:
             def compute(c, i, j, out=None, out_index=None, pass_edges=None, pass_hook=None, key=None):
                 return self.blk(c, i, j, out=out, out_index=out_index, pass_edges=pass_edges, pass_hook=pass_hook, key=key)
             eng = self.sh.ShardedBackendCorr(compute, single_process=single)
-            plan = eng.set_edges(self.ii, self.jj)
+            plan = eng.set_edges(self.ii, self.jj, dst=None if single else 0)   # outputs go back to rank 0: it gets the lighter chunks
             mine = plan.rank_edges[eng.rank]
             import inputs
             coords = inputs.make_coords(int(mine.numel()), H, W, H, W, inputs.gen(9000 + 17 * eng.rank + (1 if single else 0)))
@@ -526,7 +526,9 @@ class BackendWorkload:
                     full[t] = torch.randn(C, H, W, generator=inputs.gen(7000 + t)).half()
                 self.all_maps_dev = full.to(self.dev)
             return self.all_maps_dev
-        return self.sh.all_gather_frames(maps_dev)                    # collective 1 (NCCL all_gather_into_tensor)
+        per = (self.T + self.world - 1) // self.world                  # the block layout of __init__: known on every rank
+        counts = [max(0, min(self.T, (r + 1) * per) - r * per) for r in range(self.world)]
+        return self.sh.all_gather_frames(maps_dev, counts=counts)     # collective 1 (NCCL all_gather_into_tensor)
 
     def step(self, mode, peer=None, single=False, coords=None, maps_dev=None):
         """mode 'peer': outputs returned to rank 0 through `peer`; 'sharded': outputs stay in `peer` = a local buffer."""

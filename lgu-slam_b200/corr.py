@@ -747,7 +747,18 @@ class AltCorrBlock:
 
     def _corr_materialized(self, coords, ii, jj, out=None, out_index=None, pass_edges=None, pass_hook=None, key=None):
         B, N, H, W, S, _ = coords.shape
-        step = min(self.MAX_EDGES_PER_PASS, int(pass_edges)) if pass_edges else self.MAX_EDGES_PER_PASS
+        # pass_edges: an int (edges per pass) or a sequence of pass sizes (the sharded engine tapers the passes of a rank's
+        # last chunk so that only a small shipment is left exposed at the end of the step)
+        if pass_edges is not None and not isinstance(pass_edges, int):
+            sizes = [min(self.MAX_EDGES_PER_PASS, max(1, int(x))) for x in pass_edges]
+        else:
+            sizes = [min(self.MAX_EDGES_PER_PASS, int(pass_edges)) if pass_edges else self.MAX_EDGES_PER_PASS]
+        bounds, s0, k = [], 0, 0
+        while s0 < N:
+            n = sizes[min(k, len(sizes) - 1)]
+            bounds.append((s0, min(N, s0 + n)))
+            s0 += n
+            k += 1
         assert B == 1 and S == 1, "the materialised path serves the reference's only call shape (B = S = 1)"
         planes = self._level_planes()
         c = coords.reshape(N, H, W, 2).float().contiguous()
@@ -777,8 +788,8 @@ class AltCorrBlock:
             mask0 = torch.sigmoid(torch.var(m0.permute(0, 1, 3, 4, 2).reshape(1, H, W, 9), dim=3))
             slab0 = (off0[:1].contiguous(), (off1[:1] * mask0.view(1, H, W, 1)).contiguous())
         outs, masks, new_off1 = [], [], []
-        for s in range(0, N, step):
-            e = slice(s, min(N, s + step))
+        for s, s_end in bounds:
+            e = slice(s, s_end)
             vols = ent["vols"].get(s) if ent is not None else None
             if vols is None:
                 # Level 0 is 3/4 of the volume bytes, and the lookup below reads it only inside a 20 x 16 box per source

@@ -63,15 +63,27 @@ def reference_chunks(ii: torch.Tensor, jj: torch.Tensor, frames_per_chunk: int =
     return chunks
 
 
+# What receiving one remote edge's output rows costs the destination rank, in units of one edge of its own compute: the
+# rows (1.2 MB of fp16) are written into its HBM while its own bandwidth-bound kernels run (1.2 MB / 6.5 TB/s against
+# 13.4 us per edge; measured at 8 GPUs: 9.3 ms with the outputs returned against 8.4 ms with them left sharded).
+DST_INGRESS_COST = 0.0138
+
+
 def partition_edges(ii: torch.Tensor, jj: torch.Tensor, world_size: int,
-                    frames_per_chunk: int = FRAMES_PER_CHUNK) -> EdgePlan:
+                    frames_per_chunk: int = FRAMES_PER_CHUNK, dst: Optional[int] = None,
+                    dst_ingress_cost: float = DST_INGRESS_COST) -> EdgePlan:
     """Longest-processing-time assignment of reference chunks to ranks (cost = edge count; ties by chunk order, so
-    the plan is deterministic and identical on every rank without communication)."""
+    the plan is deterministic and identical on every rank without communication).
+    dst (world_size > 2): the rank every output is returned to starts with a handicap -- the ingress of the other
+    ranks' rows competes with its own kernels for HBM bandwidth -- so it receives the lighter chunks."""
     if world_size < 1:
         raise ValueError("world_size must be >= 1")
     chunks = reference_chunks(ii, jj, frames_per_chunk)
     owner = [0] * len(chunks)
-    load = [0] * world_size
+    load = [0.0] * world_size
+    if dst is not None and world_size > 2:
+        total = sum(int(c.numel()) for c in chunks)
+        load[dst] = dst_ingress_cost * total * (world_size - 1) / world_size
     for c in sorted(range(len(chunks)), key=lambda c: (-chunks[c].numel(), c)):
         r = min(range(world_size), key=lambda r: (load[r], r))
         owner[c] = r
@@ -84,16 +96,19 @@ def partition_edges(ii: torch.Tensor, jj: torch.Tensor, world_size: int,
     return plan
 
 
-def all_gather_frames(local: torch.Tensor, group=None) -> torch.Tensor:
+def all_gather_frames(local: torch.Tensor, group=None, counts=None) -> torch.Tensor:
     """Collective 1: every rank contributes its contiguous block of keyframe feature maps [T_r, ...] (T_r may
-    differ between ranks); returns the whole buffer [sum T_r, ...] on every rank."""
+    differ between ranks); returns the whole buffer [sum T_r, ...] on every rank.
+    counts: the per-rank T_r if the caller knows them (saves a small collective and a host synchronisation per call)."""
     world = dist.get_world_size(group)
     if world == 1:
         return local
-    n = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    if counts is None:
+        n = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n, group=group)
+        counts = [int(c.item()) for c in counts]
+    counts = [int(c) for c in counts]
     tmax = max(counts)
     padded = local
     if local.shape[0] != tmax:
@@ -267,8 +282,9 @@ class ShardedBackendCorr:
         except (TypeError, ValueError):
             self._writes_in_place = self._has_pass_hook = self._takes_key = False
 
-    def set_edges(self, ii, jj, frames_per_chunk=FRAMES_PER_CHUNK):
-        self.plan = partition_edges(ii, jj, self.world, frames_per_chunk)
+    def set_edges(self, ii, jj, frames_per_chunk=FRAMES_PER_CHUNK, dst=None):
+        """dst: the rank the outputs will be returned to (lookup_into_peer / gather="dst"), if any -- see partition_edges."""
+        self.plan = partition_edges(ii, jj, self.world, frames_per_chunk, dst=dst)
         self._idx = {}
         return self.plan
 
@@ -339,6 +355,27 @@ class ShardedBackendCorr:
     # so it runs in passes of SHIP_EDGES edges and only its last pass's rows are exposed (37 edges x 24 row tiles = 6 full
     # waves of the 148-CTA volume build)
     SHIP_EDGES = 37
+    SHIP_TAIL = (18, 12, 6)            # 3 / 2 / 1 waves: the last, exposed shipment is 6 edges (7 MB of fp16 rows)
+    SHIP_ALL_CHUNKS = True             # every chunk in passes (the destination's NVLink ingress never idles), not only the last
+
+    @classmethod
+    def _ship_schedule(cls, n, last=True):
+        """Pass sizes of a chunk of n edges: passes of SHIP_EDGES; a rank's LAST chunk ends in the tapering tail.  The
+        destination's NVLink ingress is the scarce resource of the step (4.3 GB into rank 0 at 8 GPUs in ~9 ms): measured,
+        [104, 18, 6] for the last chunk is slower than [18, 37, 37, 18, 12, 6] (9.37 against 9.11 ms)."""
+        tail = list(cls.SHIP_TAIL) if last else []
+        if n <= sum(tail) or n <= cls.SHIP_EDGES:
+            return [cls.SHIP_EDGES]                                # small chunk: plain passes
+        body = n - sum(tail)
+        k, r = divmod(body, cls.SHIP_EDGES)
+        if 0 < r < 12:                                            # no tiny leading pass: fold it into its neighbour
+            if k:
+                return [cls.SHIP_EDGES + r] + [cls.SHIP_EDGES] * (k - 1) + tail
+            if tail:
+                tail[0] += r
+                return tail
+            return [r]
+        return ([r] if r else []) + [cls.SHIP_EDGES] * k + tail
 
     def lookup_into_peer(self, coords, ii, jj, peer: PeerOutput, sync=True, coords_are_local=False, via="store"):
         """gather="dst" with NO collective on the data path.  via="store": every rank runs its chunks with the destination
@@ -386,9 +423,10 @@ class ShardedBackendCorr:
                                 peer.buffer[a:a + n_run].copy_(stage[first + src:first + src + n_run], non_blocking=True)
 
                 kw = {"key": ("chunk", c)} if self._takes_key else {}
-                if self._has_pass_hook and k == len(plan.rank_chunks[self.rank]) - 1:     # ship pass by pass
-                    self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None, pass_edges=self.SHIP_EDGES, pass_hook=ship,
-                                 **kw)
+                nck = len(plan.rank_chunks[self.rank])
+                if self._has_pass_hook and (self.SHIP_ALL_CHUNKS or k == nck - 1):      # ship pass by pass
+                    self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None,
+                                 pass_edges=self._ship_schedule(nv, last=k == nck - 1), pass_hook=ship, **kw)
                 else:
                     self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None, **kw)
                     ship(0, nv)
