@@ -67,6 +67,8 @@ def reference_chunks(ii: torch.Tensor, jj: torch.Tensor, frames_per_chunk: int =
 # rows (1.2 MB of fp16) are written into its HBM while its own bandwidth-bound kernels run (1.2 MB / 6.5 TB/s against
 # 13.4 us per edge; measured at 8 GPUs: 9.3 ms with the outputs returned against 8.4 ms with them left sharded).
 DST_INGRESS_COST = 0.0138
+DST_HANDICAP_FROM = 8      # ranks from which the handicap is applied (measured there: 9.33 -> 9.11 ms; chunk granularity leaves
+                           # nothing to gain with fewer, larger shares)
 
 
 def partition_edges(ii: torch.Tensor, jj: torch.Tensor, world_size: int,
@@ -74,14 +76,14 @@ def partition_edges(ii: torch.Tensor, jj: torch.Tensor, world_size: int,
                     dst_ingress_cost: float = DST_INGRESS_COST) -> EdgePlan:
     """Longest-processing-time assignment of reference chunks to ranks (cost = edge count; ties by chunk order, so
     the plan is deterministic and identical on every rank without communication).
-    dst (world_size > 2): the rank every output is returned to starts with a handicap -- the ingress of the other
+    dst (world_size >= DST_HANDICAP_FROM): the rank every output is returned to starts with a handicap -- the ingress of the other
     ranks' rows competes with its own kernels for HBM bandwidth -- so it receives the lighter chunks."""
     if world_size < 1:
         raise ValueError("world_size must be >= 1")
     chunks = reference_chunks(ii, jj, frames_per_chunk)
     owner = [0] * len(chunks)
     load = [0.0] * world_size
-    if dst is not None and world_size > 2:
+    if dst is not None and world_size >= DST_HANDICAP_FROM:
         total = sum(int(c.numel()) for c in chunks)
         load[dst] = dst_ingress_cost * total * (world_size - 1) / world_size
     for c in sorted(range(len(chunks)), key=lambda c: (-chunks[c].numel(), c)):
@@ -356,7 +358,10 @@ class ShardedBackendCorr:
     # waves of the 148-CTA volume build)
     SHIP_EDGES = 37
     SHIP_TAIL = (18, 12, 6)            # 3 / 2 / 1 waves: the last, exposed shipment is 6 edges (7 MB of fp16 rows)
-    SHIP_ALL_CHUNKS = True             # every chunk in passes (the destination's NVLink ingress never idles), not only the last
+    SHIP_ALL_CHUNKS_FROM = 8           # from this many ranks on, EVERY chunk runs in passes (the destination's NVLink ingress is
+                                       # then the scarce resource and must never idle: 9.33 -> 9.08 ms at 8 GPUs); with fewer
+                                       # ranks only the last chunk does -- the extra passes cost more than they hide
+                                       # (2 GPUs: 28.7 -> 30.8 ms, 4 GPUs: 15.4 -> 16.4 ms with all chunks in passes)
 
     @classmethod
     def _ship_schedule(cls, n, last=True):
@@ -424,7 +429,7 @@ class ShardedBackendCorr:
 
                 kw = {"key": ("chunk", c)} if self._takes_key else {}
                 nck = len(plan.rank_chunks[self.rank])
-                if self._has_pass_hook and (self.SHIP_ALL_CHUNKS or k == nck - 1):      # ship pass by pass
+                if self._has_pass_hook and (self.world >= self.SHIP_ALL_CHUNKS_FROM or k == nck - 1):      # ship pass by pass
                     self.compute(cc, ii[vd], jj[vd], out=stage, out_index=None,
                                  pass_edges=self._ship_schedule(nv, last=k == nck - 1), pass_hook=ship, **kw)
                 else:
