@@ -18,6 +18,7 @@ struct BpParams {
   const float* means;   // [E,P,2] or null
   const float* covs;    // [E,P,2]
   const float* den;     // [E,P]
+  float* lvl0;          // [E,P,Q] (LSU store experiments of the 16-warp kernel; the production path stores through the TMA map)
   float* lvl1;          // [E,P,Q/4] or null (direct-store path)
   float* lvl2;          // [E,P,Q/16] or null
   float* lvl3;          // [E,P,Q/64] or null
@@ -28,6 +29,7 @@ struct BpParams {
   int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
   int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
   const uint32_t* half_mask;   // [num_units] or null: bit h set = accumulator half h (256 target columns) of the unit is built
+  int l0_lsu;   // 16-warp kernel: bit 0 / 1 = upper / lower row of a pair leaves through the LSU instead of the TMA store engine
   int dbg;      // experiment switches of build_pyramid16_kernel (LGU_BUILD_DBG; 0 in production)
 };
 
@@ -51,6 +53,7 @@ static inline bool env_flag(const char* name) {   // experiment switches of the 
 // (Forming the row-invariant ddy / cov_y once per window row instead of per tap was measured: 542 -> 553 us, reverted.)
 
 // The 16-epilogue-warp kernel (build_pyramid16.cu).  Returns LGU_OK / an error code.
-int launch_build16(const CUtensorMap& mh, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st);
+int launch_build16(const CUtensorMap& mh, const CUtensorMap& mb, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm,
+                   bool flat, cudaStream_t st);
 
 }  // namespace lgu

@@ -693,18 +693,20 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   if (const char* tp = getenv("LGU_BP_TRACE_PTR")) prm.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
 #endif
   prm.ii = ii; prm.jj = jj; prm.means = means; prm.covs = covs; prm.den = den;
-  prm.lvl1 = lvl1; prm.lvl2 = lvl2; prm.lvl3 = lvl3;
+  prm.lvl0 = lvl0; prm.lvl1 = lvl1; prm.lvl2 = lvl2; prm.lvl3 = lvl3;
   prm.E = E; prm.P = P; prm.H = H; prm.gauss_radius = gauss_radius; prm.round_half = round_half;
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = lvl1 != nullptr;
   prm.dbg = getenv("LGU_BUILD_DBG") ? atoi(getenv("LGU_BUILD_DBG")) : 0;
   prm.half_mask = nullptr;
+  // level-0 rows of the 16-warp kernel through the LSU (default, 537 -> 505 us at E = 48); LGU_BUILD_L0_TMA=1: TMA stores
+  prm.l0_lsu = env_flag("LGU_BUILD_L0_TMA") ? 0 : 3;
   prm.out_slots = out_slots;
   prm.Q = P;
   prm.halves = H / 4;
   // fp16-valued maps, all four levels: the 16-epilogue-warp kernel (build_pyramid16.cu); LGU_BUILD_EPI8=1 keeps this one
   if (precision == 1 && lvl1 != nullptr && lvl2 != nullptr && lvl3 != nullptr && !wide && !env_flag("LGU_BUILD_EPI8"))
-    return launch_build16(mh, m0, m1, prm, (cudaStream_t)stream);
+    return launch_build16(mh, mh, m0, m1, prm, false, (cudaStream_t)stream);
   if (precision == 1) return launch_build<1>(mh, ml, mh, ml, m0, m1, m0w, prm, (cudaStream_t)stream);
   return launch_build<2>(mh, ml, mh, ml, m0, m1, m0w, prm, (cudaStream_t)stream);
 }
@@ -749,15 +751,19 @@ static int build_volume_impl(const void* fmaps1_hi, const void* fmaps1_lo, const
   prm.wide = wide;
   prm.trace = nullptr;
   prm.ii = ii; prm.jj = jj; prm.means = nullptr; prm.covs = nullptr; prm.den = nullptr;
-  prm.lvl1 = nullptr; prm.lvl2 = nullptr; prm.lvl3 = nullptr;
+  prm.lvl0 = volume; prm.lvl1 = nullptr; prm.lvl2 = nullptr; prm.lvl3 = nullptr;
   prm.E = E; prm.P = P; prm.H = 0; prm.gauss_radius = 0; prm.round_half = 0;
   prm.num_units = E * (P / kTileM);
   prm.has_l1 = 0;
   prm.dbg = 0;
+  prm.l0_lsu = 0;
   prm.half_mask = half_mask;
   prm.out_slots = nullptr;
   prm.Q = Q;
   prm.halves = (Q + 255) / 256;
+  // fp16-valued maps (the backend's buffer): the 16-warp kernel with its barrier-free flat epilogue; LGU_VOLUME_EPI8=1 keeps
+  // the 8-warp kernel with the pair-shared 16 KB TMA boxes
+  if (precision == 1 && !env_flag("LGU_VOLUME_EPI8")) return launch_build16(mh, mbh, m0, m0, prm, true, (cudaStream_t)stream);
   if (precision == 1) return launch_build<1>(mh, ml, mbh, mbl, m0, m0, m0w, prm, (cudaStream_t)stream);
   return launch_build<2>(mh, ml, mbh, mbl, m0, m0, m0w, prm, (cudaStream_t)stream);
 }

@@ -44,10 +44,13 @@ constexpr int kBarOffset = kABytes + kStages * kStageBytes + kStoreBytes + kL1By
 constexpr int kSmemBytes = kBarOffset + 256 + 1024;
 }  // namespace b16
 
-template <bool L1_LSU>
+// FLAT: one [E,P,Q] volume of level-0 source maps x the maps behind map_b (lgu_build_volume: no Gaussian patch, no pooled
+// levels, any Q % 4 == 0, optional half mask) -- the epilogue is then barrier-free: tcgen05.ld -> staging tile -> LSU.
+template <bool L1_LSU, bool FLAT>
 __global__ void __launch_bounds__(b16::kThreads, 1)
-build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_l0,
-                       const __grid_constant__ CUtensorMap map_l1, const BpParams prm) {
+build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
+                       const BpParams prm) {
   using namespace b16;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by POINTER arithmetic on the shared array: an integer round trip makes every derived pointer
@@ -74,6 +77,7 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_hi);
+    prefetch_tmap(&map_b);
     prefetch_tmap(&map_l0);
     prefetch_tmap(&map_l1);
     mbar_init(a_full, 1);
@@ -106,16 +110,19 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         mbar_expect_tx(a_full, kABytes);
         tma_load_2d(sA, &map_hi, a_full, 0, a_row);
         tma_load_2d(sA + kAtomBytes, &map_hi, a_full, 64, a_row);
+        const uint32_t hmask = (FLAT && prm.half_mask != nullptr) ? __ldg(prm.half_mask + u) : 0xffffffffu;
         const int nchunks = halves * 2;
-        for (int c = 0; c < nchunks; ++c, ++chunk_it) {
+        for (int c = 0; c < nchunks; ++c) {
+          if (!((hmask >> (c >> 1)) & 1u)) continue;   // sparse volume: this half is never sampled (lgu_volume_half_mask)
           const int s = chunk_it % kStages;
           const uint32_t use = chunk_it / kStages;
+          ++chunk_it;
           mbar_wait(b_empty + s, (use & 1) ^ 1);
           uint8_t* dst = sB + s * kStageBytes;
           const int b_row = b_row0 + c * kChunkN;
           mbar_expect_tx(b_full + s, kStageBytes);
-          tma_load_2d(dst, &map_hi, b_full + s, 0, b_row);
-          tma_load_2d(dst + kAtomBytes, &map_hi, b_full + s, 64, b_row);
+          tma_load_2d(dst, &map_b, b_full + s, 0, b_row);
+          tma_load_2d(dst + kAtomBytes, &map_b, b_full + s, 64, b_row);
         }
       }
     }
@@ -127,8 +134,11 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
       uint32_t unit_it = 0, chunk_it = 0, half_it = 0;
       for (int u = blockIdx.x; u < prm.num_units; u += gridDim.x, ++unit_it) {
         mbar_wait(a_full, unit_it & 1);
-        for (int h = 0; h < halves; ++h, ++half_it) {
+        const uint32_t hmask = (FLAT && prm.half_mask != nullptr) ? __ldg(prm.half_mask + u) : 0xffffffffu;
+        for (int h = 0; h < halves; ++h) {
+          if (!((hmask >> h) & 1u)) continue;
           const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
+          ++half_it;
           mbar_wait(t_empty + buf, (buf_use & 1) ^ 1);
           tc_fence_after();
           for (int c = 0; c < 2; ++c, ++chunk_it) {
@@ -175,7 +185,7 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
     // stage one 32-float row segment per lane (single staging tile: the previous store must have been read) and hand the
     // 32 x 32 tile to the TMA store engine; patched values are read back into v (they feed the pooled levels)
     auto store_tile = [&](float (&v)[32], int col, int row0, bool patch, int yy, float mx, float my, float c1, float c2,
-                          float den, unsigned bx) {
+                          float den, unsigned bx, bool lsu) {
       {
         B16_T0();
         if (lane == 0) tma_wait_read<0>();
@@ -207,7 +217,19 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         }
       }
       B16_ADD(3);
-      {
+      if (lsu) {
+        // this row leaves through the LSU: a store instruction covers 4 rows x 128 contiguous bytes (lane = row % 4 x
+        // 16-byte chunk), no proxy fence, no bulk-group wait before the tile is staged again (537 -> 505 us at E = 48)
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3), ch = lane & 7;
+          const float4 vv = *reinterpret_cast<const float4*>(my_store + row * 128 + ((ch ^ (row & 7)) << 4));
+          if (!FLAT || col + ch * 4 < Q)                         // flat volumes: Q may end inside the last half
+            __stcs(reinterpret_cast<float4*>(prm.lvl0 + (size_t)(row0 + row) * (size_t)Q + col + ch * 4), vv);
+        }
+        __syncwarp();
+      } else {
         B16_T0();
         fence_proxy_async();
         __syncwarp();
@@ -239,8 +261,11 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
       }
       float l2_prev[4] = {0.f, 0.f, 0.f, 0.f};
 
-      for (int h = 0; h < halves; ++h, ++half_it) {
+      const uint32_t hmask = (FLAT && prm.half_mask != nullptr) ? __ldg(prm.half_mask + u) : 0xffffffffu;
+      for (int h = 0; h < halves; ++h) {
+        if (!((hmask >> h) & 1u)) continue;
         const uint32_t buf = half_it & 1, buf_use = half_it >> 1;
+        ++half_it;
         {
           B16_T0();
           mbar_wait(t_full + buf, buf_use & 1);
@@ -262,9 +287,11 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
             for (int i = 0; i < 32; ++i) a[i] = __half2float(__float2half_rn(a[i]));
           }
           const bool pa = gr > 0 && ((unsigned)ya - by) < rdg;
-          store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx);
+          store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx, FLAT || (prm.l0_lsu & 1) != 0);
+          if (!FLAT) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) ha[i] = __fadd_rn(a[2 * i], a[2 * i + 1]);
+            for (int i = 0; i < 16; ++i) ha[i] = __fadd_rn(a[2 * i], a[2 * i + 1]);
+          }
         }
         {
           float b[32];
@@ -281,7 +308,8 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
             for (int i = 0; i < 32; ++i) b[i] = __half2float(__float2half_rn(b[i]));
           }
           const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
-          store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx);
+          store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx, FLAT || (prm.l0_lsu & 2) != 0);
+          if (FLAT) continue;                                   // no pooled levels: nothing to exchange, no barrier
           // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
 #pragma unroll
           for (int i = 0; i < 16; ++i) l1[i] = __fmul_rn(__fadd_rn(__fadd_rn(ha[i], b[2 * i]), b[2 * i + 1]), 0.25f);
@@ -363,17 +391,19 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-int launch_build16(const CUtensorMap& mh, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm, cudaStream_t st) {
+int launch_build16(const CUtensorMap& mh, const CUtensorMap& mb, const CUtensorMap& m0, const CUtensorMap& m1, const BpParams& prm,
+                   bool flat, cudaStream_t st) {
   // level-1 tiles through the LSU (default; 559 -> 540 us at E = 48); LGU_BUILD_L1_TMA=1: through the TMA store engine
   const bool l1_lsu = !env_flag("LGU_BUILD_L1_TMA") && prm.lvl1 != nullptr;
-  auto kern = l1_lsu ? build_pyramid16_kernel<true> : build_pyramid16_kernel<false>;
+  auto kern = flat ? build_pyramid16_kernel<true, true>
+                   : (l1_lsu ? build_pyramid16_kernel<true, false> : build_pyramid16_kernel<false, false>);
   if (int rc = optin_smem(reinterpret_cast<const void*>(kern), b16::kSmemBytes, "lgu_build_pyramid")) return rc;
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = prm.num_units < sms ? prm.num_units : sms;
-  kern<<<grid, b16::kThreads, b16::kSmemBytes, st>>>(mh, m0, m1, prm);
-  return check_launch("lgu_build_pyramid(16)");
+  kern<<<grid, b16::kThreads, b16::kSmemBytes, st>>>(mh, mb, m0, m1, prm);
+  return check_launch(flat ? "lgu_build_volume(16)" : "lgu_build_pyramid(16)");
 }
 
 }  // namespace lgu
