@@ -182,11 +182,11 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
     const long long tr_begin = clock64();
 #endif
 
-    // stage one 32-float row segment per lane (single staging tile: the previous store must have been read) and hand the
-    // 32 x 32 tile to the TMA store engine; patched values are read back into v (they feed the pooled levels)
-    auto store_tile = [&](float (&v)[32], int col, int row0, bool patch, int yy, float mx, float my, float c1, float c2,
-                          float den, unsigned bx, bool lsu) {
-      {
+    // stage_tile: one 32-float row segment per lane into the warp's swizzled staging tile (the previous flush must have read
+    // it), Gaussian window patched in shared memory, patched values read back into v (they feed the pooled levels).
+    auto stage_tile = [&](float (&v)[32], bool patch, int yy, float mx, float my, float c1, float c2, float den, unsigned bx,
+                          bool lsu) {
+      if (!lsu) {
         B16_T0();
         if (lane == 0) tma_wait_read<0>();
         __syncwarp();
@@ -217,16 +217,28 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         }
       }
       B16_ADD(3);
+    };
+    // flush_tile: the staged 32 x 32 tile to global memory.  LSU (default): a store instruction covers 4 rows x 128
+    // contiguous bytes (lane = row % 4 x 16-byte chunk) -- full lines, no proxy fence, no bulk-group wait before the tile is
+    // staged again (537 -> 505 us at E = 48 against TMA tile stores); loads in batches of four so that the stores do not
+    // serialise on one register quad.  Otherwise: one TMA tile store.
+    auto flush_tile = [&](int col, int row0, bool lsu) {
       if (lsu) {
-        // this row leaves through the LSU: a store instruction covers 4 rows x 128 contiguous bytes (lane = row % 4 x
-        // 16-byte chunk), no proxy fence, no bulk-group wait before the tile is staged again (537 -> 505 us at E = 48)
         __syncwarp();
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + (lane >> 3), ch = lane & 7;
-          const float4 vv = *reinterpret_cast<const float4*>(my_store + row * 128 + ((ch ^ (row & 7)) << 4));
-          if (!FLAT || col + ch * 4 < Q)                         // flat volumes: Q may end inside the last half
-            __stcs(reinterpret_cast<float4*>(prm.lvl0 + (size_t)(row0 + row) * (size_t)Q + col + ch * 4), vv);
+        for (int it0 = 0; it0 < 8; it0 += 4) {
+          float4 q[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = (it0 + j) * 4 + (lane >> 3), ch = lane & 7;
+            q[j] = *reinterpret_cast<const float4*>(my_store + row * 128 + ((ch ^ (row & 7)) << 4));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = (it0 + j) * 4 + (lane >> 3), ch = lane & 7;
+            if (!FLAT || col + ch * 4 < Q)                       // flat volumes: Q may end inside the last half
+              __stcs(reinterpret_cast<float4*>(prm.lvl0 + (size_t)(row0 + row) * (size_t)Q + col + ch * 4), q[j]);
+          }
         }
         __syncwarp();
       } else {
@@ -275,6 +287,8 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         const uint32_t tcol = tmem_base + lane_base + buf * 256 + xs * 32;
         const int ya = 4 * h + 2 * rp, yb = ya + 1;
         float ha[16], l1[16];
+        const bool lsu_a = FLAT || (prm.l0_lsu & 1) != 0, lsu_b = FLAT || (prm.l0_lsu & 2) != 0;
+        uint32_t braw[32];
         {
           float a[32];
           {
@@ -287,17 +301,21 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
             for (int i = 0; i < 32; ++i) a[i] = __half2float(__float2half_rn(a[i]));
           }
           const bool pa = gr > 0 && ((unsigned)ya - by) < rdg;
-          store_tile(a, ya * 64 + x0, row0, pa, ya, mx, my, c1, c2, den, bx, FLAT || (prm.l0_lsu & 1) != 0);
+          stage_tile(a, pa, ya, mx, my, c1, c2, den, bx, lsu_a);
           if (!FLAT) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) ha[i] = __fadd_rn(a[2 * i], a[2 * i + 1]);
           }
         }
+        tmem_ld32_issue(tcol + (2 * rp + 1) * 64, braw);          // the lower row travels while the upper row is flushed
+        flush_tile(ya * 64 + x0, row0, lsu_a);
         {
           float b[32];
           {
             B16_T0();
-            tmem_ld32(tcol + (2 * rp + 1) * 64, b);
+            tmem_ld32_wait(braw);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) b[i] = __uint_as_float(braw[i]);
             B16_ADD(1);
           }
           tc_fence_before();                            // last TMEM read of this half by this warp
@@ -308,12 +326,16 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
             for (int i = 0; i < 32; ++i) b[i] = __half2float(__float2half_rn(b[i]));
           }
           const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
-          store_tile(b, yb * 64 + x0, row0, pb, yb, mx, my, c1, c2, den, bx, FLAT || (prm.l0_lsu & 2) != 0);
-          if (FLAT) continue;                                   // no pooled levels: nothing to exchange, no barrier
+          stage_tile(b, pb, yb, mx, my, c1, c2, den, bx, lsu_b);
+          if (FLAT) {                                           // no pooled levels: nothing to exchange, no barrier
+            flush_tile(yb * 64 + x0, row0, lsu_b);
+            continue;
+          }
           // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)
 #pragma unroll
           for (int i = 0; i < 16; ++i) l1[i] = __fmul_rn(__fadd_rn(__fadd_rn(ha[i], b[2 * i]), b[2 * i + 1]), 0.25f);
         }
+        flush_tile(yb * 64 + x0, row0, lsu_b);
         // ---- level 1: quadrant barrier A (the tiles of the previous half were read by the engine -- the issuer's
         // wait_read before its level-0 stores of this half -- and by every warp's level-2 pass), stage, barrier B, store
         {
