@@ -408,3 +408,57 @@ def test_fused_lookup_forward_at_bench_shape_vs_reference_ops(bind):
     # level 1: its offsets carry sigmoid(var) -- a few ulp apart between torch's reduction and the kernel's -- times the
     # local slope of a white-noise pyramid (|V| up to ~5): 1e-5 relative to the largest value
     _close(got[:, 49:98], want[:, 49:98], "level 1")
+
+
+@pytest.mark.parametrize("E", [4, 48])
+def test_bench_step_backward_with_folded_gaussian_head_vs_reference_autograd(bind, E):
+    """The backward half of bench.py's step -- lgu_corr_lookup_fused_backward_gauss: one launch that returns the level and
+    offset gradients AND the Gaussian head's (means, covs, den) gradients -- against autograd through the reference's own
+    Python: GaussianMaskCuda (gaussianMask_cuda.py:7-24) / den + corr (:84-86), 3 x avg_pool2d (corr.py:83-86) and
+    CorrBlock.__call__ (corr.py:88-109), all on the reference's compiled kernels.  E = 48 is the bench shape."""
+    dev = "cuda"
+    g = inputs.gen(900 + E)
+    import torch.nn.functional as F
+    GaussFn = bind.A[1].GaussianMaskCuda
+    raw = (torch.randn(E, H, W, H, W, generator=g) * 2).to(dev)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    mean0 = (torch.stack([xs, ys], -1)[None] + 1.5 * torch.randn(E, H, W, 2, generator=g)).to(dev)
+    mean0[0, 0, 0] = torch.tensor([-2.5, 1.25]); mean0[0, 0, 1] = torch.tensor([65.0, 49.0])     # windows over the borders
+    cov0 = (torch.rand(E, H, W, 2, generator=g) * 5 + 0.05).to(dev)
+    den0 = (6.28 * torch.sqrt(cov0[..., 0] * cov0[..., 1])).contiguous()
+    off_a = (4 * torch.tanh(torch.randn(E, 98, H, W, generator=g))).to(dev)
+    off_b = (4 * torch.tanh(torch.randn(E, 98, H, W, generator=g))).to(dev)
+    coords = _coords(E, g).to(dev)
+    w = (torch.randn(1, E, 196, H, W, generator=g)).to(dev)
+    # ---- the reference graph
+    mean, cov, den = mean0.clone().requires_grad_(), cov0.clone().requires_grad_(), den0.clone().requires_grad_()
+    o0, o1 = off_a.clone().requires_grad_(), off_b.clone().requires_grad_()
+    corr1 = GaussFn.apply(mean, cov, raw, 4) / den.view(E, H, W, 1, 1) + raw
+    cur = corr1.reshape(E * H * W, 1, H, W)
+    pyr = []
+    for l in range(4):
+        pyr.append(cur.view(E, H, W, H >> l, W >> l))
+        cur = F.avg_pool2d(cur, 2, stride=2)
+    offs = [o0.permute(0, 2, 3, 1), o1.permute(0, 2, 3, 1)]
+    offs += [torch.zeros_like(offs[0]).detach(), torch.zeros_like(offs[0]).detach()]
+    blk = _bare_block(bind.A[0].CorrBlock, pyr, offs, E)
+    out, _, _ = blk(coords)
+    (out * w).sum().backward()
+    want = dict(out=out.detach(), gm=mean.grad, gc=cov.grad, gd=den.grad, g0=o0.grad, g1=o1.grad)
+    # ---- ours, on the same pyramid values
+    ops = bind.ops
+    pyr_d = [p.detach().contiguous() for p in pyr]
+    del blk, corr1, cur
+    c = coords.view(E, H, W, 2).contiguous()
+    a0 = off_a.permute(0, 2, 3, 1).contiguous()
+    a1 = off_b.permute(0, 2, 3, 1).contiguous()
+    cum = torch.ones(E, H, W, device=dev)
+    corr, mask = ops.corr_lookup_fused(pyr_d, c, a0, a1, 3, return_mask=True, cum_mask=cum)
+    _close(corr, want["out"].view(E, 196, H, W), "lookup")
+    res = ops.corr_lookup_fused_backward(pyr_d, c, a0, a1, mask, w.view(E, 196, H, W).contiguous(), cum_mask=cum,
+                                         gauss_head=(mean0.contiguous(), cov0.contiguous(), den0))
+    _close(res[6], want["gm"], "grad means")
+    _close(res[7], want["gc"], "grad covs")
+    _close(res[8], want["gd"], "grad den")
+    _close(res[4].view(E, H, W, 98).permute(0, 3, 1, 2), want["g0"], "grad offset[0]")
+    _close(res[5].view(E, H, W, 98).permute(0, 3, 1, 2), want["g1"], "grad offset[1]")
