@@ -186,7 +186,7 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
     // it), Gaussian window patched in shared memory, patched values read back into v (they feed the pooled levels).
     auto stage_tile = [&](float (&v)[32], bool patch, int yy, float mx, float my, float c1, float c2, float den, unsigned bx,
                           bool lsu) {
-      if (!lsu) {
+      if (!lsu || (!FLAT && prm.l0_lsu != 3)) {                  // a TMA store of this tile may still be reading it
         B16_T0();
         if (lane == 0) tma_wait_read<0>();
         __syncwarp();
