@@ -469,7 +469,7 @@ def test_corrblock_lookup_encoded_matches_call_plus_corr_encoder():
 
 
 @pytest.mark.parametrize("probes", [False, True])
-def test_sparse_level0_volume_is_what_the_backend_lookup_reads(probes):
+def test_sparse_volumes_are_what_the_backend_lookup_reads(probes):
     """lgu_volume_half_mask + lgu_build_volume_sparse: the halves the mask names are bit-identical to the dense build,
     and the fused backend lookup (per-corner gating, offsets bounded by 4 -- 4 * tanh, corr.py:121-128, including the
     bound itself) returns the same bits from the sparse volume although everything else in it is NaN-poisoned scratch."""
@@ -492,6 +492,7 @@ def test_sparse_level0_volume_is_what_the_backend_lookup_reads(probes):
     dense = [ops.build_volume(planes[0], None, planes[l], None, ii, jj).view(E, H, W, H >> l, W >> l) for l in range(4)]
     hm = ops.volume_half_mask(coords, 0)
     assert hm.shape == (E * H * W // 128,)
+    hm1 = ops.volume_half_mask(coords, 1)
     poison = torch.full((E, H * W, H * W), float("nan"), device=dev)
     del poison                                                    # the caching allocator hands this block to the next call
     sparse0 = ops.build_volume(planes[0], None, planes[0], None, ii, jj, half_mask=hm).view(E, H, W, H, W)
@@ -502,7 +503,10 @@ def test_sparse_level0_volume_is_what_the_backend_lookup_reads(probes):
     written = written.reshape(E, H, W, H, W)
     assert torch.equal(sparse0[written], dense[0][written])
     want = ops.altcorr_lookup_fused(dense, coords, off[0], off[1].clone(), 3, shared_offsets=False, apply_mask=True)
-    got = ops.altcorr_lookup_fused([sparse0] + dense[1:], coords, off[0], off[1].clone(), 3, shared_offsets=False,
+    poison = torch.full((E, H * W, H * W // 4), float("nan"), device=dev)
+    del poison
+    sparse1 = ops.build_volume(planes[0], None, planes[1], None, ii, jj, half_mask=hm1).view(E, H, W, H // 2, W // 2)
+    got = ops.altcorr_lookup_fused([sparse0, sparse1] + dense[2:], coords, off[0], off[1].clone(), 3, shared_offsets=False,
                                    apply_mask=True)
     assert torch.equal(torch.isnan(got), torch.isnan(want))       # (NaN only where a probe coordinate produces one)
     assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
