@@ -64,6 +64,47 @@ def test_partition_covers_every_edge_once_and_balances(world):
     assert plan2.chunk_owner == plan.chunk_owner
 
 
+def test_partition_with_a_destination_rank_gives_it_the_lighter_share():
+    """Outputs returned to one rank: from DST_HANDICAP_FROM ranks on, the destination starts the LPT assignment with a
+    handicap (the other ranks' rows arrive in its HBM while its own kernels run), so it ends with no more edges than any
+    other rank; every edge is still assigned exactly once, chunks are never split, and the plan is deterministic."""
+    sh = _sharded()
+    ii, jj = _edges(T=256, E=4096, seed=3)
+    world = sh.DST_HANDICAP_FROM
+    plain = sh.partition_edges(ii, jj, world)
+    plan = sh.partition_edges(ii, jj, world, dst=0)
+    assert sorted(torch.cat(plan.rank_edges).tolist()) == sorted(torch.cat(plain.rank_edges).tolist())
+    for c, own in enumerate(plan.chunk_owner):
+        assert set(plan.chunk_edges[c].tolist()) <= set(plan.rank_edges[own].tolist())
+    counts = plan.counts()
+    assert counts[0] == min(counts) and counts[0] <= plain.counts()[0]
+    assert max(counts) <= 1.25 * (sum(counts) / world) + 1
+    assert sh.partition_edges(ii.clone(), jj.clone(), world, dst=0).chunk_owner == plan.chunk_owner
+    # below that rank count the destination is an ordinary rank
+    assert sh.partition_edges(ii, jj, 2, dst=0).chunk_owner == sh.partition_edges(ii, jj, 2).chunk_owner
+
+
+@pytest.mark.parametrize("n", [1, 5, 36, 37, 40, 48, 73, 100, 128, 154, 256, 300])
+def test_ship_schedule_covers_the_chunk(n):
+    """Pass sizes of a chunk whose rows are shipped pass by pass (sharded.ShardedBackendCorr._ship_schedule): they cover
+    the chunk (the consumer repeats the last size and clips the last pass), a rank's last chunk ends in the tapering
+    tail, and no pass is tiny."""
+    sh = _sharded()
+    S = sh.ShardedBackendCorr
+    for last in (False, True):
+        sizes = S._ship_schedule(n, last=last)
+        assert all(x > 0 for x in sizes)
+        covered, k = 0, 0
+        while covered < n:                                        # how AltCorrBlock._corr_materialized walks the schedule
+            covered += sizes[min(k, len(sizes) - 1)]
+            k += 1
+        if len(sizes) > 1:
+            assert sum(sizes) == n
+            assert all(x >= 6 for x in sizes)
+        if last and n > sum(S.SHIP_TAIL) and n > S.SHIP_EDGES:
+            assert tuple(sizes[-len(S.SHIP_TAIL):])[1:] == S.SHIP_TAIL[1:]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
