@@ -14,6 +14,7 @@ instead.  What differs is underneath:
 The learned heads (ofsMap / ofs_residual convs, the GaussianMask MLP) stay torch modules, as in the reference.
 """
 import math
+import os
 import weakref
 
 import torch
@@ -675,7 +676,7 @@ class AltCorrBlock:
     MAX_EDGES_PER_PASS = 256          # scratch bound: 256 x 50 MB = 12.8 GB
 
     def __init__(self, ofsMap, ofs_residual, GA, fmaps, num_levels=4, radius=3, strict_ref=True, materialize=None,
-                 sampler_ops=None, cache=False, volume_cache_gb=None, sparse_volumes=True):
+                 sampler_ops=None, cache=False, volume_cache_gb=None, sparse_volumes=True, compact_boxes=True):
         """sparse_volumes (materialised path, volumes not cached): level 0 is built only where the lookup's per-pixel
         boxes can reach (lgu_volume_half_mask / lgu_build_volume_sparse); results are identical.
         cache (materialised path only): global BA calls the SAME block for the same chunks in every one of its
@@ -693,6 +694,7 @@ class AltCorrBlock:
         `clear_cache()` drops everything (call it when the feature maps change)."""
         self.cache = bool(cache)
         self.sparse_volumes = bool(sparse_volumes)
+        self.compact_boxes = bool(compact_boxes) and os.environ.get("LGU_NO_COMPACT_BOXES", "") in ("", "0")
         self._cache = {}
         self._vol_bytes = 0
         if volume_cache_gb is None and self.cache and fmaps.is_cuda:
@@ -791,16 +793,23 @@ class AltCorrBlock:
         for s, s_end in bounds:
             e = slice(s, s_end)
             vols = ent["vols"].get(s) if ent is not None else None
+            boxes0 = None
             if vols is None:
                 # Level 0 is 3/4 of the volume bytes, and the lookup below reads it only inside a 20 x 16 box per source
                 # pixel (offsets are 4 * tanh, corr.py:121-128): build only the row bands those boxes touch.  Not when the
                 # volumes are kept for later calls with other coords (the per-chunk cache).
                 sparse = self.sparse_volumes and self._vol_budget == 0 and (H * W) % 128 == 0 and 256 % W == 0
                 hm = ops.volume_half_mask(c[e], 0) if sparse else None
-                vols = [ops.build_volume(planes[0][0], planes[0][1], planes[l][0], planes[l][1], ii32[e], jj32[e],
-                                         half_mask=hm if l == 0 else None)
-                        .view(-1, H, W, H >> l, W >> l) for l in range(self.num_levels)]
-                nbytes = sum(v.numel() * 4 for v in vols)
+                # ... and with fp16-valued maps (the backend's buffer) and W = 64 level 0 is not written as rows at all:
+                # every source pixel keeps just the 16 x 20 box the lookup stages (1.3 KB instead of 7.6 KB of rows)
+                boxes0 = None
+                if sparse and self.compact_boxes and W == 64 and planes[0][1] is None:
+                    boxes0 = ops.build_boxes(planes[0][0], planes[0][0], ii32[e], jj32[e], c[e], half_mask=hm)
+                vols = [None if (l == 0 and boxes0 is not None) else
+                        ops.build_volume(planes[0][0], planes[0][1], planes[l][0], planes[l][1], ii32[e], jj32[e],
+                                         half_mask=hm if l == 0 else None).view(-1, H, W, H >> l, W >> l)
+                        for l in range(self.num_levels)]
+                nbytes = sum(v.numel() * 4 for v in vols if v is not None)
                 if ent is not None and self._vol_bytes + nbytes <= self._vol_budget:
                     ent["vols"][s] = vols
                     self._vol_bytes += nbytes
@@ -810,15 +819,15 @@ class AltCorrBlock:
                 if out is not None else {}
             if self.strict_ref:
                 o, m = ops.altcorr_lookup_fused(vols, c[e], slab0[0], slab0[1], self.radius, shared_offsets=True,
-                                                apply_mask=False, return_mask=True, **dst)
+                                                apply_mask=False, return_mask=True, boxes0=boxes0, **dst)
             else:
                 o1 = off1[e].clone()                                      # updated in place: offset[1] * mask
                 o, m = ops.altcorr_lookup_fused(vols, c[e], off0[e].contiguous(), o1, self.radius, shared_offsets=False,
-                                                apply_mask=True, return_mask=True, **dst)
+                                                apply_mask=True, return_mask=True, boxes0=boxes0, **dst)
                 new_off1.append(o1)
             outs.append(o)
             masks.append(m)
-            del vols
+            del vols, boxes0
             if pass_hook is not None:                             # rows e.start .. e.stop of this call are enqueued
                 pass_hook(e.start, e.stop)
         # the attribute the reference leaves behind: offset[1] * mask (corr.py:206)

@@ -699,6 +699,7 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   prm.has_l1 = lvl1 != nullptr;
   prm.dbg = getenv("LGU_BUILD_DBG") ? atoi(getenv("LGU_BUILD_DBG")) : 0;
   prm.half_mask = nullptr;
+  prm.boxes = nullptr; prm.box_coords = nullptr;
   // level-0 rows of the 16-warp kernel through the LSU (default, 537 -> 505 us at E = 48); LGU_BUILD_L0_TMA=1: TMA stores
   prm.l0_lsu = env_flag("LGU_BUILD_L0_TMA") ? 0 : 3;
   prm.out_slots = out_slots;
@@ -713,10 +714,12 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
 
 static int build_volume_impl(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
                              const void* fmaps2_lo, const int32_t* ii, const int32_t* jj, float* volume, int T1,
-                             int T2, int E, int P, int Q, int C, int precision, const uint32_t* half_mask, void* stream) {
+                             int T2, int E, int P, int Q, int C, int precision, const uint32_t* half_mask, void* stream,
+                             float* boxes = nullptr, const float* box_coords = nullptr) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
-  LGU_REQUIRE(fmaps1_hi && fmaps2_hi && ii && jj && volume, "lgu_build_volume: null pointer");
+  LGU_REQUIRE(fmaps1_hi && fmaps2_hi && ii && jj && (volume || boxes), "lgu_build_volume: null pointer");
+  if (boxes != nullptr) volume = boxes;                        // (tensor maps of the unused volume path need a valid base)
   LGU_REQUIRE(precision == 1 || precision == 2, "lgu_build_volume: precision must be 1 or 2");
   LGU_REQUIRE(precision == 1 || (fmaps1_lo && fmaps2_lo), "lgu_build_volume: precision 2 needs the lo planes");
   LGU_REQUIRE(T1 > 0 && T2 > 0 && E > 0 && P > 0 && Q > 0, "lgu_build_volume: bad sizes");
@@ -758,12 +761,14 @@ static int build_volume_impl(const void* fmaps1_hi, const void* fmaps1_lo, const
   prm.dbg = 0;
   prm.l0_lsu = 0;
   prm.half_mask = half_mask;
+  prm.boxes = boxes; prm.box_coords = box_coords; prm.H = boxes != nullptr ? Q / 64 : 0;
   prm.out_slots = nullptr;
   prm.Q = Q;
   prm.halves = (Q + 255) / 256;
   // fp16-valued maps (the backend's buffer): the 16-warp kernel with its barrier-free flat epilogue; LGU_VOLUME_EPI8=1 keeps
   // the 8-warp kernel with the pair-shared 16 KB TMA boxes
-  if (precision == 1 && !env_flag("LGU_VOLUME_EPI8")) return launch_build16(mh, mbh, m0, m0, prm, true, (cudaStream_t)stream);
+  if (precision == 1 && (boxes != nullptr || !env_flag("LGU_VOLUME_EPI8")))
+    return launch_build16(mh, mbh, m0, m0, prm, true, (cudaStream_t)stream);
   if (precision == 1) return launch_build<1>(mh, ml, mbh, mbl, m0, m0, m0w, prm, (cudaStream_t)stream);
   return launch_build<2>(mh, ml, mbh, mbl, m0, m0, m0w, prm, (cudaStream_t)stream);
 }
@@ -783,6 +788,25 @@ extern "C" int lgu_build_volume_sparse(const void* fmaps1_hi, const void* fmaps1
   LGU_REQUIRE(Q <= 32 * 256, "lgu_build_volume_sparse: more than 32 halves (Q = %d)", Q);
   return build_volume_impl(fmaps1_hi, fmaps1_lo, fmaps2_hi, fmaps2_lo, ii, jj, volume, T1, T2, E, P, Q, C, precision,
                            half_mask, stream);
+}
+
+// Level 0 of the backend path as COMPACT boxes: for every source pixel only the 16 x 20 window of its correlation slice that
+// lgu_altcorr_lookup_boxes_into stages around coords (rows box_origin_y(floor(cy), 7, H) .. + 15, columns
+// box_origin_x(floor(cx), 7, W) .. + 19, zeros outside the H x W grid) -- 1280 bytes per pixel instead of the rows of a 12 KB
+// slice.  Same MMAs and the same half mask as lgu_build_volume_sparse; fp16-valued maps, W = 64.
+extern "C" int lgu_build_boxes(const void* fmaps1_hi, const void* fmaps2_hi, const int32_t* ii, const int32_t* jj,
+                               const float* coords, const uint32_t* half_mask, float* boxes, int T1, int T2, int E, int H,
+                               int W, int C, void* stream) {
+  if (E == 0) return LGU_OK;
+  LGU_REQUIRE(coords && half_mask && boxes, "lgu_build_boxes: null pointer");
+  LGU_REQUIRE(((reinterpret_cast<uintptr_t>(boxes) & 15) | (reinterpret_cast<uintptr_t>(coords) & 7)) == 0,
+              "lgu_build_boxes: boxes must be 16-byte, coords 8-byte aligned");
+  if (W != 64 || H <= 0 || (H % 4) != 0 || H * W > 32 * 256) {
+    lgu::set_error("lgu_build_boxes: needs W = 64 and H %% 4 == 0 with at most 32 halves (got H=%d W=%d)", H, W);
+    return LGU_ERR_UNSUPPORTED;
+  }
+  return build_volume_impl(fmaps1_hi, nullptr, fmaps2_hi, nullptr, ii, jj, nullptr, T1, T2, E, H * W, H * W, C, 1, half_mask,
+                           stream, boxes, coords);
 }
 
 namespace lgu {

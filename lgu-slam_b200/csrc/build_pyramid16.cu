@@ -18,6 +18,7 @@
 //     quarter of the level-2 row (4 columns, one 16-byte store per lane) and, every second half, 2 columns of level 3.
 // Shared memory: A 32 KB + 3 x 32 KB operand stages + 16 x 4 KB level-0 staging + 8 x 4 KB level-1 tiles = 224 KB.
 #include "build_common.cuh"
+#include "fused_common.cuh"
 
 // LGU_B16_TRACE (diagnostic builds only, tools/diag/b16_trace.py): per epilogue warp, cycles in (0) waiting for the
 // accumulator half, (1) the two tcgen05.ld, (2) waiting for the staging tile to be free, (3) staging writes + Gaussian patch,
@@ -272,6 +273,43 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         by = (unsigned)floor_to_int(my) - (unsigned)gr;
       }
       float l2_prev[4] = {0.f, 0.f, 0.f, 0.f};
+      // compact mode: this lane's source pixel keeps only the 16 x 20 box the backend lookup stages around its coordinate
+      int cbx = 0, cby = 0;
+      float* cbox = nullptr;
+      if (FLAT && prm.boxes != nullptr) {
+        const float2 cc = __ldg(reinterpret_cast<const float2*>(prm.box_coords) + pix);
+        cbx = box_origin_x(floor_to_int(cc.x), 7, 64);
+        cby = box_origin_y(floor_to_int(cc.y), 7, prm.H);
+        cbox = prm.boxes + pix * (size_t)(fl::kBW01 * fl::kBH01);
+        if (sub == 0) {                                         // box rows outside the grid: no half produces them
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = 0; r < fl::kBH01; ++r)
+            if ((unsigned)(cby + r) >= (unsigned)prm.H) {
+#pragma unroll
+              for (int j = 0; j < fl::kBW01 / 4; ++j) *reinterpret_cast<float4*>(cbox + r * fl::kBW01 + 4 * j) = z4;
+            }
+        }
+      }
+      // one staged row of this warp (target row yy, its 32 columns) -> this lane's box row: the 16-byte chunks of the box that
+      // fall into this warp's column half come from the lane's OWN staged row (no transposition), chunks left / right of the
+      // grid are zeros (the xs = 0 / xs = 1 warp writes them)
+      auto box_row = [&](int yy) {
+        const int r = yy - cby;
+        if ((unsigned)r < (unsigned)fl::kBH01) {
+          const float4* rowp = reinterpret_cast<const float4*>(my_store + lane * 128);
+          float* dst = cbox + r * fl::kBW01;
+#pragma unroll
+          for (int j = 0; j < fl::kBW01 / 4; ++j) {
+            const int cg = (cbx >> 2) + j;                      // chunk of the 64-column target row (cbx % 4 == 0)
+            const bool mine = xs == 0 ? cg < 8 : cg >= 8;
+            if (mine) {
+              float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if ((unsigned)cg < 16u) v4 = rowp[(cg - 8 * xs) ^ rsw];
+              *reinterpret_cast<float4*>(dst + 4 * j) = v4;
+            }
+          }
+        }
+      };
 
       const uint32_t hmask = (FLAT && prm.half_mask != nullptr) ? __ldg(prm.half_mask + u) : 0xffffffffu;
       for (int h = 0; h < halves; ++h) {
@@ -308,7 +346,13 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
           }
         }
         tmem_ld32_issue(tcol + (2 * rp + 1) * 64, braw);          // the lower row travels while the upper row is flushed
-        flush_tile(ya * 64 + x0, row0, lsu_a);
+        if (FLAT && cbox != nullptr) {
+          __syncwarp();
+          box_row(ya);
+          __syncwarp();
+        } else {
+          flush_tile(ya * 64 + x0, row0, lsu_a);
+        }
         {
           float b[32];
           {
@@ -328,7 +372,13 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
           const bool pb = gr > 0 && ((unsigned)yb - by) < rdg;
           stage_tile(b, pb, yb, mx, my, c1, c2, den, bx, lsu_b);
           if (FLAT) {                                           // no pooled levels: nothing to exchange, no barrier
-            flush_tile(yb * 64 + x0, row0, lsu_b);
+            if (cbox != nullptr) {
+              __syncwarp();
+              box_row(yb);
+              __syncwarp();
+            } else {
+              flush_tile(yb * 64 + x0, row0, lsu_b);
+            }
             continue;
           }
           // 2x2 average, ATen order: ((a0 + a1) + b0) + b1, then / 4   (corr.py:86)

@@ -75,6 +75,7 @@ struct FusedLookupParams {
   const float* conv_b;         // [128] or null
   void* enc;                   // [E_out,128,P] fp32 (fp16 with HALF); rows follow out_index like `out`
   int conv_relu;
+  const float* boxes0;         // [E,P,16,20] or null: level 0 as COMPACT per-pixel boxes (lgu_build_boxes) instead of a volume
 };
 
 __device__ __forceinline__ float4 flf_lds128(uint32_t addr) {
@@ -214,6 +215,10 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 #pragma unroll
       for (int l = 0; l < LEVELS; ++l) {
         const int o = l == 0 ? kOff0 : (l == 1 ? kOff1 : (l == 2 ? kOff2 : kOff3));
+        if (PC && l == 0 && prm.boxes0 != nullptr) {            // the pixel's box was written in place of its volume slice
+          flf_bulk_g2s(dst + o * 4, prm.boxes0 + (size_t)pix * (kBW01 * kBH01), kBW01 * kBH01 * 4, bar);
+          continue;
+        }
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
                 dst + o * 4),
@@ -270,7 +275,11 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     t.gate = PC ? true : (((unsigned)t.x1 < (unsigned)W2) && ((unsigned)t.y1 < (unsigned)H2));   // Q3 / Q4
     const unsigned rx = (unsigned)t.x1 - (unsigned)xb, ry = (unsigned)t.y1 - (unsigned)yb;
     // box extents from the pitch: 20 x 16 (pitch 80) or 12 x 8 (pitch 48)
-    const bool inbox = rx < (unsigned)((pitch >> 2) - 1) && ry < (unsigned)(pitch == kBW01 * 4 ? kBH01 - 1 : kBH23 - 1);
+    bool inbox = rx < (unsigned)((pitch >> 2) - 1) && ry < (unsigned)(pitch == kBW01 * 4 ? kBH01 - 1 : kBH23 - 1);
+    const bool compact = PC && prm.boxes0 != nullptr && recoff[ps] == 0;          // level 0 held as per-pixel boxes
+    // compact level 0: an offset of exactly 4.0 whose sum with the coordinate rounds up to the next integer puts the tap
+    // on the box's last row with dy == 0 -- the row below then has weight 0 (times a finite value of the next region)
+    if (compact && ry == (unsigned)(kBH01 - 1) && rx < (unsigned)(kBW01 - 1) && t.dy == 0.0f) inbox = true;
     t.miss = t.gate && !inbox;
     const uint32_t ad = baddr + (inbox ? ry * (unsigned)pitch + rx * 4u : 0u);
     t.q11 = flf_lds(ad);
@@ -279,7 +288,19 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     t.q22 = flf_lds(ad + pitch + 4);
     if (__any_sync(0xffffffffu, t.miss)) {                      // |offset| >= 4 or clamped far-out coords: rare
       const int l = recoff[ps] / kRecBytes;
-      tap_patch_from_global<PC>(t, prm.lvl[l] + pix * (size_t)(H2 * W2), H2, W2);
+      if (compact) {
+        // no volume behind the boxes: a corner outside the box is zero if it is outside the image too (what the box
+        // holds for such cells); inside the image it cannot be served -- offsets beyond the documented bound (|o| <= 4)
+        if (t.miss) {
+          const int x2 = wrap_inc(t.x1), y2 = wrap_inc(t.y1);
+          const bool any_in = (((unsigned)t.x1 < (unsigned)W2) || ((unsigned)x2 < (unsigned)W2)) &&
+                              (((unsigned)t.y1 < (unsigned)H2) || ((unsigned)y2 < (unsigned)H2));
+          const float fill = any_in ? __int_as_float(0x7fc00000) : 0.0f;
+          t.q11 = t.q21 = t.q12 = t.q22 = fill;
+        }
+      } else {
+        tap_patch_from_global<PC>(t, prm.lvl[l] + pix * (size_t)(H2 * W2), H2, W2);
+      }
     }
     return tap_value(t);
   };
@@ -483,7 +504,8 @@ static int launch_lookup_fused(const float* lvl0, const float* lvl1, const float
                                const float* coords, const float* off0, float* off1, float* corr, float* mask_out, int E,
                                int H, int W, int num_levels, int radius, int per_corner, int shared_offsets,
                                int apply_mask, const int32_t* slots, int num_slots, float* cum_mask,
-                               const int32_t* out_index, int out_half, void* stream, const ConvArgs* conv = nullptr);
+                               const int32_t* out_index, int out_half, void* stream, const ConvArgs* conv = nullptr,
+                               const float* boxes0 = nullptr);
 
 // W [128, K] (K <= 200) -> the m16n8k8 A fragments the CONV epilogue reads: [8 warps][25 k-steps][32 lanes]{hi(a0..a3), lo(a0..a3)}
 __global__ void pack_conv1x1_kernel(const float* __restrict__ W, float4* __restrict__ frag, int K) {
@@ -565,15 +587,29 @@ extern "C" int lgu_altcorr_lookup_fused_into(const float* lvl0, const float* lvl
                                   H, W, num_levels, radius, 1, shared_offsets, apply_mask, nullptr, E, nullptr, out_index,
                                   out_half, stream);
 }
+// The backend lookup with level 0 held as COMPACT per-pixel boxes (lgu_build_boxes) instead of a volume.
+extern "C" int lgu_altcorr_lookup_boxes_into(const float* boxes0, const float* lvl1, const float* lvl2, const float* lvl3,
+                                             const float* coords, const float* off0, float* off1, void* corr,
+                                             const int32_t* out_index, int out_half, float* mask_out, int E, int H, int W,
+                                             int num_levels, int radius, int shared_offsets, int apply_mask,
+                                             void* stream) {
+  LGU_REQUIRE(E == 0 || boxes0 != nullptr, "lgu_altcorr_lookup_boxes_into: null boxes");
+  return lgu::launch_lookup_fused(nullptr, lvl1, lvl2, lvl3, coords, off0, off1, reinterpret_cast<float*>(corr), mask_out, E,
+                                  H, W, num_levels, radius, 1, shared_offsets, apply_mask, nullptr, E, nullptr, out_index,
+                                  out_half, stream, nullptr, boxes0);
+}
 static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                     const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                     int E, int H, int W, int num_levels, int radius, int per_corner,
                                     int shared_offsets, int apply_mask, const int32_t* slots, int num_slots,
                                     float* cum_mask, const int32_t* out_index, int out_half, void* stream,
-                                    const ConvArgs* conv) {
+                                    const ConvArgs* conv, const float* boxes0) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
+  if (boxes0 != nullptr) lvl0 = lvl1;                       // compact level 0: no volume behind it (the map of level 0 is unused)
   LGU_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && off0 && off1 && (corr || conv), "lgu_corr_lookup_fused: null pointer");
+  LGU_REQUIRE((reinterpret_cast<uintptr_t>(boxes0) & 15) == 0, "lgu_corr_lookup_fused: boxes are not 16-byte aligned");
+  LGU_REQUIRE(boxes0 == nullptr || (per_corner && slots == nullptr), "lgu_corr_lookup_fused: compact boxes serve the backend lookup only");
   LGU_REQUIRE(E > 0 && H > 0 && W > 0, "lgu_corr_lookup_fused: bad sizes E=%d H=%d W=%d", E, H, W);
   if (num_levels != 4 || radius != 3 || (W % 32) != 0 || (H % 8) != 0) {
     set_error("lgu_corr_lookup_fused: only num_levels=4, radius=3, W%%32==0, H%%8==0 are implemented "
@@ -596,10 +632,13 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
     prm.lvl[l] = lv[l];
     prm.H2[l] = H >> l;
     prm.W2[l] = W >> l;
+    if (l == 0 && boxes0 != nullptr) continue;
     const int rc = make_slice_map(&maps.m[l], lv[l], nslices, H >> l, W >> l, l < 2 ? fl::kBW01 : fl::kBW23,
                                   l < 2 ? fl::kBH01 : fl::kBH23);
     if (rc) return rc;
   }
+  if (boxes0 != nullptr) maps.m[0] = maps.m[1];
+  prm.boxes0 = boxes0;
   prm.coords = coords; prm.off0 = off0; prm.off1 = off1; prm.out = corr; prm.mask_out = mask_out;
   prm.cum_mask = cum_mask;
   prm.out_index = out_index;

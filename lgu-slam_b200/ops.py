@@ -659,6 +659,32 @@ def volume_half_mask(coords, level=0):
     return mask
 
 
+def build_boxes(f1_hi, f2_hi, ii, jj, coords, half_mask=None):
+    """Level 0 of the backend path as compact per-pixel boxes (lgu_build_boxes): f1_hi [T1,P,C], f2_hi [T2,P,C] fp16 planes,
+    ii, jj int32 [E], coords [E,H,W,2] (W = 64) -> [E,P,16,20] fp32: for every source pixel the 16 x 20 window of its
+    correlation slice that altcorr_lookup_fused(..., boxes0=) stages around coords, zeros outside the grid."""
+    _chk(coords, "coords", 4)
+    E, H, W, _ = coords.shape
+    for t, name in ((f1_hi, "f1_hi"), (f2_hi, "f2_hi")):
+        if not (t.is_cuda and t.dtype == torch.float16 and t.dim() == 3 and t.is_contiguous()):
+            raise RuntimeError(f"{name} must be a contiguous CUDA fp16 tensor [T,P,C]")
+    T1, P, C = f1_hi.shape
+    T2, Q, C2 = f2_hi.shape
+    if C2 != C or P != H * W or Q != P:
+        raise RuntimeError("build_boxes: level-0 maps [T,H*W,C] expected on both sides")
+    for t, name in ((ii, "ii"), (jj, "jj")):
+        if not (t.is_cuda and t.dtype == torch.int32 and t.dim() == 1 and t.is_contiguous() and t.numel() == E):
+            raise RuntimeError(f"{name} must be a contiguous CUDA int32 vector with one entry per edge")
+    if half_mask is None:
+        half_mask = volume_half_mask(coords, 0)
+    boxes = torch.empty(E, P, 16, 20, dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        st = _lib.lib().lgu_build_boxes(_p(f1_hi), _p(f2_hi), _p(ii), _p(jj), _p(coords), _p(half_mask), _p(boxes), _i(T1),
+                                        _i(T2), _i(E), _i(H), _i(W), _i(C), _stream(coords))
+    _lib.check(st, "build_boxes")
+    return boxes
+
+
 def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj, half_mask=None):
     """volume[e,p,q] = sum_c f1[ii[e],p,c] * f2[jj[e],q,c] on tcgen05 (fp32 accumulate).  f1_* [T1,P,C],
     f2_* [T2,Q,C] contiguous CUDA fp16 planes (lo planes None for single-product precision); ii, jj int32 [E].
@@ -701,14 +727,21 @@ def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj, half_mask=None):
 
 
 def altcorr_lookup_fused(volumes, coords, off0, off1, radius=3, shared_offsets=False, apply_mask=True,
-                         return_mask=False, out=None, out_index=None):
+                         return_mask=False, out=None, out_index=None, boxes0=None):
     """corr_lookup_fused with the backend samplers' semantics (per-corner gating, quirk Q4; lowMem_defSample.cu /
     altcorr_kernel.cu).  volumes: 4 tensors [E,H,W,H>>l,W>>l] from build_volume.  shared_offsets: every edge reads
     offset slab 0 (quirk Q2; off0/off1 then hold >= 1 slab); apply_mask=False: off1 is used as given.
     out: destination [E_out,196,H,W], fp32 or fp16 (rounded to nearest), possibly peer memory of another GPU mapped
-    into this process; out_index int32 [E]: row of `out` that receives edge e (default: e).  Returns `out` then."""
-    E, H, W = volumes[0].shape[:3]
+    into this process; out_index int32 [E]: row of `out` that receives edge e (default: e).  Returns `out` then.
+    boxes0 [E,H*W,16,20] (build_boxes): level 0 as compact per-pixel boxes; volumes[0] is then ignored (may be None)."""
+    E, H, W = volumes[1].shape[:3]
+    if boxes0 is not None:
+        _chk(boxes0, "boxes0", 4)
+        if tuple(boxes0.shape) != (E, H * W, 16, 20):
+            raise RuntimeError(f"boxes0 must be [E,H*W,16,20], got {tuple(boxes0.shape)}")
     for l, t in enumerate(volumes):
+        if l == 0 and boxes0 is not None:
+            continue
         _chk(t, f"volumes[{l}]", 5)
         if tuple(t.shape) != (E, H, W, H >> l, W >> l):
             raise RuntimeError(f"volumes[{l}] shape {tuple(t.shape)} != {(E, H, W, H >> l, W >> l)}")
@@ -729,15 +762,24 @@ def altcorr_lookup_fused(volumes, coords, off0, off1, radius=3, shared_offsets=F
                 raise RuntimeError("out_index must be a contiguous CUDA int32 vector with one row per edge")
         elif out.shape[0] < E:
             raise RuntimeError(f"out has {out.shape[0]} rows, {E} edges")
+        fn = _lib.lib().lgu_altcorr_lookup_boxes_into if boxes0 is not None else _lib.lib().lgu_altcorr_lookup_fused_into
         with torch.cuda.device(coords.device):
-            st = _lib.lib().lgu_altcorr_lookup_fused_into(
-                _p(volumes[0]), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]), _p(coords), _p(off0), _p(off1), _p(out),
+            st = fn(
+                _p(boxes0 if boxes0 is not None else volumes[0]), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]), _p(coords), _p(off0), _p(off1), _p(out),
                 _p(out_index) if out_index is not None else ctypes.c_void_p(0), _i(out.dtype == torch.float16),
                 _p(mask) if return_mask else ctypes.c_void_p(0), _i(E), _i(H), _i(W), _i(4), _i(radius),
                 _i(1 if shared_offsets else 0), _i(1 if apply_mask else 0), _stream(coords))
         _lib.check(st, "altcorr_lookup_fused (into)")
         return (out, mask) if return_mask else out
     corr = torch.empty(E, 196, H, W, dtype=torch.float32, device=coords.device)
+    if boxes0 is not None:
+        with torch.cuda.device(coords.device):
+            st = _lib.lib().lgu_altcorr_lookup_boxes_into(
+                _p(boxes0), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]), _p(coords), _p(off0), _p(off1), _p(corr),
+                ctypes.c_void_p(0), _i(0), _p(mask) if return_mask else ctypes.c_void_p(0), _i(E), _i(H), _i(W), _i(4),
+                _i(radius), _i(1 if shared_offsets else 0), _i(1 if apply_mask else 0), _stream(coords))
+        _lib.check(st, "altcorr_lookup_fused (boxes)")
+        return (corr, mask) if return_mask else corr
     with torch.cuda.device(coords.device):
         st = _lib.lib().lgu_altcorr_lookup_fused(_p(volumes[0]), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]),
                                                  _p(coords), _p(off0), _p(off1), _p(corr),

@@ -510,3 +510,57 @@ def test_sparse_volumes_are_what_the_backend_lookup_reads(probes):
                                    apply_mask=True)
     assert torch.equal(torch.isnan(got), torch.isnan(want))       # (NaN only where a probe coordinate produces one)
     assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
+
+
+@pytest.mark.parametrize("probes", [False, True])
+def test_compact_level0_boxes_give_the_backend_lookup_the_same_bits(probes):
+    """lgu_build_boxes + lgu_altcorr_lookup_boxes_into: level 0 kept as one 16 x 20 box per source pixel (what the fused
+    backend lookup stages anyway) instead of a volume.  The boxes equal the corresponding windows of the dense volume bit
+    for bit (zeros outside the grid) and the lookup returns the same bits, offsets bounded by 4 including the bound itself
+    and coordinates whose sum with 4.0 rounds up to the next integer (tap on the box's last row with dy == 0)."""
+    from lgu_slam_b200 import ops
+    dev, E, H, W, T = "cuda", 5, 48, 64, 4
+    g = inputs.gen(78)
+    fm = (torch.randn(T, 128, H, W, generator=g) / 4).half().to(dev)
+    planes = []
+    cur = fm.float()
+    for l in range(4):
+        planes.append(cur.permute(0, 2, 3, 1).reshape(T, -1, 128).half().contiguous())
+        cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+    ii = torch.tensor([0, 1, 2, 3, 1], dtype=torch.int32, device=dev)
+    jj = torch.tensor([1, 2, 3, 0, 0], dtype=torch.int32, device=dev)
+    coords = inputs.make_coords(E, H, W, H, W, g, probes=probes).permute(0, 2, 3, 1).contiguous().to(dev)
+    coords[1, 5, :, :] = torch.tensor([30.999998, 20.999998])    # + 4.0 rounds up to 35.0 / 25.0 in fp32
+    coords[1, 6, :, :] = torch.tensor([10.9999995, 39.9999962])
+    off = [(4.0 * torch.tanh(3.0 * torch.randn(E, H, W, 98, generator=g))).to(dev).contiguous() for _ in range(2)]
+    off[0][0, 0, :, :] = 4.0
+    off[0][0, 1, :, :] = -4.0
+    off[0][1, 5:7, :, :] = 4.0
+    off[1][1, 0, :, :] = 4.0
+    dense = [ops.build_volume(planes[0], None, planes[l], None, ii, jj).view(E, H, W, H >> l, W >> l) for l in range(4)]
+    poison = torch.full((E, H * W, 16, 20), float("nan"), device=dev)
+    del poison
+    boxes = ops.build_boxes(planes[0], planes[0], ii, jj, coords)
+    assert boxes.shape == (E, H * W, 16, 20)
+    # the boxes against windows of the dense volume
+    c = torch.nan_to_num(coords.reshape(E, H * W, 2), nan=0.0)
+    fx = torch.floor(c[..., 0]).clamp(-64, W + 64).long()
+    fy = torch.floor(c[..., 1]).clamp(-64, H + 64).long()
+    xb = ((fx - 7) >> 2) << 2
+    yb = fy - 7
+    Y = yb[..., None, None] + torch.arange(16, device=dev).view(1, 1, 16, 1)
+    X = xb[..., None, None] + torch.arange(20, device=dev).view(1, 1, 1, 20)
+    ok = (X >= 0) & (X < W) & (Y >= 0) & (Y < H)
+    idx = (Y.clamp(0, H - 1) * W + X.clamp(0, W - 1)).reshape(E, H * W, 320)
+    want_boxes = torch.where(ok.reshape(E, H * W, 320), dense[0].reshape(E, H * W, H * W).gather(2, idx),
+                             torch.zeros((), device=dev)).view(E, H * W, 16, 20)
+    assert torch.equal(boxes, want_boxes)
+    want = ops.altcorr_lookup_fused(dense, coords, off[0], off[1].clone(), 3, shared_offsets=False, apply_mask=True)
+    got = ops.altcorr_lookup_fused([None] + dense[1:], coords, off[0], off[1].clone(), 3, shared_offsets=False,
+                                   apply_mask=True, boxes0=boxes)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
+    out16 = torch.zeros(E, 196, H, W, dtype=torch.float16, device=dev)
+    ops.altcorr_lookup_fused([None] + dense[1:], coords, off[0], off[1].clone(), 3, shared_offsets=False, apply_mask=True,
+                             boxes0=boxes, out=out16)
+    assert torch.equal(torch.nan_to_num(out16.float()), torch.nan_to_num(want.half().float()))
