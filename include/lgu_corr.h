@@ -363,15 +363,17 @@ LGU_API int lgu_build_volume_sparse(const void* fmaps1_hi, const void* fmaps1_lo
  * pixel, the 16 x 20 window of its correlation slice that the fused backend lookup stages around coords [E,H,W,2]
  * (rows box_origin_y = clamp(floor(cy)) - 7 .. + 15, columns (clamp(floor(cx)) - 7) & ~3 .. + 19; zeros outside the H x W
  * grid) -- 1280 B per pixel instead of 12 KB (7.6 KB with the half mask), and one contiguous read per pixel for the lookup
- * instead of 16 strided rows.  fp16-valued maps (one product, fp32 accumulate), W = 64, C = 128; half_mask from
- * lgu_volume_half_mask(coords, level 0).  lgu_altcorr_lookup_boxes_into = lgu_altcorr_lookup_fused_into with `boxes0` in
- * place of the level-0 volume; offsets must be bounded by 4 (4 * tanh, corr.py:121-128): a tap whose footprint leaves the
+ * instead of 16 strided rows.  fp16-valued maps (one product, fp32 accumulate), C = 128; level 0 (W = 64) or level 1
+ * (fmaps2 = the level-1 pooled maps, W = 64 so that W >> 1 = 32; coords stay in level-0 units and are halved like the lookup
+ * does); half_mask from lgu_volume_half_mask(coords, level).  lgu_altcorr_lookup_boxes_into =
+ * lgu_altcorr_lookup_fused_into with `boxes0` in place of the level-0 volume and, if not NULL, `boxes1` in place of lvl1
+ * (which may then be NULL); offsets must be bounded by 4 (4 * tanh, corr.py:121-128): a tap whose footprint leaves the
  * box inside the grid returns NaN. */
 LGU_API int lgu_build_boxes(const void* fmaps1_hi, const void* fmaps2_hi, const int32_t* ii, const int32_t* jj,
                                    const float* coords, const uint32_t* half_mask, float* boxes,
-                                   int T1, int T2, int E, int H, int W, int C, void* stream);
-LGU_API int lgu_altcorr_lookup_boxes_into(const float* boxes0, const float* lvl1, const float* lvl2, const float* lvl3,
-                                   const float* coords, const float* off0, float* off1, void* corr,
+                                   int T1, int T2, int E, int H, int W, int C, int level, void* stream);
+LGU_API int lgu_altcorr_lookup_boxes_into(const float* boxes0, const float* boxes1, const float* lvl1, const float* lvl2,
+                                   const float* lvl3, const float* coords, const float* off0, float* off1, void* corr,
                                    const int32_t* out_index, int out_half, float* mask_out,
                                    int E, int H, int W, int num_levels, int radius,
                                    int shared_offsets, int apply_mask, void* stream);

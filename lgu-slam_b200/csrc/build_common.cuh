@@ -29,6 +29,7 @@ struct BpParams {
   int Q;        // target pixels per map (== P for the pyramid build; any multiple of 4 in flat volume mode)
   int halves;   // 256-column accumulator halves per unit: ceil(Q / 256)
   const uint32_t* half_mask;   // [num_units] or null: bit h set = accumulator half h (256 target columns) of the unit is built
+  int box_W, box_level;       // compact mode: columns of the target grid (64 or 32) and the level the coords are halved to
   float* boxes;               // FLAT 16-warp kernel: [E,P,16,20] or null -- write each source pixel's lookup box (rows
   const float* box_coords;    //   box_origin_y(floor(cy),7,H) .. +15, cols box_origin_x(floor(cx),7,64) .. +19 around box_coords [E,P,2],
                               //   zeros outside the target grid) INSTEAD of the volume rows (lgu_build_boxes)

@@ -699,7 +699,7 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
   prm.has_l1 = lvl1 != nullptr;
   prm.dbg = getenv("LGU_BUILD_DBG") ? atoi(getenv("LGU_BUILD_DBG")) : 0;
   prm.half_mask = nullptr;
-  prm.boxes = nullptr; prm.box_coords = nullptr;
+  prm.boxes = nullptr; prm.box_coords = nullptr; prm.box_W = 64; prm.box_level = 0;
   // level-0 rows of the 16-warp kernel through the LSU (default, 537 -> 505 us at E = 48); LGU_BUILD_L0_TMA=1: TMA stores
   prm.l0_lsu = env_flag("LGU_BUILD_L0_TMA") ? 0 : 3;
   prm.out_slots = out_slots;
@@ -715,7 +715,7 @@ static int build_pyramid_impl(const void* fmaps_hi, const void* fmaps_lo, const 
 static int build_volume_impl(const void* fmaps1_hi, const void* fmaps1_lo, const void* fmaps2_hi,
                              const void* fmaps2_lo, const int32_t* ii, const int32_t* jj, float* volume, int T1,
                              int T2, int E, int P, int Q, int C, int precision, const uint32_t* half_mask, void* stream,
-                             float* boxes = nullptr, const float* box_coords = nullptr) {
+                             float* boxes = nullptr, const float* box_coords = nullptr, int box_W = 64, int box_level = 0) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(fmaps1_hi && fmaps2_hi && ii && jj && (volume || boxes), "lgu_build_volume: null pointer");
@@ -761,7 +761,8 @@ static int build_volume_impl(const void* fmaps1_hi, const void* fmaps1_lo, const
   prm.dbg = 0;
   prm.l0_lsu = 0;
   prm.half_mask = half_mask;
-  prm.boxes = boxes; prm.box_coords = box_coords; prm.H = boxes != nullptr ? Q / 64 : 0;
+  prm.boxes = boxes; prm.box_coords = box_coords; prm.box_W = box_W; prm.box_level = box_level;
+  prm.H = boxes != nullptr ? Q / box_W : 0;
   prm.out_slots = nullptr;
   prm.Q = Q;
   prm.halves = (Q + 255) / 256;
@@ -796,17 +797,20 @@ extern "C" int lgu_build_volume_sparse(const void* fmaps1_hi, const void* fmaps1
 // slice.  Same MMAs and the same half mask as lgu_build_volume_sparse; fp16-valued maps, W = 64.
 extern "C" int lgu_build_boxes(const void* fmaps1_hi, const void* fmaps2_hi, const int32_t* ii, const int32_t* jj,
                                const float* coords, const uint32_t* half_mask, float* boxes, int T1, int T2, int E, int H,
-                               int W, int C, void* stream) {
+                               int W, int C, int level, void* stream) {
   if (E == 0) return LGU_OK;
   LGU_REQUIRE(coords && half_mask && boxes, "lgu_build_boxes: null pointer");
   LGU_REQUIRE(((reinterpret_cast<uintptr_t>(boxes) & 15) | (reinterpret_cast<uintptr_t>(coords) & 7)) == 0,
               "lgu_build_boxes: boxes must be 16-byte, coords 8-byte aligned");
-  if (W != 64 || H <= 0 || (H % 4) != 0 || H * W > 32 * 256) {
-    lgu::set_error("lgu_build_boxes: needs W = 64 and H %% 4 == 0 with at most 32 halves (got H=%d W=%d)", H, W);
+  const int H2 = H >> level, W2 = W >> level;
+  if (level < 0 || level > 1 || (W2 != 64 && W2 != 32) || H2 <= 0 || (H2 * W2) % 256 != 0 || H2 * W2 > 32 * 256 ||
+      (H % (2 << level)) != 0) {
+    lgu::set_error("lgu_build_boxes: needs level 0 or 1, W >> level in {64, 32} and whole halves (got H=%d W=%d level=%d)",
+                   H, W, level);
     return LGU_ERR_UNSUPPORTED;
   }
-  return build_volume_impl(fmaps1_hi, nullptr, fmaps2_hi, nullptr, ii, jj, nullptr, T1, T2, E, H * W, H * W, C, 1, half_mask,
-                           stream, boxes, coords);
+  return build_volume_impl(fmaps1_hi, nullptr, fmaps2_hi, nullptr, ii, jj, nullptr, T1, T2, E, H * W, H2 * W2, C, 1, half_mask,
+                           stream, boxes, coords, W2, level);
 }
 
 namespace lgu {

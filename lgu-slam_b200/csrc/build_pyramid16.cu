@@ -278,8 +278,10 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
       float* cbox = nullptr;
       if (FLAT && prm.boxes != nullptr) {
         const float2 cc = __ldg(reinterpret_cast<const float2*>(prm.box_coords) + pix);
-        cbx = box_origin_x(floor_to_int(cc.x), 7, 64);
-        cby = box_origin_y(floor_to_int(cc.y), 7, prm.H);
+        float cx = cc.x, cy = cc.y;
+        for (int l = 0; l < prm.box_level; ++l) { cx = __fmul_rn(cx, 0.5f); cy = __fmul_rn(cy, 0.5f); }   // the lookup's halving
+        cbx = box_origin_x(floor_to_int(cx), 7, prm.box_W);
+        cby = box_origin_y(floor_to_int(cy), 7, prm.H);
         cbox = prm.boxes + pix * (size_t)(fl::kBW01 * fl::kBH01);
         if (sub == 0) {                                         // box rows outside the grid: no half produces them
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -290,21 +292,23 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
             }
         }
       }
-      // one staged row of this warp (target row yy, its 32 columns) -> this lane's box row: the 16-byte chunks of the box that
-      // fall into this warp's column half come from the lane's OWN staged row (no transposition), chunks left / right of the
-      // grid are zeros (the xs = 0 / xs = 1 warp writes them)
-      auto box_row = [&](int yy) {
+      // one staged row of this warp (32 consecutive targets q0 .. q0 + 31 = target row q0 / W, columns q0 % W ..) -> this
+      // lane's box row: the 16-byte chunks of the box that fall into these columns come from the lane's OWN staged row (no
+      // transposition); chunks left / right of the grid are zeros (written by the first / last column block of the row)
+      auto box_row = [&](int q0) {
+        const int bw = prm.box_W;
+        const int yy = q0 / bw, blk = (q0 - yy * bw) >> 5, nblk = bw >> 5;
         const int r = yy - cby;
         if ((unsigned)r < (unsigned)fl::kBH01) {
           const float4* rowp = reinterpret_cast<const float4*>(my_store + lane * 128);
           float* dst = cbox + r * fl::kBW01;
 #pragma unroll
           for (int j = 0; j < fl::kBW01 / 4; ++j) {
-            const int cg = (cbx >> 2) + j;                      // chunk of the 64-column target row (cbx % 4 == 0)
-            const bool mine = xs == 0 ? cg < 8 : cg >= 8;
+            const int cg = (cbx >> 2) + j;                      // chunk of the target row (cbx % 4 == 0)
+            const bool mine = (blk == 0 || cg >= 8 * blk) && (blk == nblk - 1 || cg < 8 * (blk + 1));
             if (mine) {
               float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if ((unsigned)cg < 16u) v4 = rowp[(cg - 8 * xs) ^ rsw];
+              if ((unsigned)cg < (unsigned)(bw >> 2)) v4 = rowp[(cg - 8 * blk) ^ rsw];
               *reinterpret_cast<float4*>(dst + 4 * j) = v4;
             }
           }
@@ -348,7 +352,7 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         tmem_ld32_issue(tcol + (2 * rp + 1) * 64, braw);          // the lower row travels while the upper row is flushed
         if (FLAT && cbox != nullptr) {
           __syncwarp();
-          box_row(ya);
+          box_row(ya * 64 + x0);
           __syncwarp();
         } else {
           flush_tile(ya * 64 + x0, row0, lsu_a);
@@ -374,7 +378,7 @@ build_pyramid16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
           if (FLAT) {                                           // no pooled levels: nothing to exchange, no barrier
             if (cbox != nullptr) {
               __syncwarp();
-              box_row(yb);
+              box_row(yb * 64 + x0);
               __syncwarp();
             } else {
               flush_tile(yb * 64 + x0, row0, lsu_b);

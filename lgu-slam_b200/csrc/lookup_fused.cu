@@ -76,6 +76,7 @@ struct FusedLookupParams {
   void* enc;                   // [E_out,128,P] fp32 (fp16 with HALF); rows follow out_index like `out`
   int conv_relu;
   const float* boxes0;         // [E,P,16,20] or null: level 0 as COMPACT per-pixel boxes (lgu_build_boxes) instead of a volume
+  const float* boxes1;         // the same for level 1
 };
 
 __device__ __forceinline__ float4 flf_lds128(uint32_t addr) {
@@ -215,8 +216,8 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
 #pragma unroll
       for (int l = 0; l < LEVELS; ++l) {
         const int o = l == 0 ? kOff0 : (l == 1 ? kOff1 : (l == 2 ? kOff2 : kOff3));
-        if (PC && l == 0 && prm.boxes0 != nullptr) {            // the pixel's box was written in place of its volume slice
-          flf_bulk_g2s(dst + o * 4, prm.boxes0 + (size_t)pix * (kBW01 * kBH01), kBW01 * kBH01 * 4, bar);
+        if (PC && l < 2 && (l == 0 ? prm.boxes0 : prm.boxes1) != nullptr) {   // the pixel's box was written in place of its slice
+          flf_bulk_g2s(dst + o * 4, (l == 0 ? prm.boxes0 : prm.boxes1) + (size_t)pix * (kBW01 * kBH01), kBW01 * kBH01 * 4, bar);
           continue;
         }
         asm volatile(
@@ -276,7 +277,8 @@ lookup_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedLookupPar
     const unsigned rx = (unsigned)t.x1 - (unsigned)xb, ry = (unsigned)t.y1 - (unsigned)yb;
     // box extents from the pitch: 20 x 16 (pitch 80) or 12 x 8 (pitch 48)
     bool inbox = rx < (unsigned)((pitch >> 2) - 1) && ry < (unsigned)(pitch == kBW01 * 4 ? kBH01 - 1 : kBH23 - 1);
-    const bool compact = PC && prm.boxes0 != nullptr && recoff[ps] == 0;          // level 0 held as per-pixel boxes
+    const bool compact = PC && ((prm.boxes0 != nullptr && recoff[ps] == 0) ||      // level 0 / 1 held as per-pixel boxes
+                                (prm.boxes1 != nullptr && recoff[ps] == kRecBytes));
     // compact level 0: an offset of exactly 4.0 whose sum with the coordinate rounds up to the next integer puts the tap
     // on the box's last row with dy == 0 -- the row below then has weight 0 (times a finite value of the next region)
     if (compact && ry == (unsigned)(kBH01 - 1) && rx < (unsigned)(kBW01 - 1) && t.dy == 0.0f) inbox = true;
@@ -505,7 +507,7 @@ static int launch_lookup_fused(const float* lvl0, const float* lvl1, const float
                                int H, int W, int num_levels, int radius, int per_corner, int shared_offsets,
                                int apply_mask, const int32_t* slots, int num_slots, float* cum_mask,
                                const int32_t* out_index, int out_half, void* stream, const ConvArgs* conv = nullptr,
-                               const float* boxes0 = nullptr);
+                               const float* boxes0 = nullptr, const float* boxes1 = nullptr);
 
 // W [128, K] (K <= 200) -> the m16n8k8 A fragments the CONV epilogue reads: [8 warps][25 k-steps][32 lanes]{hi(a0..a3), lo(a0..a3)}
 __global__ void pack_conv1x1_kernel(const float* __restrict__ W, float4* __restrict__ frag, int K) {
@@ -588,25 +590,29 @@ extern "C" int lgu_altcorr_lookup_fused_into(const float* lvl0, const float* lvl
                                   out_half, stream);
 }
 // The backend lookup with level 0 held as COMPACT per-pixel boxes (lgu_build_boxes) instead of a volume.
-extern "C" int lgu_altcorr_lookup_boxes_into(const float* boxes0, const float* lvl1, const float* lvl2, const float* lvl3,
-                                             const float* coords, const float* off0, float* off1, void* corr,
-                                             const int32_t* out_index, int out_half, float* mask_out, int E, int H, int W,
-                                             int num_levels, int radius, int shared_offsets, int apply_mask,
+extern "C" int lgu_altcorr_lookup_boxes_into(const float* boxes0, const float* boxes1, const float* lvl1, const float* lvl2,
+                                             const float* lvl3, const float* coords, const float* off0, float* off1,
+                                             void* corr, const int32_t* out_index, int out_half, float* mask_out, int E,
+                                             int H, int W, int num_levels, int radius, int shared_offsets, int apply_mask,
                                              void* stream) {
   LGU_REQUIRE(E == 0 || boxes0 != nullptr, "lgu_altcorr_lookup_boxes_into: null boxes");
+  LGU_REQUIRE(E == 0 || boxes1 != nullptr || lvl1 != nullptr, "lgu_altcorr_lookup_boxes_into: level 1 needs boxes or a volume");
   return lgu::launch_lookup_fused(nullptr, lvl1, lvl2, lvl3, coords, off0, off1, reinterpret_cast<float*>(corr), mask_out, E,
                                   H, W, num_levels, radius, 1, shared_offsets, apply_mask, nullptr, E, nullptr, out_index,
-                                  out_half, stream, nullptr, boxes0);
+                                  out_half, stream, nullptr, boxes0, boxes1);
 }
 static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const float* lvl2, const float* lvl3,
                                     const float* coords, const float* off0, float* off1, float* corr, float* mask_out,
                                     int E, int H, int W, int num_levels, int radius, int per_corner,
                                     int shared_offsets, int apply_mask, const int32_t* slots, int num_slots,
                                     float* cum_mask, const int32_t* out_index, int out_half, void* stream,
-                                    const ConvArgs* conv, const float* boxes0) {
+                                    const ConvArgs* conv, const float* boxes0, const float* boxes1) {
   using namespace lgu;
   if (E == 0) return LGU_OK;
-  if (boxes0 != nullptr) lvl0 = lvl1;                       // compact level 0: no volume behind it (the map of level 0 is unused)
+  if (boxes1 != nullptr && lvl1 == nullptr) lvl1 = lvl2;    // compact levels: no volume behind them (their maps are unused)
+  if (boxes0 != nullptr) lvl0 = lvl1;
+  LGU_REQUIRE(boxes1 == nullptr || boxes0 != nullptr, "lgu_corr_lookup_fused: compact level 1 needs compact level 0");
+  LGU_REQUIRE((reinterpret_cast<uintptr_t>(boxes1) & 15) == 0, "lgu_corr_lookup_fused: boxes are not 16-byte aligned");
   LGU_REQUIRE(lvl0 && lvl1 && lvl2 && lvl3 && coords && off0 && off1 && (corr || conv), "lgu_corr_lookup_fused: null pointer");
   LGU_REQUIRE((reinterpret_cast<uintptr_t>(boxes0) & 15) == 0, "lgu_corr_lookup_fused: boxes are not 16-byte aligned");
   LGU_REQUIRE(boxes0 == nullptr || (per_corner && slots == nullptr), "lgu_corr_lookup_fused: compact boxes serve the backend lookup only");
@@ -632,13 +638,15 @@ static int lgu::launch_lookup_fused(const float* lvl0, const float* lvl1, const 
     prm.lvl[l] = lv[l];
     prm.H2[l] = H >> l;
     prm.W2[l] = W >> l;
-    if (l == 0 && boxes0 != nullptr) continue;
+    if ((l == 0 && boxes0 != nullptr) || (l == 1 && boxes1 != nullptr)) continue;
     const int rc = make_slice_map(&maps.m[l], lv[l], nslices, H >> l, W >> l, l < 2 ? fl::kBW01 : fl::kBW23,
                                   l < 2 ? fl::kBH01 : fl::kBH23);
     if (rc) return rc;
   }
+  if (boxes1 != nullptr) maps.m[1] = maps.m[2];
   if (boxes0 != nullptr) maps.m[0] = maps.m[1];
   prm.boxes0 = boxes0;
+  prm.boxes1 = boxes1;
   prm.coords = coords; prm.off0 = off0; prm.off1 = off1; prm.out = corr; prm.mask_out = mask_out;
   prm.cum_mask = cum_mask;
   prm.out_index = out_index;

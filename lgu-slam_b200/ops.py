@@ -659,10 +659,11 @@ def volume_half_mask(coords, level=0):
     return mask
 
 
-def build_boxes(f1_hi, f2_hi, ii, jj, coords, half_mask=None):
+def build_boxes(f1_hi, f2_hi, ii, jj, coords, half_mask=None, level=0):
     """Level 0 of the backend path as compact per-pixel boxes (lgu_build_boxes): f1_hi [T1,P,C], f2_hi [T2,P,C] fp16 planes,
     ii, jj int32 [E], coords [E,H,W,2] (W = 64) -> [E,P,16,20] fp32: for every source pixel the 16 x 20 window of its
-    correlation slice that altcorr_lookup_fused(..., boxes0=) stages around coords, zeros outside the grid."""
+    correlation slice that altcorr_lookup_fused(..., boxes0=) stages around coords, zeros outside the grid.
+    level = 1: f2_hi holds the level-1 pooled maps [T2,P/4,C]; the result goes to altcorr_lookup_fused(..., boxes1=)."""
     _chk(coords, "coords", 4)
     E, H, W, _ = coords.shape
     for t, name in ((f1_hi, "f1_hi"), (f2_hi, "f2_hi")):
@@ -670,17 +671,17 @@ def build_boxes(f1_hi, f2_hi, ii, jj, coords, half_mask=None):
             raise RuntimeError(f"{name} must be a contiguous CUDA fp16 tensor [T,P,C]")
     T1, P, C = f1_hi.shape
     T2, Q, C2 = f2_hi.shape
-    if C2 != C or P != H * W or Q != P:
-        raise RuntimeError("build_boxes: level-0 maps [T,H*W,C] expected on both sides")
+    if C2 != C or P != H * W or Q != (H >> level) * (W >> level) or level not in (0, 1):
+        raise RuntimeError("build_boxes: f1 [T,H*W,C] and f2 [T,(H>>level)*(W>>level),C] expected, level 0 or 1")
     for t, name in ((ii, "ii"), (jj, "jj")):
         if not (t.is_cuda and t.dtype == torch.int32 and t.dim() == 1 and t.is_contiguous() and t.numel() == E):
             raise RuntimeError(f"{name} must be a contiguous CUDA int32 vector with one entry per edge")
     if half_mask is None:
-        half_mask = volume_half_mask(coords, 0)
+        half_mask = volume_half_mask(coords, level)
     boxes = torch.empty(E, P, 16, 20, dtype=torch.float32, device=coords.device)
     with torch.cuda.device(coords.device):
         st = _lib.lib().lgu_build_boxes(_p(f1_hi), _p(f2_hi), _p(ii), _p(jj), _p(coords), _p(half_mask), _p(boxes), _i(T1),
-                                        _i(T2), _i(E), _i(H), _i(W), _i(C), _stream(coords))
+                                        _i(T2), _i(E), _i(H), _i(W), _i(C), _i(level), _stream(coords))
     _lib.check(st, "build_boxes")
     return boxes
 
@@ -727,20 +728,24 @@ def build_volume(f1_hi, f1_lo, f2_hi, f2_lo, ii, jj, half_mask=None):
 
 
 def altcorr_lookup_fused(volumes, coords, off0, off1, radius=3, shared_offsets=False, apply_mask=True,
-                         return_mask=False, out=None, out_index=None, boxes0=None):
+                         return_mask=False, out=None, out_index=None, boxes0=None, boxes1=None):
     """corr_lookup_fused with the backend samplers' semantics (per-corner gating, quirk Q4; lowMem_defSample.cu /
     altcorr_kernel.cu).  volumes: 4 tensors [E,H,W,H>>l,W>>l] from build_volume.  shared_offsets: every edge reads
     offset slab 0 (quirk Q2; off0/off1 then hold >= 1 slab); apply_mask=False: off1 is used as given.
     out: destination [E_out,196,H,W], fp32 or fp16 (rounded to nearest), possibly peer memory of another GPU mapped
     into this process; out_index int32 [E]: row of `out` that receives edge e (default: e).  Returns `out` then.
-    boxes0 [E,H*W,16,20] (build_boxes): level 0 as compact per-pixel boxes; volumes[0] is then ignored (may be None)."""
-    E, H, W = volumes[1].shape[:3]
-    if boxes0 is not None:
-        _chk(boxes0, "boxes0", 4)
-        if tuple(boxes0.shape) != (E, H * W, 16, 20):
-            raise RuntimeError(f"boxes0 must be [E,H*W,16,20], got {tuple(boxes0.shape)}")
+    boxes0 [E,H*W,16,20] (build_boxes): level 0 as compact per-pixel boxes; volumes[0] is then ignored (may be None);
+    boxes1: the same for level 1 (needs boxes0)."""
+    E, H, W = volumes[2].shape[:3]
+    if boxes1 is not None and boxes0 is None:
+        raise RuntimeError("boxes1 needs boxes0")
+    for name, bx in (("boxes0", boxes0), ("boxes1", boxes1)):
+        if bx is not None:
+            _chk(bx, name, 4)
+            if tuple(bx.shape) != (E, H * W, 16, 20):
+                raise RuntimeError(f"{name} must be [E,H*W,16,20], got {tuple(bx.shape)}")
     for l, t in enumerate(volumes):
-        if l == 0 and boxes0 is not None:
+        if (l == 0 and boxes0 is not None) or (l == 1 and boxes1 is not None):
             continue
         _chk(t, f"volumes[{l}]", 5)
         if tuple(t.shape) != (E, H, W, H >> l, W >> l):
@@ -762,10 +767,16 @@ def altcorr_lookup_fused(volumes, coords, off0, off1, radius=3, shared_offsets=F
                 raise RuntimeError("out_index must be a contiguous CUDA int32 vector with one row per edge")
         elif out.shape[0] < E:
             raise RuntimeError(f"out has {out.shape[0]} rows, {E} edges")
-        fn = _lib.lib().lgu_altcorr_lookup_boxes_into if boxes0 is not None else _lib.lib().lgu_altcorr_lookup_fused_into
+        null = ctypes.c_void_p(0)
+        if boxes0 is not None:
+            head = (_p(boxes0), _p(boxes1) if boxes1 is not None else null, _p(volumes[1]) if boxes1 is None else null)
+            fn = _lib.lib().lgu_altcorr_lookup_boxes_into
+        else:
+            head = (_p(volumes[0]), _p(volumes[1]))
+            fn = _lib.lib().lgu_altcorr_lookup_fused_into
         with torch.cuda.device(coords.device):
             st = fn(
-                _p(boxes0 if boxes0 is not None else volumes[0]), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]), _p(coords), _p(off0), _p(off1), _p(out),
+                *head, _p(volumes[2]), _p(volumes[3]), _p(coords), _p(off0), _p(off1), _p(out),
                 _p(out_index) if out_index is not None else ctypes.c_void_p(0), _i(out.dtype == torch.float16),
                 _p(mask) if return_mask else ctypes.c_void_p(0), _i(E), _i(H), _i(W), _i(4), _i(radius),
                 _i(1 if shared_offsets else 0), _i(1 if apply_mask else 0), _stream(coords))
@@ -774,8 +785,10 @@ def altcorr_lookup_fused(volumes, coords, off0, off1, radius=3, shared_offsets=F
     corr = torch.empty(E, 196, H, W, dtype=torch.float32, device=coords.device)
     if boxes0 is not None:
         with torch.cuda.device(coords.device):
+            null = ctypes.c_void_p(0)
             st = _lib.lib().lgu_altcorr_lookup_boxes_into(
-                _p(boxes0), _p(volumes[1]), _p(volumes[2]), _p(volumes[3]), _p(coords), _p(off0), _p(off1), _p(corr),
+                _p(boxes0), _p(boxes1) if boxes1 is not None else null, _p(volumes[1]) if boxes1 is None else null,
+                _p(volumes[2]), _p(volumes[3]), _p(coords), _p(off0), _p(off1), _p(corr),
                 ctypes.c_void_p(0), _i(0), _p(mask) if return_mask else ctypes.c_void_p(0), _i(E), _i(H), _i(W), _i(4),
                 _i(radius), _i(1 if shared_offsets else 0), _i(1 if apply_mask else 0), _stream(coords))
         _lib.check(st, "altcorr_lookup_fused (boxes)")

@@ -560,6 +560,24 @@ def test_compact_level0_boxes_give_the_backend_lookup_the_same_bits(probes):
                                    apply_mask=True, boxes0=boxes)
     assert torch.equal(torch.isnan(got), torch.isnan(want))
     assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want))
+    # level 1 as boxes too
+    poison = torch.full((E, H * W, 16, 20), float("nan"), device=dev)
+    del poison
+    boxes1 = ops.build_boxes(planes[0], planes[1], ii, jj, coords, level=1)
+    c1 = torch.nan_to_num(coords.reshape(E, H * W, 2), nan=0.0) * 0.5
+    fx1 = torch.floor(c1[..., 0]).clamp(-64, W // 2 + 64).long()
+    fy1 = torch.floor(c1[..., 1]).clamp(-64, H // 2 + 64).long()
+    X1 = (((fx1 - 7) >> 2) << 2)[..., None, None] + torch.arange(20, device=dev).view(1, 1, 1, 20)
+    Y1 = (fy1 - 7)[..., None, None] + torch.arange(16, device=dev).view(1, 1, 16, 1)
+    ok1 = (X1 >= 0) & (X1 < W // 2) & (Y1 >= 0) & (Y1 < H // 2)
+    idx1 = (Y1.clamp(0, H // 2 - 1) * (W // 2) + X1.clamp(0, W // 2 - 1)).reshape(E, H * W, 320)
+    want1 = torch.where(ok1.reshape(E, H * W, 320), dense[1].reshape(E, H * W, H * W // 4).gather(2, idx1),
+                        torch.zeros((), device=dev)).view(E, H * W, 16, 20)
+    assert torch.equal(boxes1, want1)
+    got2 = ops.altcorr_lookup_fused([None, None] + dense[2:], coords, off[0], off[1].clone(), 3, shared_offsets=False,
+                                    apply_mask=True, boxes0=boxes, boxes1=boxes1)
+    assert torch.equal(torch.isnan(got2), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(got2), torch.nan_to_num(want))
     out16 = torch.zeros(E, 196, H, W, dtype=torch.float16, device=dev)
     ops.altcorr_lookup_fused([None] + dense[1:], coords, off[0], off[1].clone(), 3, shared_offsets=False, apply_mask=True,
                              boxes0=boxes, out=out16)
